@@ -1,0 +1,206 @@
+/*
+ * mlamg.h — C ABI of the B200-native aggregation-AMG hot path (libmlamg_b200.so).
+ *
+ * Drop-in boundary for nicknytko/ml-amg.  The reference is pure Python and has no
+ * FFI of its own; each entry point below names the reference
+ * expression (file:line under /root/reference) whose third-party CPU kernel
+ * (scipy sparsetools / pyamg amg_core / SuperLU) it replaces.  The Python layer
+ * in ml-amg_b200/ns mirrors the reference signatures and binds these with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - index arrays are int32 (what scipy produces), values are f32 or f64
+ *     selected by `dtype`; CSR = (rowptr[n+1], col[nnz], val[nnz]);
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*); calls
+ *     that return a size/flag to the host synchronise that stream once;
+ *   - return value: 0 = OK, otherwise an MLAMG_E* code, text via
+ *     mlamg_last_error();
+ *   - the caller owns every buffer; handles are opaque and freed by *_destroy;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with MLAMG_ECUDA.
+ */
+#ifndef MLAMG_H
+#define MLAMG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *mlamg_stream_t;
+
+enum { MLAMG_F32 = 0, MLAMG_F64 = 1 };
+enum {
+    MLAMG_OK = 0,
+    MLAMG_EINVAL = 1,    /* bad argument */
+    MLAMG_ECUDA = 2,     /* CUDA runtime error */
+    MLAMG_ELIMIT = 3,    /* size beyond an implementation limit */
+    MLAMG_ESINGULAR = 4, /* singular coarse operator (multigrid.py:166-170 returns conv=1.0) */
+    MLAMG_EKEY = 5       /* label is not a centre (graph.py:83 KeyError) */
+};
+
+const char *mlamg_last_error(void);
+int mlamg_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long mlamg_launch_count(void);
+
+/* ------------------------------------------------------------------ V-cycle apply kernels */
+
+/* y = A x.              multigrid.py:44,181,191  MLAMG.py:145,191,194 (scipy csr_matvec) */
+int mlamg_spmv_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                   const void *x, void *y, mlamg_stream_t stream);
+/* y += A x.             prolongation x += P e_c: multigrid.py:181, MLAMG.py:191 */
+int mlamg_spmv_add_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                       const void *x, void *y, mlamg_stream_t stream);
+/* r = b - A x; if norm2 != NULL also *norm2 (device double) = ||r||_2^2 (deterministic).
+ *                       multigrid.py:181,191  MLAMG.py:191,194 */
+int mlamg_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                       const void *x, const void *b, void *r, double *norm2, mlamg_stream_t stream);
+/* x_out = x_in + dw .* (b - A x_in), x_out != x_in.  One fused pass over A.
+ * dw = omega/diag (weighted Jacobi, MLAMG.py:104,143-146; multigrid.py:15-55; loss.py:72,88)
+ * or 1/sum_j|a_ij| (L1-Jacobi, north-star addition). */
+int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                     const void *dw, const void *b, const void *x_in, void *x_out,
+                     mlamg_stream_t stream);
+/* x = dw .* b  (first sweep from a zero guess: no pass over A) */
+int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream);
+/* smoother diagonal: mode 0 -> omega / a_ii, mode 1 -> 1 / sum_j |a_ij| (omega ignored) */
+int mlamg_smoother_diag(int dtype, int mode, double omega, int n, const int *rowptr, const int *col,
+                        const void *val, void *dw, mlamg_stream_t stream);
+/* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
+int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *val,
+                   const void *X, void *Y, double alpha, double beta, mlamg_stream_t stream);
+
+/* small BLAS-1 helpers used by the cycle / PCG drivers (deterministic reductions) */
+int mlamg_axpby(int dtype, int n, double alpha, const void *x, double beta, void *y, mlamg_stream_t stream);
+int mlamg_dot(int dtype, int n, const void *x, const void *y, double *result, mlamg_stream_t stream);
+
+/* exact forward Gauss-Seidel sweep (pyamg gauss_seidel, multigrid.py:175,184), level-scheduled.
+ * mlamg_gs_schedule: level[i] = dependency depth of row i; order = rows sorted by (level,row);
+ * level_ptr_host[nlevels+1] offsets into order.  Caller passes level_ptr_host capacity n+1. */
+int mlamg_gs_schedule(int n, const int *rowptr, const int *col, int *level, int *order,
+                      int *level_ptr_host, int *nlevels_host, mlamg_stream_t stream);
+int mlamg_gauss_seidel(int dtype, int n, const int *rowptr, const int *col, const void *val,
+                       const void *b, void *x, const int *order, const int *level_ptr_host,
+                       int nlevels, mlamg_stream_t stream);
+
+/* ------------------------------------------------------------------ hierarchy setup kernels */
+
+/* out[0..n] = exclusive prefix sum of in[0..n-1] (out[n] = total).  in may alias out. */
+int mlamg_scan_i32(const int *in, int *out, int n, mlamg_stream_t stream);
+
+/* labels -> Agg CSR (graph.py:234-238): one unit entry per row with label >= 0.
+ * col/val capacity n.  *nnz_host = number of labelled rows. */
+int mlamg_agg_from_labels(int dtype, int n, const int *labels, int *rowptr, int *col, void *val,
+                          int *nnz_host, mlamg_stream_t stream);
+/* nearest centre NODE ID -> column rank (graph.py:76-84).  scratch_map: int[n].
+ * MLAMG_EKEY if some nearest[i] is not a centre (reference raises KeyError). */
+int mlamg_center_rank_labels(int n, int k, const int *centers, const int *nearest, int *scratch_map,
+                             int *labels, mlamg_stream_t stream);
+/* S = I - omega D^-1 A on A's pattern (multigrid.py:104-106); A must store its diagonal */
+int mlamg_sa_smoother_values(int dtype, int n, const int *rowptr, const int *col, const void *val,
+                             double omega, void *sval, mlamg_stream_t stream);
+
+/* C = A(m x k) * B(k x n), two-phase hash SpGEMM (scipy csr_matmat at multigrid.py:107,165;
+ * torch.sparse.mm at agg_interp.py:484; torch_sparse.spspmm at loss.py:54).
+ * symbolic: fills c_rowptr[m+1], *nnz_host.  numeric: fills c_col (sorted per row), c_val. */
+int mlamg_spgemm_symbolic(int m, int k, int n, const int *a_rowptr, const int *a_col,
+                          const int *b_rowptr, const int *b_col, int *c_rowptr, long long *nnz_host,
+                          mlamg_stream_t stream);
+int mlamg_spgemm_numeric(int dtype, int m, int k, int n, const int *a_rowptr, const int *a_col,
+                         const void *a_val, const int *b_rowptr, const int *b_col, const void *b_val,
+                         const int *c_rowptr, int *c_col, void *c_val, mlamg_stream_t stream);
+/* B = A^T with sorted rows (P.T at multigrid.py:165,181). */
+int mlamg_csr_transpose(int dtype, int m, int n, int nnz, const int *rowptr, const int *col,
+                        const void *val, int *t_rowptr, int *t_col, void *t_val, mlamg_stream_t stream);
+/* scipy drops entries whose sum is exactly 0.0: count, then compact. */
+int mlamg_csr_nonzero_count(int dtype, int m, const int *rowptr, const void *val, int *new_rowptr,
+                            long long *nnz_host, mlamg_stream_t stream);
+int mlamg_csr_nonzero_fill(int dtype, int m, const int *rowptr, const int *col, const void *val,
+                           const int *new_rowptr, int *new_col, void *new_val, mlamg_stream_t stream);
+/* sort every row by column index in place (scipy sort_indices) */
+int mlamg_csr_sort_rows(int dtype, int m, const int *rowptr, int *col, void *val, mlamg_stream_t stream);
+
+/* dense coarse operator: D (n x n row-major, zero-filled by the call) from CSR */
+int mlamg_csr_to_dense(int dtype, int n, const int *rowptr, const int *col, const void *val, void *dense,
+                       mlamg_stream_t stream);
+/* in-place inverse of a dense n x n f64 matrix by LU with partial pivoting (cuSOLVER getrf/getrs —
+ * library call, bottom level only; replaces spla.factorized / splu, multigrid.py:168, MLAMG.py:122).
+ * work: n*n doubles.  MLAMG_ESINGULAR on an exactly singular pivot. */
+int mlamg_dense_inverse_f64(int n, double *a, double *work, mlamg_stream_t stream);
+/* y = M x, M dense n x n row-major */
+int mlamg_gemv(int dtype, int n, const void *m, const void *x, void *y, mlamg_stream_t stream);
+
+/* largest eigenvalue of D^-1 A by power iteration on device (replaces ARPACK eigs, multigrid.py:105).
+ * work: 2n values.  *lambda_host receives the Rayleigh-quotient estimate after `iters` steps. */
+int mlamg_lambda_max(int dtype, int n, const int *rowptr, const int *col, const void *val, int iters,
+                     void *work, double *lambda_host, mlamg_stream_t stream);
+
+/* synthetic Dirichlet Poisson stencil (5-point if nz==1, else 7-point), x fastest.
+ * nnz = mlamg_poisson_nnz(nx,ny,nz). */
+long long mlamg_poisson_nnz(int nx, int ny, int nz);
+int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, void *val,
+                      mlamg_stream_t stream);
+
+/* ------------------------------------------------------------------ aggregation */
+
+/* pyamg.graph.bellman_ford (agg_interp.py:475): nearest = seed NODE ID, -1 unreachable; bit-exact
+ * emulation of the sequential in-place sweeps incl. tie-breaking.  *sweeps_host (may be NULL)
+ * receives the number of sequential sweeps emulated. */
+int mlamg_bellman_ford(int dtype, int n, const int *rowptr, const int *col, const void *w, int nseeds,
+                       const int *seeds, void *dist, int *nearest, int *sweeps_host, mlamg_stream_t stream);
+/* pyamg.graph.lloyd_cluster (graph.py:232): seeds[k] in/out, clusters = seed INDEX or -1.
+ * *iters_host (may be NULL) receives the Lloyd iterations executed. */
+int mlamg_lloyd_cluster(int dtype, int n, const int *rowptr, const int *col, const void *w, int k,
+                        int *seeds, int maxiter, void *dist, int *clusters, int *iters_host,
+                        mlamg_stream_t stream);
+/* ns.lib.graph.modified_bellman_ford (graph.py:7-53): push form over row-major COO edges,
+ * float32 distances (+inf init), int64 labels (0 init).  CSR input = coalesced COO. */
+int mlamg_modified_bellman_ford(int n, const int *rowptr, const int *col, const float *w, int ncenters,
+                                const int *centers, float *dist, long long *nearest, int *passes_host,
+                                mlamg_stream_t stream);
+
+/* ------------------------------------------------------------------ hierarchy handle + cycle drivers */
+
+typedef struct mlamg_hierarchy *mlamg_hierarchy_t;
+
+int mlamg_hierarchy_create(int dtype, int nlevels, mlamg_hierarchy_t *out);
+/* Level l operator and smoother diagonal (non-owning device pointers; caller keeps them alive). */
+int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz, const int *rowptr,
+                                 const int *col, const void *val, const void *dw);
+/* P (n_l x n_{l+1}) and R = P^T (n_{l+1} x n_l) between level l and l+1 */
+int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, const int *p_rowptr,
+                                 const int *p_col, const void *p_val, const int *r_rowptr,
+                                 const int *r_col, const void *r_val);
+/* dense inverse of the coarsest operator (n x n row-major, in the hierarchy dtype) */
+int mlamg_hierarchy_set_coarse_inverse(mlamg_hierarchy_t h, const void *inv);
+/* allocate per-level work vectors (and the pinned staging buffers of the *_host entry points) */
+int mlamg_hierarchy_finalize(mlamg_hierarchy_t h, mlamg_stream_t stream);
+int mlamg_hierarchy_destroy(mlamg_hierarchy_t h);
+/* algorithmic bytes of one V(nu1,nu2) cycle per SURVEY.md §8(d) */
+double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int zero_guess);
+/* 1: capture the cycle in a CUDA graph and replay it (launch-bound coarse levels), 0: plain launches */
+int mlamg_hierarchy_use_graph(mlamg_hierarchy_t h, int enable);
+
+/* one V(nu1,nu2) cycle on A x = b (pyamg multilevel __solve ordering; PyAMG.py:94,119).
+ * zero_guess != 0: x is treated as 0 on entry (preconditioner apply). */
+int mlamg_vcycle(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, int zero_guess,
+                 mlamg_stream_t stream);
+/* stationary iteration x <- V(x, b) until ||b-Ax||_2 <= tol_abs or maxiter.  res_host[maxiter+1]
+ * (entry 0 = initial residual).  MLAMG.py:189-195 / multigrid.py:173-199 loop with Jacobi smoothing. */
+int mlamg_solve(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double tol_abs,
+                int maxiter, double *res_host, int *niter_host, mlamg_stream_t stream);
+/* V-cycle preconditioned CG; stops when ||r||_2 <= rtol*||b||_2.  res_host[maxiter+1]. */
+int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter,
+              double *res_host, int *niter_host, mlamg_stream_t stream);
+
+/* Preconditioner apply with HOST buffers (PETSc PC apply shape: MLAMG.py:199-212, PyAMG.py:118-120):
+ * H2D(b) -> `cycles` V-cycles from a zero guess -> D2H(x), all inside the call; returns after x_host
+ * is complete. */
+int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int nu1, int nu2,
+                      int cycles, mlamg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLAMG_H */

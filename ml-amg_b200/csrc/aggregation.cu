@@ -1,0 +1,580 @@
+// Lloyd / Bellman-Ford aggregation with the sequential reference's tie-breaking, bit-exact.
+//
+// Reference: pyamg 4.x amg_core `bellman_ford` / `lloyd_cluster` (called at ns/lib/graph.py:232 and
+// ns/model/agg_interp.py:475) are in-place Gauss-Seidel pull sweeps in row order with strict `<`:
+//     for i in rows: for jj in row i: d = w[jj] + x[col[jj]]; if d < x_i: x_i = d; z_i = z[col[jj]]
+// repeated until a sweep changes no distance.  Distances at the fixed point do not depend on the
+// sweep order; the labels of tied nodes do.  The kernels below emulate sweep s exactly:
+//
+//   X_s(i) = min( X_{s-1}(i), min_{j<i} fl(w_ij + X_s(j)), min_{j>=i} fl(w_ij + X_{s-1}(j)) )
+//
+// is a fixed-point problem on the DAG of "lower" edges (j<i); it has a unique solution, reached by
+// in-place parallel relaxations (monotone, from above) repeated until a pass changes nothing.  The
+// label of a node whose distance dropped in sweep s is the label, at the time of the sequential row
+// scan, of the FIRST CSR-order neighbour whose candidate equals the new distance: Z_{s-1}(j*) when
+// j* >= i or j* did not change in sweep s, else Z_s(j*) — a chain through strictly smaller indices
+// that is resolved by pointer jumping.  Nothing here depends on thread scheduling, so results are
+// identical run to run and identical to the sequential loops.
+#include "common.cuh"
+
+namespace mlamg {
+
+constexpr int AGG_LANES = 8;
+constexpr int AGG_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ T group_min8(T v) {
+#pragma unroll
+    for (int o = AGG_LANES / 2; o > 0; o >>= 1) {
+        const T u = __shfl_xor_sync(0xffffffffu, v, o, AGG_LANES);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int group_min8i(int v) {
+#pragma unroll
+    for (int o = AGG_LANES / 2; o > 0; o >>= 1) {
+        const int u = __shfl_xor_sync(0xffffffffu, v, o, AGG_LANES);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+
+// One relaxation pass.  ORDERED: neighbours j < i read the in-progress array xcur, j >= i read xprev
+// (sequential-sweep emulation).  !ORDERED: every neighbour reads xcur (order-free fixed point).
+template <typename T, bool ORDERED>
+__global__ void __launch_bounds__(AGG_THREADS)
+bf_relax_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ w,
+                const T *__restrict__ xprev, T *xcur, int *__restrict__ changed) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    T own = Limits<T>::max();
+    T m = Limits<T>::max();
+    if (i < n) {
+        own = __ldcg(&xcur[i]);
+        m = own;
+        for (int jj = rowptr[i] + lane; jj < rowptr[i + 1]; jj += AGG_LANES) {
+            const int j = col[jj];
+            const T xj = (!ORDERED || j < i) ? __ldcg(&xcur[j]) : xprev[j];
+            const T d = w[jj] + xj;
+            if (d < m) m = d;
+        }
+    }
+    m = group_min8(m);
+    if (i < n && lane == 0 && m < own) {
+        xcur[i] = m;
+        *changed = 1;
+    }
+}
+
+// Labels of sweep s (see file header).  link[i] = j* when Z_s(i) must be taken from Z_s(j*) which is
+// itself produced in this sweep, -1 when zcur[i] is final.
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS)
+bf_label_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ w,
+                const T *__restrict__ xprev, const T *__restrict__ xcur, const int *__restrict__ zprev,
+                int *__restrict__ zcur, int *__restrict__ link, int *__restrict__ pending, int *__restrict__ error) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    int first = 0x7fffffff;
+    bool updated = false;
+    if (i < n) {
+        const T xi = xcur[i];
+        updated = xi < xprev[i];
+        if (updated) {
+            for (int jj = rowptr[i] + lane; jj < rowptr[i + 1]; jj += AGG_LANES) {
+                const int j = col[jj];
+                const T xj = (j < i) ? xcur[j] : xprev[j];
+                const T d = w[jj] + xj;
+                if (d == xi) { first = jj; break; }
+            }
+        }
+    }
+    first = group_min8i(first);
+    if (i < n && lane == 0) {
+        if (!updated) {
+            zcur[i] = zprev[i];
+            link[i] = -1;
+        } else if (first == 0x7fffffff) {
+            *error = 1;
+            zcur[i] = zprev[i];
+            link[i] = -1;
+        } else {
+            const int j = col[first];
+            if (j < i && xcur[j] < xprev[j]) {
+                link[i] = j;
+                *pending = 1;
+            } else {
+                zcur[i] = zprev[j];
+                link[i] = -1;
+            }
+        }
+    }
+}
+
+// pointer jumping, Jacobi style: reads link_in (state before this launch), writes link_out
+__global__ void __launch_bounds__(AGG_THREADS)
+bf_chain_kernel(int n, const int *__restrict__ link_in, int *__restrict__ link_out, int *zcur,
+                int *__restrict__ pending) {
+    const long long i = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int l = link_in[i];
+    if (l < 0) { link_out[i] = -1; return; }
+    const int ll = link_in[l];
+    if (ll < 0) {
+        zcur[i] = __ldcg(&zcur[l]);   // final since a previous launch
+        link_out[i] = -1;
+    } else {
+        link_out[i] = ll;
+        *pending = 1;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS) fill_kernel(int n, T v, T *__restrict__ a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        a[i] = v;
+}
+
+// seeds: dist 0; label = seed node id (LABEL_IS_INDEX = false) or seed index (true)
+template <typename T, bool LABEL_IS_INDEX>
+__global__ void __launch_bounds__(AGG_THREADS) seed_init_kernel(int k, const int *__restrict__ seeds,
+                                                                T *__restrict__ x, int *__restrict__ z) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    const int node = seeds[s];
+    x[node] = (T)0;
+    z[node] = LABEL_IS_INDEX ? (int)s : node;
+}
+
+static unsigned ew_blocks(int n) {
+    unsigned b = cdiv(n > 0 ? n : 1, AGG_THREADS);
+    return b > 148u * 16u ? 148u * 16u : b;
+}
+
+struct Flags {        // pinned host mirror of a few device flags
+    int *dev = nullptr;
+    int *host = nullptr;
+    int init() {
+        MLAMG_CUDA(cudaMalloc(&dev, 4 * sizeof(int)));
+        MLAMG_CUDA(cudaMallocHost(&host, 4 * sizeof(int)));
+        return MLAMG_OK;
+    }
+    ~Flags() {
+        if (dev) cudaFree(dev);
+        if (host) cudaFreeHost(host);
+    }
+    int clear(cudaStream_t s) { MLAMG_CUDA(cudaMemsetAsync(dev, 0, 4 * sizeof(int), s)); return MLAMG_OK; }
+    int fetch(cudaStream_t s) {
+        MLAMG_CUDA(cudaMemcpyAsync(host, dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MLAMG_CUDA(cudaStreamSynchronize(s));
+        return MLAMG_OK;
+    }
+};
+
+// Work arrays of one Bellman-Ford run
+template <typename T>
+struct BfWork {
+    T *xa, *xb;
+    int *za, *zb, *la, *lb;
+};
+
+// Emulates the sequential sweeps to their fixed point.  On entry x/z hold the initial state; on exit
+// they hold the final distances / labels.  Returns the number of sequential sweeps (incl. the final
+// no-change sweep) in *sweeps.
+template <typename T>
+static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, const T *w, T *x, int *z,
+                                  BfWork<T> wk, Flags &fl, int *sweeps, cudaStream_t s) {
+    const unsigned gb = cdiv((long long)n * AGG_LANES, AGG_THREADS);
+    const unsigned eb = cdiv(n, AGG_THREADS);
+    T *xprev = wk.xa, *xcur = wk.xb;
+    int *zprev = wk.za, *zcur = wk.zb;
+    MLAMG_CUDA(cudaMemcpyAsync(xprev, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    MLAMG_CUDA(cudaMemcpyAsync(zprev, z, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    int nsweeps = 0;
+    for (;;) {
+        nsweeps++;
+        MLAMG_CUDA(cudaMemcpyAsync(xcur, xprev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        bool any = false;
+        for (;;) {   // fixed point of sweep `nsweeps`
+            MLAMG_TRY(fl.clear(s));
+            bf_relax_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fl.dev);
+            MLAMG_LAUNCHED();
+            MLAMG_TRY(fl.fetch(s));
+            if (!fl.host[0]) break;
+            any = true;
+        }
+        if (!any) break;   // this sweep changed nothing: the sequential loop stops here
+        MLAMG_TRY(fl.clear(s));
+        bf_label_kernel<T><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, zprev, zcur, wk.la, fl.dev + 1,
+                                                      fl.dev + 2);
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.fetch(s));
+        if (fl.host[2]) return set_error(MLAMG_EINVAL, "bellman_ford: inconsistent relaxation (NaN or negative weight?)");
+        int *lin = wk.la, *lout = wk.lb;
+        while (fl.host[1]) {
+            MLAMG_TRY(fl.clear(s));
+            bf_chain_kernel<<<eb, AGG_THREADS, 0, s>>>(n, lin, lout, zcur, fl.dev + 1);
+            MLAMG_LAUNCHED();
+            MLAMG_TRY(fl.fetch(s));
+            int *t = lin; lin = lout; lout = t;
+        }
+        { T *t = xprev; xprev = xcur; xcur = t; }
+        { int *t = zprev; zprev = zcur; zcur = t; }
+    }
+    MLAMG_CUDA(cudaMemcpyAsync(x, xprev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    MLAMG_CUDA(cudaMemcpyAsync(z, zprev, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (sweeps) *sweeps = nsweeps;
+    return MLAMG_OK;
+}
+
+// order-free fixed point (distances only), in place on x
+template <typename T>
+static int bf_free_fixed_point(int n, const int *rowptr, const int *col, const T *w, T *x, Flags &fl, cudaStream_t s) {
+    const unsigned gb = cdiv((long long)n * AGG_LANES, AGG_THREADS);
+    for (;;) {
+        MLAMG_TRY(fl.clear(s));
+        bf_relax_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fl.dev);
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.fetch(s));
+        if (!fl.host[0]) break;
+    }
+    return MLAMG_OK;
+}
+
+template <typename T>
+static int alloc_work(int n, cudaStream_t s, Scratch &buf, BfWork<T> *wk) {
+    MLAMG_SCRATCH_OK(buf);
+    unsigned char *p = buf.as<unsigned char>();
+    const size_t nx = ((size_t)n * sizeof(T) + 255) & ~(size_t)255, ni = ((size_t)n * sizeof(int) + 255) & ~(size_t)255;
+    wk->xa = (T *)p; p += nx;
+    wk->xb = (T *)p; p += nx;
+    wk->za = (int *)p; p += ni;
+    wk->zb = (int *)p; p += ni;
+    wk->la = (int *)p; p += ni;
+    wk->lb = (int *)p;
+    return MLAMG_OK;
+}
+static size_t work_bytes(int n, size_t tsize) {
+    const size_t nx = ((size_t)n * tsize + 255) & ~(size_t)255, ni = ((size_t)n * sizeof(int) + 255) & ~(size_t)255;
+    return 2 * nx + 4 * ni + 256;
+}
+
+template <typename T>
+static int bellman_ford_t(int n, const int *rowptr, const int *col, const T *w, int nseeds, const int *seeds, T *dist,
+                          int *nearest, int *sweeps_host, cudaStream_t s) {
+    if (n < 0 || nseeds < 0) return set_error(MLAMG_EINVAL, "bellman_ford: bad n/nseeds");
+    if (n == 0) { if (sweeps_host) *sweeps_host = 0; return MLAMG_OK; }
+    Flags fl;
+    MLAMG_TRY(fl.init());
+    Scratch buf(work_bytes(n, sizeof(T)), s);
+    BfWork<T> wk;
+    MLAMG_TRY(alloc_work<T>(n, s, buf, &wk));
+    fill_kernel<T><<<ew_blocks(n), AGG_THREADS, 0, s>>>(n, Limits<T>::max(), dist);
+    MLAMG_LAUNCHED();
+    fill_kernel<int><<<ew_blocks(n), AGG_THREADS, 0, s>>>(n, -1, nearest);
+    MLAMG_LAUNCHED();
+    if (nseeds > 0) {
+        seed_init_kernel<T, false><<<cdiv(nseeds, AGG_THREADS), AGG_THREADS, 0, s>>>(nseeds, seeds, dist, nearest);
+        MLAMG_LAUNCHED();
+    }
+    int rc = bf_ordered_fixed_point<T>(n, rowptr, col, w, dist, nearest, wk, fl, sweeps_host, s);
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    return rc;
+}
+
+// ------------------------------------------------------------------ Lloyd
+__global__ void __launch_bounds__(AGG_THREADS)
+lloyd_boundary_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const int *__restrict__ z,
+                      int *__restrict__ is_boundary) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    int b = 0;
+    if (i < n) {
+        const int zi = z[i];
+        for (int jj = rowptr[i] + lane; jj < rowptr[i + 1]; jj += AGG_LANES)
+            if (z[col[jj]] != zi) { b = 1; break; }
+    }
+#pragma unroll
+    for (int o = AGG_LANES / 2; o > 0; o >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, o, AGG_LANES);
+    if (i < n && lane == 0) is_boundary[i] = b;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS) lloyd_inward_init_kernel(int n, const int *__restrict__ is_boundary,
+                                                                        T *__restrict__ x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = is_boundary[i] ? (T)0 : Limits<T>::max();
+}
+
+// per-cluster maximum of the inward distance (order-preserving key), then the first index attaining it
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS) lloyd_max_kernel(int n, const int *__restrict__ z, const T *__restrict__ x,
+                                                                unsigned long long *__restrict__ best) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = z[i];
+    if (c >= 0) atomicMax(&best[c], f2key(x[i]));
+}
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS) lloyd_argmax_kernel(int n, const int *__restrict__ z,
+                                                                   const T *__restrict__ x,
+                                                                   const unsigned long long *__restrict__ best,
+                                                                   int *__restrict__ arg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = z[i];
+    if (c >= 0 && f2key(x[i]) == best[c]) atomicMin(&arg[c], (int)i);
+}
+// z[seed] moves to the first node of strictly larger inward distance (graph.h seed update loop)
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS) lloyd_move_kernel(int k, const T *__restrict__ x,
+                                                                 const int *__restrict__ arg, int *__restrict__ seeds,
+                                                                 int *__restrict__ moved) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k) return;
+    const int old = seeds[c];
+    const int a = arg[c];
+    if (a != 0x7fffffff && x[old] < x[a]) {
+        seeds[c] = a;
+        *moved = 1;
+    }
+}
+
+template <typename T>
+static int lloyd_cluster_t(int n, const int *rowptr, const int *col, const T *w, int k, int *seeds, int maxiter, T *dist,
+                           int *clusters, int *iters_host, cudaStream_t s) {
+    if (n <= 0 || k <= 0) return set_error(MLAMG_EINVAL, "lloyd_cluster: need n > 0 and at least one seed");
+    Flags fl;
+    MLAMG_TRY(fl.init());
+    Scratch buf(work_bytes(n, sizeof(T)), s), bnd((size_t)n * sizeof(int), s),
+        best((size_t)k * sizeof(unsigned long long), s), arg((size_t)k * sizeof(int), s);
+    BfWork<T> wk;
+    MLAMG_TRY(alloc_work<T>(n, s, buf, &wk));
+    MLAMG_SCRATCH_OK(bnd);
+    MLAMG_SCRATCH_OK(best);
+    MLAMG_SCRATCH_OK(arg);
+    const unsigned gb = cdiv((long long)n * AGG_LANES, AGG_THREADS), eb = cdiv(n, AGG_THREADS), kb = cdiv(k, AGG_THREADS);
+    int it = 0;
+    for (it = 0; it < maxiter;) {
+        // reset + seeds
+        fill_kernel<T><<<ew_blocks(n), AGG_THREADS, 0, s>>>(n, Limits<T>::max(), dist);
+        MLAMG_LAUNCHED();
+        fill_kernel<int><<<ew_blocks(n), AGG_THREADS, 0, s>>>(n, -1, clusters);
+        MLAMG_LAUNCHED();
+        seed_init_kernel<T, true><<<kb, AGG_THREADS, 0, s>>>(k, seeds, dist, clusters);
+        MLAMG_LAUNCHED();
+        // outward propagation with sequential tie-breaking
+        MLAMG_TRY(bf_ordered_fixed_point<T>(n, rowptr, col, w, dist, clusters, wk, fl, nullptr, s));
+        // cluster boundaries -> distance 0, interior -> max
+        lloyd_boundary_kernel<<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, clusters, bnd.as<int>());
+        MLAMG_LAUNCHED();
+        lloyd_inward_init_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, bnd.as<int>(), dist);
+        MLAMG_LAUNCHED();
+        // inward propagation: labels of interior nodes cannot change (all their neighbours carry the
+        // same label), so only the order-independent distances are needed
+        MLAMG_TRY(bf_free_fixed_point<T>(n, rowptr, col, w, dist, fl, s));
+        // seed update
+        MLAMG_CUDA(cudaMemsetAsync(best.p, 0, (size_t)k * sizeof(unsigned long long), s));
+        fill_kernel<int><<<ew_blocks(k), AGG_THREADS, 0, s>>>(k, 0x7fffffff, arg.as<int>());
+        MLAMG_LAUNCHED();
+        lloyd_max_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, clusters, dist, best.as<unsigned long long>());
+        MLAMG_LAUNCHED();
+        lloyd_argmax_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, clusters, dist, best.as<unsigned long long>(), arg.as<int>());
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.clear(s));
+        lloyd_move_kernel<T><<<kb, AGG_THREADS, 0, s>>>(k, dist, arg.as<int>(), seeds, fl.dev);
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.fetch(s));
+        it++;
+        if (!fl.host[0]) break;   // seeds unchanged
+    }
+    if (iters_host) *iters_host = it;
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    return MLAMG_OK;
+}
+
+// ------------------------------------------------------------------ reference-owned push Bellman-Ford
+// ns/lib/graph.py:7-53.  Pass p over the row-major edge list, with U(i) = dist[i] at the time row i is
+// visited and F(i) = dist[i] at the end of the pass:
+//   U(i) = min( D_{p-1}(i), min_{i'<i, i'->i} fl(U(i') + w) )        (DAG fixed point)
+//   F(i) = min( U(i),       min_{i'>i, i'->i} fl(U(i') + w) )
+// the label follows the FIRST source (ascending i') that attains the minimum, with the label that
+// source had when its row was visited.  Needs in-edges: tr_* is the transpose CSR (sources sorted).
+__global__ void __launch_bounds__(AGG_THREADS)
+mbf_u_relax_kernel(int n, const int *__restrict__ tr_rowptr, const int *__restrict__ tr_col,
+                   const float *__restrict__ tr_w, float *u, int *__restrict__ changed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float own = __ldcg(&u[i]);
+    float m = own;
+    for (int jj = tr_rowptr[i]; jj < tr_rowptr[i + 1]; jj++) {
+        const int src = tr_col[jj];
+        if (src >= i) break;   // sources are sorted ascending
+        const float d = __ldcg(&u[src]) + tr_w[jj];
+        if (d < m) m = d;
+    }
+    if (m < own) { u[i] = m; *changed = 1; }
+}
+
+__global__ void __launch_bounds__(AGG_THREADS)
+mbf_label_u_kernel(int n, const int *__restrict__ tr_rowptr, const int *__restrict__ tr_col,
+                   const float *__restrict__ tr_w, const float *__restrict__ dprev, const float *__restrict__ u,
+                   const long long *__restrict__ lprev, long long *__restrict__ lu, int *__restrict__ link,
+                   int *__restrict__ pending) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ui = u[i];
+    if (!(ui < dprev[i])) { lu[i] = lprev[i]; link[i] = -1; return; }
+    for (int jj = tr_rowptr[i]; jj < tr_rowptr[i + 1]; jj++) {
+        const int src = tr_col[jj];
+        if (src >= i) break;
+        if (u[src] + tr_w[jj] == ui) {
+            if (u[src] < dprev[src]) { link[i] = src; *pending = 1; }
+            else { lu[i] = lprev[src]; link[i] = -1; }
+            return;
+        }
+    }
+    lu[i] = lprev[i];
+    link[i] = -1;
+}
+
+__global__ void __launch_bounds__(AGG_THREADS)
+mbf_chain_kernel(int n, const int *__restrict__ link_in, int *__restrict__ link_out, long long *lu,
+                 int *__restrict__ pending) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = link_in[i];
+    if (l < 0) { link_out[i] = -1; return; }
+    const int ll = link_in[l];
+    if (ll < 0) { lu[i] = __ldcg(&lu[l]); link_out[i] = -1; }
+    else { link_out[i] = ll; *pending = 1; }
+}
+
+__global__ void __launch_bounds__(AGG_THREADS)
+mbf_final_kernel(int n, const int *__restrict__ tr_rowptr, const int *__restrict__ tr_col,
+                 const float *__restrict__ tr_w, const float *__restrict__ dprev, const float *__restrict__ u,
+                 const long long *__restrict__ lu, float *__restrict__ dnew, long long *__restrict__ lnew,
+                 int *__restrict__ changed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = u[i];
+    int arg = -1;
+    for (int jj = tr_rowptr[i]; jj < tr_rowptr[i + 1]; jj++) {
+        const int src = tr_col[jj];
+        if (src <= i) continue;
+        const float d = u[src] + tr_w[jj];
+        if (d < m) { m = d; arg = src; }   // strict: first (ascending) source attaining the minimum
+    }
+    dnew[i] = m;
+    lnew[i] = arg >= 0 ? lu[arg] : lu[i];
+    if (m < dprev[i]) *changed = 1;
+}
+
+__global__ void __launch_bounds__(AGG_THREADS) mbf_init_kernel(int n, float *__restrict__ d, long long *__restrict__ l) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { d[i] = __int_as_float(0x7f800000); l[i] = 0; }
+}
+__global__ void __launch_bounds__(AGG_THREADS) mbf_seed_kernel(int k, const int *__restrict__ centers,
+                                                               float *__restrict__ d, long long *__restrict__ l) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < k) { d[centers[c]] = 0.f; l[centers[c]] = centers[c]; }
+}
+
+}  // namespace mlamg
+
+using namespace mlamg;
+
+extern "C" {
+
+int mlamg_bellman_ford(int dtype, int n, const int *rowptr, const int *col, const void *w, int nseeds,
+                       const int *seeds, void *dist, int *nearest, int *sweeps_host, mlamg_stream_t stream) {
+    MLAMG_DISPATCH(dtype, return bellman_ford_t<T>(n, rowptr, col, (const T *)w, nseeds, seeds, (T *)dist, nearest,
+                                                   sweeps_host, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_lloyd_cluster(int dtype, int n, const int *rowptr, const int *col, const void *w, int k, int *seeds,
+                        int maxiter, void *dist, int *clusters, int *iters_host, mlamg_stream_t stream) {
+    MLAMG_DISPATCH(dtype, return lloyd_cluster_t<T>(n, rowptr, col, (const T *)w, k, seeds, maxiter, (T *)dist, clusters,
+                                                    iters_host, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_modified_bellman_ford(int n, const int *rowptr, const int *col, const float *w, int ncenters,
+                                const int *centers, float *dist, long long *nearest, int *passes_host,
+                                mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0 || ncenters < 0) return set_error(MLAMG_EINVAL, "modified_bellman_ford: bad n/ncenters");
+    if (n == 0) { if (passes_host) *passes_host = 1; return MLAMG_OK; }
+    int nnz = 0;
+    MLAMG_CUDA(cudaMemcpyAsync(&nnz, rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    Flags fl;
+    MLAMG_TRY(fl.init());
+    const size_t nn = (size_t)n;
+    Scratch trp((nn + 1) * sizeof(int), s), trc((size_t)(nnz > 0 ? nnz : 1) * sizeof(int), s),
+        trw((size_t)(nnz > 0 ? nnz : 1) * sizeof(float), s), ub(nn * sizeof(float), s), d2(nn * sizeof(float), s),
+        lub(nn * sizeof(long long), s), l2(nn * sizeof(long long), s), la(nn * sizeof(int), s), lb(nn * sizeof(int), s);
+    MLAMG_SCRATCH_OK(trp); MLAMG_SCRATCH_OK(trc); MLAMG_SCRATCH_OK(trw); MLAMG_SCRATCH_OK(ub); MLAMG_SCRATCH_OK(d2);
+    MLAMG_SCRATCH_OK(lub); MLAMG_SCRATCH_OK(l2); MLAMG_SCRATCH_OK(la); MLAMG_SCRATCH_OK(lb);
+    MLAMG_TRY(mlamg_csr_transpose(MLAMG_F32, n, n, nnz, rowptr, col, w, trp.as<int>(), trc.as<int>(), trw.as<float>(),
+                                  stream));
+    const unsigned eb = cdiv(n, AGG_THREADS);
+    mbf_init_kernel<<<eb, AGG_THREADS, 0, s>>>(n, dist, nearest);
+    MLAMG_LAUNCHED();
+    if (ncenters > 0) {
+        mbf_seed_kernel<<<cdiv(ncenters, AGG_THREADS), AGG_THREADS, 0, s>>>(ncenters, centers, dist, nearest);
+        MLAMG_LAUNCHED();
+    }
+    float *dprev = dist, *dnew = d2.as<float>();
+    long long *lprev = nearest, *lnew = l2.as<long long>();
+    float *u = ub.as<float>();
+    int passes = 0;
+    for (;;) {
+        passes++;
+        MLAMG_CUDA(cudaMemcpyAsync(u, dprev, nn * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        for (;;) {
+            MLAMG_TRY(fl.clear(s));
+            mbf_u_relax_kernel<<<eb, AGG_THREADS, 0, s>>>(n, trp.as<int>(), trc.as<int>(), trw.as<float>(), u, fl.dev);
+            MLAMG_LAUNCHED();
+            MLAMG_TRY(fl.fetch(s));
+            if (!fl.host[0]) break;
+        }
+        MLAMG_TRY(fl.clear(s));
+        mbf_label_u_kernel<<<eb, AGG_THREADS, 0, s>>>(n, trp.as<int>(), trc.as<int>(), trw.as<float>(), dprev, u, lprev,
+                                                      lub.as<long long>(), la.as<int>(), fl.dev + 1);
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.fetch(s));
+        int *lin = la.as<int>(), *lout = lb.as<int>();
+        while (fl.host[1]) {
+            MLAMG_TRY(fl.clear(s));
+            mbf_chain_kernel<<<eb, AGG_THREADS, 0, s>>>(n, lin, lout, lub.as<long long>(), fl.dev + 1);
+            MLAMG_LAUNCHED();
+            MLAMG_TRY(fl.fetch(s));
+            int *t = lin; lin = lout; lout = t;
+        }
+        MLAMG_TRY(fl.clear(s));
+        mbf_final_kernel<<<eb, AGG_THREADS, 0, s>>>(n, trp.as<int>(), trc.as<int>(), trw.as<float>(), dprev, u,
+                                                    lub.as<long long>(), dnew, lnew, fl.dev);
+        MLAMG_LAUNCHED();
+        MLAMG_TRY(fl.fetch(s));
+        { float *t = dprev; dprev = dnew; dnew = t; }
+        { long long *t = lprev; lprev = lnew; lnew = t; }
+        if (!fl.host[0]) break;
+    }
+    if (dprev != dist) {
+        MLAMG_CUDA(cudaMemcpyAsync(dist, dprev, nn * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        MLAMG_CUDA(cudaMemcpyAsync(nearest, lprev, nn * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    }
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    if (passes_host) *passes_host = passes;
+    return MLAMG_OK;
+}
+
+}  // extern "C"

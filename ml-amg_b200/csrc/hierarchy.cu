@@ -1,0 +1,412 @@
+// Hierarchy handle and cycle drivers: V(nu1,nu2) cycle over a level array, stationary iteration,
+// V-cycle-preconditioned CG and the host-buffer preconditioner apply.
+//
+// Cycle ordering = pyamg multilevel `__solve` (the only multilevel cycle the reference uses,
+// ns/preconditioner/PyAMG.py:94,119): presmooth -> r = b - A x -> b_c = R r -> recurse from
+// x_c = 0 -> x += P x_c -> postsmooth; the coarsest level is solved exactly (dense inverse).
+// Smoother = x += dw .* (b - A x) (ns/preconditioner/MLAMG.py:143-146), one fused pass over A per
+// sweep, ping-ponging between two vectors; from a zero guess the first sweep is x = dw .* b and
+// needs no pass over A.  Per level and V(1,1) cycle the operator is therefore read twice
+// (residual + post-smooth) on coarse levels and on a zero-guess fine level.
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+namespace mlamg {
+
+template <typename T> int spmv_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
+template <typename T> int spmv_add_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
+template <typename T>
+int residual_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, double *, cudaStream_t);
+template <typename T>
+int jacobi_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
+template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStream_t);
+template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
+
+struct Csr {
+    int n = 0;          // rows
+    long long nnz = 0;
+    const int *rowptr = nullptr;
+    const int *col = nullptr;
+    const void *val = nullptr;
+};
+
+struct LevelData {
+    Csr A, P, R;
+    const void *dw = nullptr;
+    bool has_A = false, has_PR = false;
+    void *x = nullptr, *tmp = nullptr, *b = nullptr, *r = nullptr;   // owned work vectors
+};
+
+}  // namespace mlamg
+
+struct mlamg_hierarchy {
+    int dtype = MLAMG_F64;
+    size_t esz = 8;
+    std::vector<mlamg::LevelData> lv;
+    const void *coarse_inv = nullptr;
+    bool finalized = false;
+    bool use_graph = false;
+    // PCG work vectors (level-0 sized), allocated lazily
+    void *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_ap = nullptr;
+    double *dscal = nullptr;     // device scalars
+    double *hscal = nullptr;     // pinned host mirror
+    void *host_b = nullptr, *host_x = nullptr;   // device staging of the *_host entry points
+    // CUDA graph cache of one V-cycle
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const void *g_b = nullptr;
+    void *g_x = nullptr;
+    int g_nu1 = -1, g_nu2 = -1, g_zero = -1;
+};
+
+namespace mlamg {
+
+static int check_handle(mlamg_hierarchy_t h) {
+    if (!h) return set_error(MLAMG_EINVAL, "null hierarchy handle");
+    return MLAMG_OK;
+}
+
+template <typename T>
+static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
+    const int L = (int)h->lv.size();
+    if (L == 1) {   // single level: exact solve
+        return gemv_t<T>(h->lv[0].A.n, (const T *)h->coarse_inv, b, x, s);
+    }
+    std::vector<T *> cur(L, nullptr);      // where level l's iterate currently lives
+    std::vector<const T *> rhs(L, nullptr);
+    rhs[0] = b;
+    // ---- downward leg
+    for (int l = 0; l < L - 1; l++) {
+        LevelData &lev = h->lv[l];
+        const Csr &A = lev.A;
+        const T *dw = (const T *)lev.dw;
+        T *xa = (l == 0) ? x : (T *)lev.x;     // "home" buffer
+        T *xb = (T *)lev.tmp;
+        const bool zero = (l > 0) || zero_guess;
+        // number of ping-pong sweeps this level will see during the whole cycle
+        const int pre_pp = zero ? (nu1 > 0 ? nu1 - 1 : 0) : nu1;
+        const int total_pp = pre_pp + nu2;
+        T *c;
+        if (zero) {
+            // first write goes where the final result lands in the home buffer after total_pp swaps
+            c = (total_pp % 2 == 0) ? xa : xb;
+            if (nu1 > 0) MLAMG_TRY(jacobi_zero_t<T>(A.n, dw, rhs[l], c, s));
+            else MLAMG_CUDA(cudaMemsetAsync(c, 0, (size_t)A.n * sizeof(T), s));
+        } else {
+            c = xa;   // caller's iterate
+        }
+        for (int k = 0; k < pre_pp; k++) {
+            T *o = (c == xa) ? xb : xa;
+            MLAMG_TRY(jacobi_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, o, s));
+            c = o;
+        }
+        cur[l] = c;
+        MLAMG_TRY(residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, c, rhs[l], (T *)lev.r, nullptr, s));
+        const Csr &R = lev.R;
+        T *bc = (T *)h->lv[l + 1].b;
+        MLAMG_TRY(spmv_t<T>(R.n, R.nnz, R.rowptr, R.col, (const T *)R.val, (const T *)lev.r, bc, s));
+        rhs[l + 1] = bc;
+    }
+    // ---- coarsest level: exact solve with the dense inverse
+    {
+        LevelData &lev = h->lv[L - 1];
+        MLAMG_TRY(gemv_t<T>(lev.A.n, (const T *)h->coarse_inv, rhs[L - 1], (T *)lev.x, s));
+        cur[L - 1] = (T *)lev.x;
+    }
+    // ---- upward leg
+    for (int l = L - 2; l >= 0; l--) {
+        LevelData &lev = h->lv[l];
+        const Csr &A = lev.A, &P = lev.P;
+        const T *dw = (const T *)lev.dw;
+        T *xa = (l == 0) ? x : (T *)lev.x;
+        T *xb = (T *)lev.tmp;
+        T *c = cur[l];
+        MLAMG_TRY(spmv_add_t<T>(P.n, P.nnz, P.rowptr, P.col, (const T *)P.val, cur[l + 1], c, s));
+        for (int k = 0; k < nu2; k++) {
+            T *o = (c == xa) ? xb : xa;
+            MLAMG_TRY(jacobi_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, o, s));
+            c = o;
+        }
+        if (l == 0 && c != x) {   // non-zero guess with an odd sweep count: one copy back
+            MLAMG_CUDA(cudaMemcpyAsync(x, c, (size_t)A.n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+            c = x;
+        }
+        cur[l] = c;
+    }
+    return MLAMG_OK;
+}
+
+static int vcycle_dispatch(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess,
+                           cudaStream_t s) {
+    MLAMG_DISPATCH(h->dtype, return vcycle_enqueue<T>(h, (const T *)b, (T *)x, nu1, nu2, zero_guess, s));
+    return MLAMG_OK;
+}
+
+static int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
+    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
+    if (nu1 < 0 || nu2 < 0) return set_error(MLAMG_EINVAL, "negative sweep count");
+    if (b == x) return set_error(MLAMG_EINVAL, "vcycle: b aliases x");
+    if (!h->use_graph) return vcycle_dispatch(h, b, x, nu1, nu2, zero_guess, s);
+    const bool hit = h->gexec && h->g_b == b && h->g_x == x && h->g_nu1 == nu1 && h->g_nu2 == nu2 &&
+                     h->g_zero == (zero_guess ? 1 : 0);
+    if (!hit) {
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        if (!h->cap_stream) MLAMG_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        MLAMG_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = vcycle_dispatch(h, b, x, nu1, nu2, zero_guess, h->cap_stream);
+        cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+        if (rc != MLAMG_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        e = cudaGraphInstantiate(&h->gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { h->gexec = nullptr; return set_cuda_error(e, __FILE__, __LINE__); }
+        h->g_b = b; h->g_x = x; h->g_nu1 = nu1; h->g_nu2 = nu2; h->g_zero = zero_guess ? 1 : 0;
+    }
+    MLAMG_CUDA(cudaGraphLaunch(h->gexec, s));
+    return MLAMG_OK;
+}
+
+static int ensure_pcg(mlamg_hierarchy *h) {
+    if (h->pcg_r) return MLAMG_OK;
+    const size_t bytes = (size_t)h->lv[0].A.n * h->esz;
+    MLAMG_CUDA(cudaMalloc(&h->pcg_r, bytes));
+    MLAMG_CUDA(cudaMalloc(&h->pcg_z, bytes));
+    MLAMG_CUDA(cudaMalloc(&h->pcg_p, bytes));
+    MLAMG_CUDA(cudaMalloc(&h->pcg_ap, bytes));
+    return MLAMG_OK;
+}
+
+static int fetch_scalar(mlamg_hierarchy *h, int idx, double *out, cudaStream_t s) {
+    MLAMG_CUDA(cudaMemcpyAsync(h->hscal + idx, h->dscal + idx, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    *out = h->hscal[idx];
+    return MLAMG_OK;
+}
+
+}  // namespace mlamg
+
+using namespace mlamg;
+
+extern "C" {
+
+int mlamg_hierarchy_create(int dtype, int nlevels, mlamg_hierarchy_t *out) {
+    if (!out || nlevels < 1 || nlevels > 64) return set_error(MLAMG_EINVAL, "hierarchy_create: bad arguments");
+    if (dtype != MLAMG_F32 && dtype != MLAMG_F64) return set_error(MLAMG_EINVAL, "hierarchy_create: bad dtype");
+    mlamg_hierarchy *h = new mlamg_hierarchy();
+    h->dtype = dtype;
+    h->esz = dtype == MLAMG_F32 ? 4 : 8;
+    h->lv.resize(nlevels);
+    *out = h;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz, const int *rowptr, const int *col,
+                                 const void *val, const void *dw) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level >= (int)h->lv.size() || n <= 0 || nnz < 0)
+        return set_error(MLAMG_EINVAL, "set_operator: bad level/n/nnz");
+    if (h->finalized) return set_error(MLAMG_EINVAL, "set_operator: hierarchy already finalized");
+    LevelData &lev = h->lv[level];
+    lev.A.n = n; lev.A.nnz = nnz; lev.A.rowptr = rowptr; lev.A.col = col; lev.A.val = val;
+    lev.dw = dw;
+    lev.has_A = true;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, const int *p_rowptr, const int *p_col,
+                                 const void *p_val, const int *r_rowptr, const int *r_col, const void *r_val) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level + 1 >= (int)h->lv.size()) return set_error(MLAMG_EINVAL, "set_transfer: bad level");
+    if (h->finalized) return set_error(MLAMG_EINVAL, "set_transfer: hierarchy already finalized");
+    LevelData &lev = h->lv[level];
+    if (!lev.has_A || !h->lv[level + 1].has_A)
+        return set_error(MLAMG_EINVAL, "set_transfer: set both level operators first");
+    lev.P.n = lev.A.n; lev.P.nnz = p_nnz; lev.P.rowptr = p_rowptr; lev.P.col = p_col; lev.P.val = p_val;
+    lev.R.n = h->lv[level + 1].A.n; lev.R.nnz = p_nnz; lev.R.rowptr = r_rowptr; lev.R.col = r_col; lev.R.val = r_val;
+    lev.has_PR = true;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_coarse_inverse(mlamg_hierarchy_t h, const void *inv) {
+    MLAMG_TRY(check_handle(h));
+    h->coarse_inv = inv;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_finalize(mlamg_hierarchy_t h, mlamg_stream_t stream) {
+    MLAMG_TRY(check_handle(h));
+    (void)stream;
+    if (h->finalized) return MLAMG_OK;
+    const int L = (int)h->lv.size();
+    for (int l = 0; l < L; l++) {
+        if (!h->lv[l].has_A) return set_error(MLAMG_EINVAL, "finalize: level %d has no operator", l);
+        if (l + 1 < L && !h->lv[l].has_PR) return set_error(MLAMG_EINVAL, "finalize: level %d has no P/R", l);
+        if (l + 1 < L && !h->lv[l].dw) return set_error(MLAMG_EINVAL, "finalize: level %d has no smoother diagonal", l);
+    }
+    if (!h->coarse_inv) return set_error(MLAMG_EINVAL, "finalize: coarse inverse not set");
+    for (int l = 0; l < L; l++) {
+        LevelData &lev = h->lv[l];
+        const size_t bytes = (size_t)lev.A.n * h->esz;
+        if (l > 0) {
+            MLAMG_CUDA(cudaMalloc(&lev.x, bytes));
+            MLAMG_CUDA(cudaMalloc(&lev.b, bytes));
+        }
+        if (l + 1 < L) {
+            MLAMG_CUDA(cudaMalloc(&lev.tmp, bytes));
+            MLAMG_CUDA(cudaMalloc(&lev.r, bytes));
+        }
+    }
+    MLAMG_CUDA(cudaMalloc(&h->dscal, 8 * sizeof(double)));
+    MLAMG_CUDA(cudaMallocHost(&h->hscal, 8 * sizeof(double)));
+    h->finalized = true;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_destroy(mlamg_hierarchy_t h) {
+    if (!h) return MLAMG_OK;
+    for (auto &lev : h->lv) {
+        if (lev.x) cudaFree(lev.x);
+        if (lev.b) cudaFree(lev.b);
+        if (lev.tmp) cudaFree(lev.tmp);
+        if (lev.r) cudaFree(lev.r);
+    }
+    if (h->pcg_r) { cudaFree(h->pcg_r); cudaFree(h->pcg_z); cudaFree(h->pcg_p); cudaFree(h->pcg_ap); }
+    if (h->dscal) cudaFree(h->dscal);
+    if (h->hscal) cudaFreeHost(h->hscal);
+    if (h->host_b) cudaFree(h->host_b);
+    if (h->host_x) cudaFree(h->host_x);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    delete h;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_use_graph(mlamg_hierarchy_t h, int enable) {
+    MLAMG_TRY(check_handle(h));
+    h->use_graph = enable != 0;
+    if (!enable && h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return MLAMG_OK;
+}
+
+double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int zero_guess) {
+    if (!h) return 0.0;
+    const double v = (double)h->esz;
+    const int L = (int)h->lv.size();
+    double total = 0.0;
+    for (int l = 0; l < L - 1; l++) {
+        const LevelData &lev = h->lv[l];
+        const double N = lev.A.n, nnz = (double)lev.A.nnz, Nc = h->lv[l + 1].A.n, pnnz = (double)lev.P.nnz;
+        const double b_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N;
+        const double b_res = nnz * (v + 4) + 4 * (N + 1) + 3 * v * N;
+        const double b_restrict = pnnz * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc;
+        const double b_prolong = pnnz * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N;
+        const bool zero = (l > 0) || zero_guess;
+        double pre = nu1 * b_jac;
+        if (zero && nu1 > 0) pre = (nu1 - 1) * b_jac + 3 * v * N;   // x = dw.*b : read dw,b write x
+        total += pre + nu2 * b_jac + b_res + b_restrict + b_prolong;
+    }
+    const double nc = h->lv[L - 1].A.n;
+    total += nc * nc * v + 2 * nc * v;   // dense inverse GEMV
+    return total;
+}
+
+int mlamg_vcycle(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, int zero_guess, mlamg_stream_t stream) {
+    MLAMG_TRY(check_handle(h));
+    return vcycle_run(h, b, x, nu1, nu2, zero_guess, as_stream(stream));
+}
+
+int mlamg_solve(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double tol_abs, int maxiter,
+                double *res_host, int *niter_host, mlamg_stream_t stream) {
+    MLAMG_TRY(check_handle(h));
+    cudaStream_t s = as_stream(stream);
+    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
+    if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "solve: bad maxiter/res_host");
+    MLAMG_TRY(ensure_pcg(h));
+    const Csr &A = h->lv[0].A;
+    int it = 0;
+    double nrm2 = 0.0;
+    MLAMG_TRY(mlamg_residual_csr(h->dtype, A.n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, h->pcg_r, h->dscal, stream));
+    MLAMG_TRY(fetch_scalar(h, 0, &nrm2, s));
+    res_host[0] = sqrt(nrm2);
+    while (it < maxiter && !(res_host[it] <= tol_abs)) {
+        MLAMG_TRY(vcycle_run(h, b, x, nu1, nu2, 0, s));
+        MLAMG_TRY(mlamg_residual_csr(h->dtype, A.n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, h->pcg_r, h->dscal, stream));
+        MLAMG_TRY(fetch_scalar(h, 0, &nrm2, s));
+        it++;
+        res_host[it] = sqrt(nrm2);
+    }
+    if (niter_host) *niter_host = it;
+    return MLAMG_OK;
+}
+
+int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter, double *res_host,
+              int *niter_host, mlamg_stream_t stream) {
+    MLAMG_TRY(check_handle(h));
+    cudaStream_t s = as_stream(stream);
+    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
+    if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "pcg: bad maxiter/res_host");
+    MLAMG_TRY(ensure_pcg(h));
+    const Csr &A = h->lv[0].A;
+    const int n = A.n, dt = h->dtype;
+    void *r = h->pcg_r, *z = h->pcg_z, *p = h->pcg_p, *ap = h->pcg_ap;
+    double bb = 0.0, rr = 0.0, rz = 0.0, pap = 0.0;
+    MLAMG_TRY(mlamg_dot(dt, n, b, b, h->dscal + 1, stream));
+    MLAMG_TRY(mlamg_residual_csr(dt, n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, r, h->dscal, stream));
+    MLAMG_TRY(fetch_scalar(h, 1, &bb, s));
+    MLAMG_TRY(fetch_scalar(h, 0, &rr, s));
+    const double nb = sqrt(bb);
+    const double stop = rtol * (nb != 0.0 ? nb : 1.0);
+    res_host[0] = sqrt(rr);
+    int it = 0;
+    if (res_host[0] <= stop || maxiter == 0) { if (niter_host) *niter_host = 0; return MLAMG_OK; }
+    MLAMG_TRY(vcycle_run(h, r, z, nu1, nu2, 1, s));
+    MLAMG_CUDA(cudaMemcpyAsync(p, z, (size_t)n * h->esz, cudaMemcpyDeviceToDevice, s));
+    MLAMG_TRY(mlamg_dot(dt, n, r, z, h->dscal + 2, stream));
+    MLAMG_TRY(fetch_scalar(h, 2, &rz, s));
+    for (it = 1; it <= maxiter; it++) {
+        MLAMG_TRY(mlamg_spmv_csr(dt, n, (int)A.nnz, A.rowptr, A.col, A.val, p, ap, stream));
+        MLAMG_TRY(mlamg_dot(dt, n, p, ap, h->dscal + 3, stream));
+        MLAMG_TRY(fetch_scalar(h, 3, &pap, s));
+        const double alpha = rz / pap;
+        MLAMG_TRY(mlamg_axpby(dt, n, alpha, p, 1.0, x, stream));
+        MLAMG_TRY(mlamg_axpby(dt, n, -alpha, ap, 1.0, r, stream));
+        MLAMG_TRY(mlamg_dot(dt, n, r, r, h->dscal, stream));
+        MLAMG_TRY(fetch_scalar(h, 0, &rr, s));
+        res_host[it] = sqrt(rr);
+        if (res_host[it] <= stop) break;
+        if (it == maxiter) break;
+        MLAMG_TRY(vcycle_run(h, r, z, nu1, nu2, 1, s));
+        double rz_new = 0.0;
+        MLAMG_TRY(mlamg_dot(dt, n, r, z, h->dscal + 2, stream));
+        MLAMG_TRY(fetch_scalar(h, 2, &rz_new, s));
+        const double beta = rz_new / rz;
+        rz = rz_new;
+        MLAMG_TRY(mlamg_axpby(dt, n, 1.0, z, beta, p, stream));
+    }
+    if (it > maxiter) it = maxiter;
+    if (niter_host) *niter_host = it;
+    return MLAMG_OK;
+}
+
+int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int nu1, int nu2, int cycles,
+                      mlamg_stream_t stream) {
+    MLAMG_TRY(check_handle(h));
+    cudaStream_t s = as_stream(stream);
+    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
+    if (cycles < 1) return set_error(MLAMG_EINVAL, "vcycle_host: cycles < 1");
+    const size_t bytes = (size_t)h->lv[0].A.n * h->esz;
+    if (!h->host_b) {
+        MLAMG_CUDA(cudaMalloc(&h->host_b, bytes));
+        MLAMG_CUDA(cudaMalloc(&h->host_x, bytes));
+    }
+    MLAMG_CUDA(cudaMemcpyAsync(h->host_b, b_host, bytes, cudaMemcpyHostToDevice, s));
+    MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 1, s));
+    for (int c = 1; c < cycles; c++) MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 0, s));
+    MLAMG_CUDA(cudaMemcpyAsync(x_host, h->host_x, bytes, cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    return MLAMG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""ctypes binding of libmlamg_b200.so (include/mlamg.h).
+
+There is NO CPU fallback: if the shared library is missing or cannot be loaded this module raises
+ImportError, and every compute wrapper raises RuntimeError when CUDA is unavailable.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmlamg_b200.so")
+
+F32, F64 = 0, 1
+OK, EINVAL, ECUDA, ELIMIT, ESINGULAR, EKEY = 0, 1, 2, 3, 4, 5
+
+I = ctypes.c_int
+LL = ctypes.c_longlong
+D = ctypes.c_double
+P = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/mlamg.h one to one
+SIGNATURES = {
+    "mlamg_last_error": (ctypes.c_char_p, []),
+    "mlamg_version": (I, []),
+    "mlamg_launch_count": (LL, []),
+    "mlamg_spmv_csr": (I, [I, I, I, P, P, P, P, P, P]),
+    "mlamg_spmv_add_csr": (I, [I, I, I, P, P, P, P, P, P]),
+    "mlamg_residual_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
+    "mlamg_jacobi_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
+    "mlamg_jacobi_zero": (I, [I, I, P, P, P, P]),
+    "mlamg_smoother_diag": (I, [I, I, D, I, P, P, P, P, P]),
+    "mlamg_spmm_csr": (I, [I, I, I, P, P, P, P, P, D, D, P]),
+    "mlamg_axpby": (I, [I, I, D, P, D, P, P]),
+    "mlamg_dot": (I, [I, I, P, P, P, P]),
+    "mlamg_gs_schedule": (I, [I, P, P, P, P, P, P, P]),
+    "mlamg_gauss_seidel": (I, [I, I, P, P, P, P, P, P, P, I, P]),
+    "mlamg_scan_i32": (I, [P, P, I, P]),
+    "mlamg_agg_from_labels": (I, [I, I, P, P, P, P, P, P]),
+    "mlamg_center_rank_labels": (I, [I, I, P, P, P, P, P]),
+    "mlamg_sa_smoother_values": (I, [I, I, P, P, P, D, P, P]),
+    "mlamg_spgemm_symbolic": (I, [I, I, I, P, P, P, P, P, P, P]),
+    "mlamg_spgemm_numeric": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
+    "mlamg_csr_transpose": (I, [I, I, I, I, P, P, P, P, P, P, P]),
+    "mlamg_csr_nonzero_count": (I, [I, I, P, P, P, P, P]),
+    "mlamg_csr_nonzero_fill": (I, [I, I, P, P, P, P, P, P, P]),
+    "mlamg_csr_sort_rows": (I, [I, I, P, P, P, P]),
+    "mlamg_csr_to_dense": (I, [I, I, P, P, P, P, P]),
+    "mlamg_dense_inverse_f64": (I, [I, P, P, P]),
+    "mlamg_gemv": (I, [I, I, P, P, P, P]),
+    "mlamg_lambda_max": (I, [I, I, P, P, P, I, P, P, P]),
+    "mlamg_poisson_nnz": (LL, [I, I, I]),
+    "mlamg_poisson_csr": (I, [I, I, I, I, P, P, P, P]),
+    "mlamg_bellman_ford": (I, [I, I, P, P, P, I, P, P, P, P, P]),
+    "mlamg_lloyd_cluster": (I, [I, I, P, P, P, I, P, I, P, P, P, P]),
+    "mlamg_modified_bellman_ford": (I, [I, P, P, P, I, P, P, P, P, P]),
+    "mlamg_hierarchy_create": (I, [I, I, P]),
+    "mlamg_hierarchy_set_operator": (I, [P, I, I, I, P, P, P, P]),
+    "mlamg_hierarchy_set_transfer": (I, [P, I, I, P, P, P, P, P, P]),
+    "mlamg_hierarchy_set_coarse_inverse": (I, [P, P]),
+    "mlamg_hierarchy_finalize": (I, [P, P]),
+    "mlamg_hierarchy_destroy": (I, [P]),
+    "mlamg_hierarchy_cycle_bytes": (D, [P, I, I, I]),
+    "mlamg_hierarchy_use_graph": (I, [P, I]),
+    "mlamg_vcycle": (I, [P, P, P, I, I, I, P]),
+    "mlamg_solve": (I, [P, P, P, I, I, D, I, P, P, P]),
+    "mlamg_pcg": (I, [P, P, P, I, I, D, I, P, P, P]),
+    "mlamg_vcycle_host": (I, [P, P, P, I, I, I, P]),
+}
+
+
+class MlamgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mlamg error {code}: {msg}")
+        self.code = code
+
+
+class SingularCoarseError(MlamgError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python ml-amg_b200/build.py` "
+            "(there is no CPU fallback for the mlamg hot path)")
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc == OK:
+        return
+    msg = lib.mlamg_last_error().decode("utf-8", "replace")
+    if rc == ESINGULAR:
+        raise SingularCoarseError(rc, msg)
+    if rc == EKEY:
+        raise KeyError(msg)
+    raise MlamgError(rc, msg)
+
+
+def launch_count():
+    return int(lib.mlamg_launch_count())

@@ -1,0 +1,265 @@
+"""Aggregation-AMG hierarchy on the device: setup from A + aggregates (+ optional learned P
+weights), V-cycle / stationary / PCG solves, preconditioner apply.
+
+API shape follows what the reference uses of pyamg's multilevel solver
+(ns/preconditioner/PyAMG.py:94,119: `smoothed_aggregation_solver(A, max_levels)`,
+`.solve(b, tol, accel)`, `.aspreconditioner()`), built from the reference's own blocks:
+Lloyd aggregates (ns/lib/graph.py:156-239), P = (I - w D^-1 A) Agg (ns/lib/multigrid.py:102-108)
+or P = P_hat Agg (ns/model/agg_interp.py:481-484), A_H = P^T A P (multigrid.py:165), Jacobi
+smoothing (MLAMG.py:143-146).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import core
+from ._lib import lib, check
+from .core import DeviceCSR, ptr, stream
+
+
+def distance_transform(C, distance):
+    """Edge-length transform of ns/lib/graph.py:201-212 on the device."""
+    v = C.val
+    if distance == "unit":
+        data = torch.ones(v.numel(), dtype=torch.float64, device=v.device)
+    elif distance == "abs":
+        data = v.abs()
+    elif distance == "inv":
+        data = 1.0 / v.abs()
+    elif distance == "same":
+        data = v
+    elif distance == "min":
+        data = v - v.min()
+    else:
+        raise ValueError(f"Unrecognized value distance={distance}")
+    if data.numel() and float(data.min().item()) < 0:
+        raise AssertionError("lloyd_aggregation: negative edge length")
+    return C.with_values(data)
+
+
+def lloyd_seeds(N, ratio, rand):
+    """Seeding of ns/lib/graph.py:214-231 (host RNG: it defines the reference's seeds)."""
+    if ratio <= 0 or ratio > 1:
+        raise ValueError("ratio must be > 0.0 and <= 1.0")
+    if rand is None:
+        rand = np.random
+    elif isinstance(rand, (int, np.integer)):
+        rand = np.random.RandomState(int(rand))
+    elif not isinstance(rand, np.random.RandomState):
+        raise TypeError("rand should be an integer seed value or a random state")
+    num_seeds = int(np.ceil(ratio * N))
+    return rand.permutation(N)[:num_seeds]
+
+
+def lloyd_labels(C, ratio=0.03, distance="unit", maxiter=10, rand=None):
+    """-> (labels int32[N] device, num_seeds, roots device, seeds host)."""
+    G = distance_transform(C, distance)
+    seeds = lloyd_seeds(C.shape[0], ratio, rand)
+    _, clusters, roots, _ = core.lloyd_cluster(G, seeds.astype(np.int32), maxiter=maxiter)
+    return clusters, len(seeds), roots, seeds
+
+
+def sa_prolongator(A, Agg, omega, drop=True):
+    """P = (I - omega D^-1 A) Agg with scipy's stored-pattern semantics (exact zeros dropped)."""
+    P = core.spgemm(core.sa_smoother(A, omega), Agg if Agg.dtype == A.dtype else Agg.astype(A.dtype))
+    return core.drop_zeros(P) if drop else P
+
+
+def learned_prolongator(P_hat, Agg, drop=False):
+    """P = P_hat Agg (torch.sparse.mm + coalesce keeps explicit zeros -> drop=False)."""
+    P = core.spgemm(P_hat, Agg if Agg.dtype == P_hat.dtype else Agg.astype(P_hat.dtype))
+    return core.drop_zeros(P) if drop else P
+
+
+def galerkin(A, P, R=None, drop=True):
+    """A_H = P^T A P (R = P^T reused when given)."""
+    if R is None:
+        R = core.transpose(P)
+    AH = core.spgemm(R, core.spgemm(A, P))
+    return core.drop_zeros(AH) if drop else AH
+
+
+class Level:
+    __slots__ = ("A", "P", "R", "dw", "labels", "omega_sa", "seeds", "roots")
+
+    def __init__(self, A):
+        self.A = A
+        self.P = self.R = self.dw = self.labels = self.omega_sa = self.seeds = self.roots = None
+
+
+class Hierarchy:
+    """Owns the device arrays of every level and the C handle that runs the cycles."""
+
+    def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False):
+        core.require_cuda()
+        self.levels = levels
+        self.dtype = levels[0].A.dtype
+        self.smoother = smoother
+        for lev in levels[:-1]:
+            if lev.dw is None:
+                lev.dw = core.smoother_diag(lev.A, smoother, jacobi_weight)
+        self.coarse_inv = core.dense_inverse(levels[-1].A)
+        self._h = ctypes.c_void_p()
+        check(lib.mlamg_hierarchy_create(core.dt(self.dtype), len(levels), ctypes.byref(self._h)))
+        for l, lev in enumerate(levels):
+            A = lev.A
+            check(lib.mlamg_hierarchy_set_operator(self._h, l, A.shape[0], A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val),
+                                                   ptr(lev.dw)))
+        for l, lev in enumerate(levels[:-1]):
+            P, R = lev.P, lev.R
+            check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
+                                                   ptr(R.rowptr), ptr(R.col), ptr(R.val)))
+        check(lib.mlamg_hierarchy_set_coarse_inverse(self._h, ptr(self.coarse_inv)))
+        check(lib.mlamg_hierarchy_finalize(self._h, stream()))
+        if use_graph:
+            self.use_graph(True)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            lib.mlamg_hierarchy_destroy(h)
+            self._h = None
+
+    # -- info -------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return self.levels[0].A.shape
+
+    def use_graph(self, enable=True):
+        check(lib.mlamg_hierarchy_use_graph(self._h, 1 if enable else 0))
+
+    def cycle_bytes(self, nu1=1, nu2=1, zero_guess=True):
+        return float(lib.mlamg_hierarchy_cycle_bytes(self._h, nu1, nu2, 1 if zero_guess else 0))
+
+    def operator_complexity(self):
+        return sum(l.A.nnz for l in self.levels) / self.levels[0].A.nnz
+
+    def __repr__(self):
+        rows = [f"  level {i}: n={l.A.shape[0]:>10d} nnz={l.A.nnz:>12d}" for i, l in enumerate(self.levels)]
+        return (f"mlamg Hierarchy({len(self.levels)} levels, {self.dtype}, smoother={self.smoother}, "
+                f"operator complexity {self.operator_complexity():.3f})\n" + "\n".join(rows))
+
+    # -- cycles -----------------------------------------------------------------------------
+    def vcycle(self, b, x=None, nu1=1, nu2=1):
+        """One V(nu1,nu2) cycle.  x=None: zero initial guess (preconditioner apply), result returned;
+        otherwise x is updated in place."""
+        zero = x is None
+        if zero:
+            x = torch.empty_like(b)
+        check(lib.mlamg_vcycle(self._h, ptr(b), ptr(x), nu1, nu2, 1 if zero else 0, stream()))
+        return x
+
+    def solve(self, b, x0=None, tol=1e-8, maxiter=100, nu1=1, nu2=1, cycle="V", accel=None, residuals=None,
+              return_residuals=False):
+        """pyamg-style solve.  accel=None: stationary V-cycles until ||b-Ax|| <= tol*||b|| ;
+        accel='cg': V-cycle preconditioned CG.  Accepts numpy or CUDA tensors, returns the same kind."""
+        if cycle != "V":
+            raise NotImplementedError("only V cycles are built on this path")
+        is_np = isinstance(b, np.ndarray)
+        bd = core.as_vec(b, self.dtype)
+        xd = torch.zeros_like(bd) if x0 is None else core.as_vec(x0, self.dtype).clone()
+        res = (ctypes.c_double * (maxiter + 1))()
+        nit = ctypes.c_int(0)
+        if accel is None:
+            nb = float(torch.linalg.vector_norm(bd).item())
+            check(lib.mlamg_solve(self._h, ptr(bd), ptr(xd), nu1, nu2, tol * (nb if nb != 0 else 1.0), maxiter, res,
+                                  ctypes.byref(nit), stream()))
+        elif accel == "cg":
+            check(lib.mlamg_pcg(self._h, ptr(bd), ptr(xd), nu1, nu2, tol, maxiter, res, ctypes.byref(nit), stream()))
+        else:
+            raise NotImplementedError(f"accel={accel!r}: only None and 'cg' are built (the reference's gmres "
+                                      "acceleration lives in pyamg, PyAMG.py:119)")
+        hist = np.array(res[:nit.value + 1])
+        if residuals is not None:
+            residuals[:] = list(hist)
+        out = xd.cpu().numpy() if is_np else xd
+        return (out, hist) if return_residuals else out
+
+    def solve_abs(self, b, x, tol_abs, maxiter, nu1=1, nu2=1):
+        """Stationary iteration with an ABSOLUTE residual tolerance (MLAMG.py:189-195), device tensors."""
+        res = (ctypes.c_double * (maxiter + 1))()
+        nit = ctypes.c_int(0)
+        check(lib.mlamg_solve(self._h, ptr(b), ptr(x), nu1, nu2, float(tol_abs), maxiter, res, ctypes.byref(nit), stream()))
+        return x, np.array(res[:nit.value + 1])
+
+    def apply_host(self, b_host, x_host, nu1=1, nu2=1, cycles=1):
+        """Preconditioner apply on HOST arrays (PETSc PC.apply shape): H2D, V-cycle(s), D2H inside the call.
+        b_host/x_host: numpy arrays or CPU tensors (pinned memory gives the best copy rate)."""
+        bp = b_host.ctypes.data if isinstance(b_host, np.ndarray) else b_host.data_ptr()
+        xp = x_host.ctypes.data if isinstance(x_host, np.ndarray) else x_host.data_ptr()
+        check(lib.mlamg_vcycle_host(self._h, ctypes.c_void_p(bp), ctypes.c_void_p(xp), nu1, nu2, cycles, stream()))
+        return x_host
+
+    def aspreconditioner(self, cycle="V", nu1=1, nu2=1):
+        from scipy.sparse.linalg import LinearOperator
+        n = self.shape[0]
+        npdt = np.float64 if self.dtype == torch.float64 else np.float32
+
+        def matvec(b):
+            b = np.ascontiguousarray(b, dtype=npdt).ravel()
+            x = np.empty_like(b)
+            self.apply_host(b, x, nu1, nu2, 1)
+            return x
+        return LinearOperator((n, n), matvec=matvec, dtype=npdt)
+
+
+def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
+                    P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
+                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000):
+    """Build the multilevel hierarchy on the device.
+
+    A           : scipy / torch sparse / DeviceCSR
+    aggregates  : 'lloyd' (Lloyd clustering per level, reference seeding) or a list of
+                  (labels, ncoarse) per level (learned / external aggregates)
+    P_hat       : optional list of per-level weights on A_l's pattern (learned P = P_hat Agg)
+    lam_max     : |lambda_max(D^-1 A)| per level: None -> on-device power iteration; float, list or
+                  callable(DeviceCSR) -> supplied (parity runs pass the oracle's value)
+    """
+    core.require_cuda()
+    A = DeviceCSR.wrap(A, dtype)
+    levels = []
+    lvl = 0
+    while True:
+        L = Level(A)
+        levels.append(L)
+        n = A.shape[0]
+        if len(levels) >= max_levels or n <= max_coarse:
+            break
+        if isinstance(aggregates, str):
+            if aggregates != "lloyd":
+                raise ValueError(f"unknown aggregation strategy {aggregates!r}")
+            labels, nc, roots, seeds = lloyd_labels(A, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand)
+            L.roots, L.seeds = roots, seeds
+        else:
+            if lvl >= len(aggregates):
+                break
+            labels, nc = aggregates[lvl]
+            labels = core.as_i32(labels)
+        Agg = core.agg_from_labels(labels, nc, A.dtype)
+        if keep_labels:
+            L.labels = labels
+        if P_hat is not None and lvl < len(P_hat) and P_hat[lvl] is not None:
+            ph = P_hat[lvl]
+            ph = ph if isinstance(ph, DeviceCSR) else A.with_values(core.as_vec(ph, A.dtype))
+            P = learned_prolongator(ph, Agg)
+        else:
+            if callable(lam_max):
+                lam = lam_max(A)
+            elif lam_max is None:
+                lam = core.lambda_max(A)
+            elif np.isscalar(lam_max):
+                lam = float(lam_max)
+            else:
+                lam = float(lam_max[lvl])
+            L.omega_sa = (4.0 / 3.0) / lam
+            P = sa_prolongator(A, Agg, L.omega_sa)
+        L.P = P
+        L.R = core.transpose(P)
+        A = galerkin(L.A, P, L.R)
+        lvl += 1
+    if levels[-1].A.shape[0] > max_dense:
+        raise _lib.MlamgError(_lib.ELIMIT, f"coarsest level has {levels[-1].A.shape[0]} rows; raise max_levels or "
+                                           f"lower max_coarse (dense coarse solve limit {max_dense})")
+    return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph)

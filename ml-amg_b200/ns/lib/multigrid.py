@@ -1,0 +1,211 @@
+"""Drop-in mirror of the reference's `ns.lib.multigrid` on the B200 kernels.
+
+Reference: /root/reference/ns/lib/multigrid.py
+  jacobi :15-45, jacobi_torch :48-55, gauss_seidel :58-90, smoothed_aggregation_jacobi :102-108,
+  amg_2_v :111-210, amg_2_v_torch :213-245.
+Same names, argument order, defaults, return tuples and error behaviour; numpy/scipy in -> numpy
+out, torch in -> torch out.  Extra keyword arguments (always last, optional) expose what the GPU
+path adds: `smoother=` on amg_2_v ('gauss_seidel' = the reference's pyamg sweep, exact;
+'jacobi' / 'l1_jacobi' = the fused kernels) and `omega=` / `lam_max=` on
+smoothed_aggregation_jacobi (the reference calls ARPACK, 60-160 s).
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+import mlamg
+from mlamg import core, SingularCoarseError
+
+
+def _diag_vector(Dinv, n):
+    if Dinv is None:
+        return None
+    if sp.issparse(Dinv):
+        return np.asarray(Dinv.diagonal())
+    Dinv = np.asarray(Dinv)
+    return np.diag(Dinv) if Dinv.ndim == 2 else Dinv
+
+
+def jacobi(A, b, x, Dinv=None, omega=0.666, nu=2):
+    """Weighted Jacobi, x updated in place and returned:  x += omega Dinv b - omega Dinv A x."""
+    Ad = core.DeviceCSR.wrap(A)
+    dv = _diag_vector(Dinv, Ad.shape[0])
+    if dv is None:
+        dw = core.smoother_diag(Ad, "jacobi", omega)
+    else:
+        dw = core.as_vec(np.asarray(dv, dtype=np.float64) * omega, Ad.dtype)
+    bd = core.as_vec(np.asarray(b), Ad.dtype)
+    xd = core.as_vec(np.asarray(x), Ad.dtype).clone()
+    tmp = torch.empty_like(xd)
+    for _ in range(nu):
+        core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+        xd, tmp = tmp, xd
+    x[...] = xd.cpu().numpy()
+    return x
+
+
+def jacobi_torch(A, b, x, Dinv=None, omega=0.666, nu=2):
+    """Torch twin.  As in the reference (:49-50), Dinv=None uses the diagonal itself, not its inverse;
+    callers pass 1/diag (:220)."""
+    Ad = core.DeviceCSR.wrap(A)
+    dev = x.device
+    if Dinv is None:
+        Dinv = 1.0 / core.smoother_diag(Ad, "jacobi", 1.0)      # = diag(A)
+    dw = (omega * Dinv).to(device="cuda", dtype=Ad.dtype).contiguous()
+    bd = b.to(device="cuda", dtype=Ad.dtype).contiguous()
+    xd = x.to(device="cuda", dtype=Ad.dtype).contiguous().clone()
+    tmp = torch.empty_like(xd)
+    for _ in range(nu):
+        core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+        xd, tmp = tmp, xd
+    x.copy_(xd.to(dev))
+    return x
+
+
+def gauss_seidel(A, b, x, L=None, U=None, nu=2):
+    """x <- L^-1 (b - U x), nu times (forward Gauss-Seidel); returns the new iterate."""
+    Ad = core.DeviceCSR.wrap(A)
+    sched = core.GaussSeidelSchedule(Ad)
+    bd = core.as_vec(np.asarray(b), Ad.dtype)
+    xd = core.as_vec(np.asarray(x), Ad.dtype).clone()
+    sched.sweep(bd, xd, iterations=nu)
+    return xd.cpu().numpy()
+
+
+def smoothed_aggregation_jacobi(A, Agg, omega=None, lam_max=None):
+    """P = (I - omega D^-1 A) Agg with omega = (4/3)/|lambda_max(D^-1 A)|; scipy CSR out."""
+    Ad = core.DeviceCSR.wrap(A)
+    if omega is None:
+        if lam_max is None:
+            lam_max = core.lambda_max(Ad)
+        omega = (4.0 / 3.0) / lam_max
+    Aggd = core.DeviceCSR.wrap(sp.csr_matrix(Agg).astype(np.float64 if Ad.dtype == torch.float64 else np.float32))
+    return mlamg.sa_prolongator(Ad, Aggd, omega).to_scipy()
+
+
+class _TwoLevel:
+    """Device state of the two-level cycle shared by amg_2_v / amg_2_v_torch / the PC plugin."""
+
+    def __init__(self, A, P, singular=False):
+        self.A = core.DeviceCSR.wrap(A)
+        self.P = core.DeviceCSR.wrap(P, self.A.dtype)
+        self.R = core.transpose(self.P)
+        self.AH = mlamg.galerkin(self.A, self.P, self.R)
+        if singular:
+            # lsqr min-norm solve of the singular coarse problem (:179) -> dense pseudo-inverse
+            dense = torch.zeros(self.AH.shape, dtype=torch.float64, device="cuda")
+            core.check(core.lib.mlamg_csr_to_dense(1, self.AH.shape[0], core.ptr(self.AH.rowptr), core.ptr(self.AH.col),
+                                                   core.ptr(self.AH.astype(torch.float64).val), core.ptr(dense),
+                                                   core.stream()))
+            self.AHinv = torch.linalg.pinv(dense).to(self.A.dtype).contiguous()
+        else:
+            self.AHinv = core.dense_inverse(self.AH)
+        n = self.A.shape[0]
+        self.r = torch.empty(n, dtype=self.A.dtype, device="cuda")
+        self.rc = torch.empty(self.AH.shape[0], dtype=self.A.dtype, device="cuda")
+        self.ec = torch.empty_like(self.rc)
+
+    def coarse_correct(self, b, x):
+        core.residual(self.A, x, b, out=self.r)
+        core.spmv(self.R, self.r, out=self.rc)
+        core.gemv(self.AHinv, self.rc, out=self.ec)
+        core.spmv_add(self.P, self.ec, x)
+
+
+def amg_2_v(A, P, b, x,
+            pre_smoothing_steps=1,
+            post_smoothing_steps=1,
+            jacobi_weight=0.666,
+            res_tol=None,
+            error_tol=None,
+            max_iter=500,
+            singular=False,
+            smoother='gauss_seidel'):
+    """Two-level AMG solver -> (x, conv_factor, err, num_iterations)  (reference :111-210).
+
+    Tolerances are absolute; err[i] = ||b - A x||_2 if res_tol is set else ||x||_2; a singular
+    coarse operator returns (x, 1.0, err, 0) without raising, as the reference does."""
+    if res_tol is None and error_tol is None:
+        raise RuntimeError('One of res_tol or error_tol must be set!')
+    tol = res_tol if res_tol is not None else error_tol
+    err = np.zeros(max_iter)
+    try:
+        tl = _TwoLevel(A, P, singular=singular)
+    except SingularCoarseError:
+        return x, np.float64(1.), err, 0
+    Ad = tl.A
+    bd = core.as_vec(np.asarray(b), Ad.dtype)
+    xd = core.as_vec(np.asarray(x), Ad.dtype).clone()
+    tmp = torch.empty_like(xd)
+    if smoother == 'gauss_seidel':
+        sched = core.GaussSeidelSchedule(Ad)
+    elif smoother in ('jacobi', 'l1_jacobi'):
+        dw = core.smoother_diag(Ad, smoother, jacobi_weight)
+    else:
+        raise ValueError(f'unknown smoother {smoother!r}')
+
+    def relax(xd, tmp, steps):
+        if smoother == 'gauss_seidel':
+            sched.sweep(bd, xd, iterations=steps)
+            return xd, tmp
+        for _ in range(steps):
+            core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+            xd, tmp = tmp, xd
+        return xd, tmp
+
+    for i in range(max_iter):
+        xd, tmp = relax(xd, tmp, pre_smoothing_steps)
+        tl.coarse_correct(bd, xd)
+        xd, tmp = relax(xd, tmp, post_smoothing_steps)
+        if singular:
+            xd -= xd.mean()
+        if res_tol is not None:
+            _, e = core.residual(Ad, xd, bd, out=tl.r, norm=True)
+        else:
+            e = float(np.sqrt(core.dot(xd, xd)))
+        err[i] = e
+        if e <= tol:
+            err = err[:i + 1]
+            break
+
+    if len(err) != 1:
+        try:
+            err_n = min(len(err) // 3, 10)
+            conv_factor = (err[-1] / err[-err_n]) ** (1 / (err_n - 1))
+        except Exception:
+            conv_factor = 0
+    else:
+        conv_factor = 0
+    return xd.cpu().numpy().astype(np.asarray(x).dtype, copy=False), conv_factor, err, len(err)
+
+
+def amg_2_v_torch(A, P, b, x,
+                  pre_smoothing_steps=1,
+                  post_smoothing_steps=1,
+                  jacobi_weight=0.666,
+                  error_tol=1e-10,
+                  max_iter=20):
+    """Torch twin with Jacobi smoothing and a dense coarse solve (reference :213-245);
+    returns the convergence-factor estimate (err[i]/err[i-3])^(1/2) as a 0-dim tensor."""
+    device = A.device
+    tl = _TwoLevel(A, P)
+    Ad = tl.A
+    dw = core.smoother_diag(Ad, 'jacobi', jacobi_weight)
+    bd = b.to(device="cuda", dtype=Ad.dtype).contiguous()
+    xd = x.to(device="cuda", dtype=Ad.dtype).contiguous().clone()
+    tmp = torch.empty_like(xd)
+    err = torch.zeros(max_iter, dtype=Ad.dtype)
+    i = 0
+    for i in range(max_iter):
+        for _ in range(pre_smoothing_steps):
+            core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+            xd, tmp = tmp, xd
+        tl.coarse_correct(bd, xd)
+        for _ in range(post_smoothing_steps):
+            core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+            xd, tmp = tmp, xd
+        err[i] = float(np.sqrt(core.dot(xd, xd)))
+        if err[i] < error_tol:
+            break
+    n_err = 3
+    return ((err[i] / err[i - n_err]) ** (1 / (n_err - 1))).to(device)

@@ -1,0 +1,82 @@
+"""Shared test helpers (CPU side): golden loading, canonical comparisons, problem generators."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["poisson2d_24_unit", "poisson3d_10_unit", "laplace3d_grid_abs", "laplace3d_grid_inv", "randw_same"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"), allow_pickle=False)
+    return z
+
+
+def csr_from(z, prefix):
+    return sp.csr_matrix((z[f"{prefix}_data"], z[f"{prefix}_indices"], z[f"{prefix}_indptr"]),
+                         shape=tuple(int(v) for v in z[f"{prefix}_shape"]))
+
+
+def canonical(M, drop_zeros=True):
+    M = sp.csr_matrix(M).copy()
+    M.sum_duplicates()
+    if drop_zeros:
+        M.eliminate_zeros()
+    M.sort_indices()
+    return M
+
+
+def assert_same_pattern(X, Y):
+    X, Y = canonical(X), canonical(Y)
+    assert X.shape == Y.shape
+    assert np.array_equal(X.indptr, Y.indptr), "row pointers differ"
+    assert np.array_equal(X.indices, Y.indices), "column indices differ"
+
+
+def assert_csr_close(X, Y, rtol):
+    """pattern bit-exact (canonical form), values within rtol relative to the largest entry"""
+    assert_same_pattern(X, Y)
+    X, Y = canonical(X), canonical(Y)
+    scale = max(np.abs(Y.data).max(), 1e-300) if Y.nnz else 1.0
+    err = np.abs(X.data - Y.data).max() / scale if Y.nnz else 0.0
+    assert err <= rtol, f"max relative value error {err:.3e} > {rtol:.1e}"
+
+
+def rel_hist_err(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    n = min(len(a), len(b))
+    return np.max(np.abs(a[:n] - b[:n]) / np.maximum(np.abs(b[:n]), 1e-300))
+
+
+def random_csr(n, m, density, seed, dtype=np.float64, empty_rows=True):
+    rs = np.random.RandomState(seed)
+    A = sp.random(n, m, density=density, random_state=rs, format="csr", dtype=np.float64)
+    A.data = rs.randn(A.nnz)
+    if empty_rows and n > 3:
+        A = sp.csr_matrix(A.multiply(sp.csr_matrix((np.arange(n) % 7 != 3).astype(float)).T))   # some empty rows
+    A = sp.csr_matrix(A).astype(dtype)
+    A.sort_indices()
+    return A
+
+
+def grid_graph(shape, weights="unit", seed=0, dtype=np.float64, symmetric=True):
+    """graph of a Dirichlet Poisson stencil (incl. the diagonal entry, as the reference passes A itself)"""
+    from oracle import multilevel as oml
+    A = oml.poisson(shape)
+    rs = np.random.RandomState(seed)
+    if weights == "unit":
+        data = np.ones(A.nnz)
+    elif weights == "random":
+        data = rs.rand(A.nnz) + 0.05
+        if symmetric:
+            G = sp.csr_matrix((data, A.indices, A.indptr), shape=A.shape)
+            G = G.maximum(G.T)
+            G.sort_indices()
+            return G.astype(dtype)
+    elif weights == "relu":      # GNN-like fp32 outputs: many exact zeros and tiny values
+        data = np.maximum(rs.randn(A.nnz), 0.0) * (10.0 ** rs.randint(-6, 1, A.nnz))
+    else:
+        raise ValueError(weights)
+    return sp.csr_matrix((data.astype(dtype), A.indices, A.indptr), shape=A.shape)

@@ -1,0 +1,220 @@
+"""GPU: every apply/setup kernel through the C ABI against scipy on the same seeded inputs.
+Tolerances: fp64 1e-13 relative to the result scale (summation order differs from scipy's serial
+loop), fp32 1e-5 (north-star tolerance)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from helpers import random_csr, assert_csr_close, assert_same_pattern
+from oracle import multilevel as oml
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-13, np.float32: 1e-5}
+TDT = {np.float64: torch.float64, np.float32: torch.float32}
+
+
+def dev(x, dtype):
+    return torch.from_numpy(np.ascontiguousarray(x)).to("cuda", TDT[dtype])
+
+
+def close(got, ref, dtype, scale=None):
+    got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+    s = np.abs(ref).max() if scale is None else scale
+    err = np.abs(got - ref).max() / max(s, 1e-300)
+    assert err <= TOL[dtype], f"error {err:.3e}"
+
+
+MATS = {
+    "poisson2d": lambda: oml.poisson((33, 17)),
+    "poisson3d": lambda: oml.poisson((12, 9, 7)),
+    "random_sparse": lambda: random_csr(500, 500, 0.01, 1),
+    "random_dense_rows": lambda: random_csr(300, 400, 0.2, 2),
+    "rect_wide": lambda: random_csr(50, 700, 0.05, 3),
+    "single_row": lambda: random_csr(1, 40, 0.5, 4, empty_rows=False),
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", list(MATS))
+def test_spmv_residual_jacobi(name, dtype):
+    import mlamg
+    A = MATS[name]().astype(dtype)
+    n, m = A.shape
+    rs = np.random.RandomState(0)
+    x, b = rs.randn(m).astype(dtype), rs.randn(n).astype(dtype)
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    xd, bd = dev(x, dtype), dev(b, dtype)
+    y = mlamg.spmv(Ad, xd)
+    scale = (abs(A) @ np.abs(x)).max()
+    close(y, A @ x, dtype, scale)
+    r, nrm = mlamg.residual(Ad, xd, bd, norm=True)
+    close(r, b - A @ x, dtype, scale + np.abs(b).max())
+    assert abs(nrm - np.linalg.norm((b - A @ x).astype(np.float64))) <= 10 * TOL[dtype] * max(nrm, 1e-30)
+    y0 = rs.randn(n).astype(dtype)
+    yd = dev(y0, dtype)
+    mlamg.spmv_add(Ad, xd, yd)
+    close(yd, y0 + A @ x, dtype, scale + np.abs(y0).max())
+    if n == m:
+        dw = rs.rand(n).astype(dtype)
+        xn = mlamg.jacobi_sweep(Ad, dev(dw, dtype), bd, xd)
+        close(xn, x + dw * (b - A @ x), dtype, scale + np.abs(b).max())
+        close(mlamg.jacobi_zero(dev(dw, dtype), bd), dw * b, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_smoother_diag_and_dot_axpby(dtype):
+    import mlamg
+    A = oml.poisson((20, 11)).astype(dtype)
+    A.data = A.data * (1 + 0.1 * np.random.RandomState(0).rand(A.nnz)).astype(dtype)
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    close(mlamg.smoother_diag(Ad, "jacobi", 0.7), dtype(0.7) / A.diagonal(), dtype)
+    close(mlamg.smoother_diag(Ad, "l1_jacobi"), 1.0 / np.asarray(abs(A).sum(axis=1)).ravel(), dtype)
+    rs = np.random.RandomState(1)
+    x, y = rs.randn(100003).astype(dtype), rs.randn(100003).astype(dtype)
+    xd, yd = dev(x, dtype), dev(y, dtype)
+    d = mlamg.dot(xd, yd)
+    assert abs(d - float(x.astype(np.float64) @ y.astype(np.float64))) <= 1e-6 * np.linalg.norm(x) * np.linalg.norm(y) * (1 if dtype == np.float32 else 1e-7)
+    assert mlamg.dot(xd, yd) == d                        # deterministic reduction
+    mlamg.axpby(0.5, xd, -2.0, yd)
+    close(yd, dtype(0.5) * x - dtype(2.0) * y, dtype)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2047, 2048, 2049, 70001, 3000000])
+def test_scan(n):
+    import mlamg
+    rs = np.random.RandomState(n)
+    c = rs.randint(0, 9, size=n).astype(np.int32)
+    out = mlamg.scan_i32(torch.from_numpy(c).cuda()).cpu().numpy()
+    ref = np.concatenate([[0], np.cumsum(c)]).astype(np.int32)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", list(MATS))
+def test_transpose_sorted(name, dtype):
+    import mlamg
+    A = MATS[name]().astype(dtype)
+    T = mlamg.transpose(mlamg.DeviceCSR.from_scipy(A)).to_scipy()
+    ref = sp.csr_matrix(A.T)
+    ref.sort_indices()
+    assert T.has_sorted_indices or np.all(np.diff(T.indices)[np.diff(T.indices) < 0] is not None)
+    assert np.array_equal(T.indptr, ref.indptr) and np.array_equal(T.indices, ref.indices)
+    assert np.array_equal(T.data, ref.data)              # pure data movement: bit-exact
+
+
+SPGEMM_CASES = {
+    "stencil_x_stencil": lambda: (oml.poisson((15, 13)), oml.poisson((15, 13))),
+    "random_x_random": lambda: (random_csr(300, 200, 0.05, 5), random_csr(200, 250, 0.05, 6)),
+    "cta_bin": lambda: (random_csr(60, 400, 0.3, 7), random_csr(400, 900, 0.05, 8)),        # ub ~ 5000 per row
+    "dense_rows": lambda: (random_csr(20, 300, 0.9, 9), random_csr(300, 3000, 0.3, 10)),     # ~3000 nnz rows
+    "empty": lambda: (sp.csr_matrix((7, 5)), sp.csr_matrix((5, 9))),
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", list(SPGEMM_CASES))
+def test_spgemm(name, dtype):
+    import mlamg
+    A, B = SPGEMM_CASES[name]()
+    A, B = sp.csr_matrix(A).astype(dtype), sp.csr_matrix(B).astype(dtype)
+    C = mlamg.spgemm(mlamg.DeviceCSR.from_scipy(A), mlamg.DeviceCSR.from_scipy(B))
+    Cs = C.to_scipy()
+    assert Cs.has_canonical_format or True
+    assert np.all(np.diff(Cs.indptr) >= 0)
+    # structural pattern of the GPU result = scipy's structural product (incl. numerically zero sums)
+    S = (sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape) @
+         sp.csr_matrix((np.ones(B.nnz), B.indices, B.indptr), shape=B.shape))
+    assert_same_pattern(sp.csr_matrix((np.ones(Cs.nnz), Cs.indices, Cs.indptr), shape=Cs.shape), S)
+    for i in range(Cs.shape[0]):                         # sorted rows
+        seg = Cs.indices[Cs.indptr[i]:Cs.indptr[i + 1]]
+        assert np.all(np.diff(seg) > 0)
+    ref = (A.astype(np.float64) @ B.astype(np.float64))
+    scale = (abs(A).astype(np.float64) @ abs(B).astype(np.float64))
+    err = abs(Cs.astype(np.float64) - ref).max() / max(scale.max(), 1e-300) if ref.nnz else 0.0
+    assert err <= (1e-14 if dtype == np.float64 else 1e-6)
+    # scipy semantics: exact zeros dropped
+    Cz = mlamg.drop_zeros(C).to_scipy()
+    assert_csr_close(Cz, A @ B, 1e-12 if dtype == np.float64 else 1e-5)
+
+
+def test_drop_zeros_and_sort_rows():
+    import mlamg
+    A = random_csr(200, 150, 0.1, 11)
+    A.data[::3] = 0.0
+    out = mlamg.drop_zeros(mlamg.DeviceCSR.from_scipy(A)).to_scipy()
+    ref = A.copy()
+    ref.eliminate_zeros()
+    assert np.array_equal(out.indptr, ref.indptr) and np.array_equal(out.indices, ref.indices) and np.array_equal(out.data, ref.data)
+    # unsorted rows (long and short) -> sort_indices
+    rs = np.random.RandomState(0)
+    B = random_csr(40, 5000, 0.5, 12, empty_rows=True)
+    perm_idx, perm_dat = B.indices.copy(), B.data.copy()
+    for i in range(B.shape[0]):
+        s, e = B.indptr[i], B.indptr[i + 1]
+        p = rs.permutation(e - s)
+        perm_idx[s:e], perm_dat[s:e] = B.indices[s:e][p], B.data[s:e][p]
+    D = mlamg.DeviceCSR(torch.from_numpy(B.indptr.astype(np.int32)).cuda(), torch.from_numpy(perm_idx.astype(np.int32)).cuda(),
+                        torch.from_numpy(perm_dat).cuda(), B.shape)
+    out = mlamg.sort_rows(D).to_scipy()
+    assert np.array_equal(out.indices, B.indices) and np.array_equal(out.data, B.data)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spmm_and_gemv(dtype):
+    import mlamg
+    A = random_csr(300, 200, 0.05, 13).astype(dtype)
+    rs = np.random.RandomState(2)
+    for k in (1, 7, 50):
+        X = rs.randn(200, k).astype(dtype)
+        Y = mlamg.spmm(mlamg.DeviceCSR.from_scipy(A), dev(X, dtype))
+        close(Y, A @ X, dtype, (abs(A) @ np.abs(X)).max())
+    M = rs.randn(70, 70).astype(dtype)
+    v = rs.randn(70).astype(dtype)
+    close(mlamg.gemv(dev(M, dtype), dev(v, dtype)), M @ v, dtype, (np.abs(M) @ np.abs(v)).max())
+
+
+def test_poisson_generator_matches_oracle():
+    import mlamg
+    for shape in [(7,), (9, 6), (5, 4, 3), (16, 16, 16)]:
+        A = mlamg.poisson(shape).to_scipy()
+        ref = oml.poisson(shape)
+        assert np.array_equal(A.indptr, ref.indptr) and np.array_equal(A.indices, ref.indices) and np.array_equal(A.data, ref.data)
+
+
+def test_dense_inverse_and_singular():
+    import mlamg
+    A = oml.poisson((9, 8))
+    inv = mlamg.dense_inverse(mlamg.DeviceCSR.from_scipy(A)).cpu().numpy()
+    assert np.abs(inv @ A.toarray() - np.eye(72)).max() < 1e-12
+    S = sp.csr_matrix(np.array([[1.0, 2.0], [2.0, 4.0]]))
+    with pytest.raises(mlamg.SingularCoarseError):
+        mlamg.dense_inverse(mlamg.DeviceCSR.from_scipy(S))
+
+
+def test_lambda_max_power_iteration():
+    import mlamg
+    n = 24
+    lam = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(oml.poisson((n, n))), iters=200)
+    exact = 1 + np.cos(np.pi / (n + 1))
+    assert exact * 0.97 <= lam <= exact * (1 + 1e-9)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gauss_seidel_bit_exact(dtype):
+    import mlamg
+    from oracle import pyamg_restated as pr
+    rs = np.random.RandomState(3)
+    for A in (oml.poisson((13, 11)), oml.poisson((6, 5, 4)), (random_csr(120, 120, 0.05, 14, empty_rows=False) + 5 * sp.eye(120)).tocsr()):
+        A = sp.csr_matrix(A).astype(dtype)
+        A.sort_indices()
+        n = A.shape[0]
+        b, x0 = rs.randn(n).astype(dtype), rs.randn(n).astype(dtype)
+        ref = x0.copy()
+        pr.gauss_seidel(A, ref, b, iterations=3)
+        Ad = mlamg.DeviceCSR.from_scipy(A)
+        sched = mlamg.GaussSeidelSchedule(Ad)
+        xd = dev(x0, dtype)
+        sched.sweep(dev(b, dtype), xd, iterations=3)
+        assert np.array_equal(xd.cpu().numpy(), ref), "forward Gauss-Seidel must be bit-identical to the sequential loop"

@@ -1,0 +1,119 @@
+"""CPU: the oracle against (a) the golden vectors produced by the UNMODIFIED reference modules,
+(b) its own independent pure-Python twin, (c) known-answer facts."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import pyamg_restated as pr, reference_path as rp, multilevel as oml
+from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, rel_hist_err, grid_graph
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_restated_path_matches_reference_golden(name):
+    z = load_golden(name)
+    A, C = csr_from(z, "A"), csr_from(z, "C")
+    Agg, roots, seeds = rp.lloyd_aggregation(C, ratio=float(z["ratio"]), distance=str(z["distance"]), rand=int(z["rand"]))
+    Agg_ref = csr_from(z, "Agg")
+    assert np.array_equal(seeds, z["seeds"]) and np.array_equal(roots, z["roots"])
+    assert (Agg != Agg_ref).nnz == 0 and Agg.dtype == np.int8
+    omega = (4.0 / 3.0) / float(z["lam_max"])
+    P = rp.smoothed_aggregation_jacobi(A, Agg, omega=omega)
+    assert_csr_close(P, csr_from(z, "P"), 1e-14)
+    assert_csr_close(rp.galerkin(A, sp.csr_matrix(P)), csr_from(z, "AH"), 1e-13)
+    # the two-level driver, with the reference's own P
+    Pref = csr_from(z, "P")
+    n = A.shape[0]
+    x0 = np.random.RandomState(0).randn(n)
+    x0 /= np.linalg.norm(x0, 2)
+    x, conv, err, nit = rp.amg_2_v(A, Pref, np.zeros(n), x0, res_tol=1e-10)
+    assert nit == int(z["gs_nit"])
+    assert rel_hist_err(err, z["gs_err"]) < 1e-12
+    assert abs(conv - float(z["gs_conv"])) < 1e-12
+    b2 = np.random.RandomState(1).randn(n)
+    x, conv, err, nit = rp.amg_2_v(A, Pref, b2, np.zeros(n), res_tol=1e-8, pre_smoothing_steps=2, post_smoothing_steps=2)
+    assert nit == int(z["gs2_nit"]) and rel_hist_err(err, z["gs2_err"]) < 1e-10
+    xj = rp.jacobi(A, b2, x0.copy(), omega=0.666, nu=3)
+    assert np.allclose(xj, z["jacobi_x"], rtol=1e-14, atol=1e-15)
+
+
+def test_lambda_max_known_answer():
+    # rho(D^-1 A) of the n x n 5-point Dirichlet Laplacian is 1 + cos(pi/(n+1))
+    n = 24
+    lam = float(load_golden("poisson2d_24_unit")["lam_max"])
+    assert abs(lam - (1 + np.cos(np.pi / (n + 1)))) < 1e-10
+
+
+def test_modified_bellman_ford_matches_reference_golden():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "ref_modified_bf.npz"))
+    n = int(z["n"])
+    S = sp.coo_matrix((z["w"], (z["row"], z["col"])), shape=(n, n))
+    dist, near = rp.modified_bellman_ford(S, z["centers"])
+    assert np.array_equal(dist, z["dist"]) and np.array_equal(near, z["nearest"])
+    Agg = rp.nearest_center_to_agg(z["centers"], near).tocoo()
+    assert np.array_equal(Agg.row, z["agg_row"]) and np.array_equal(Agg.col, z["agg_col"])
+
+
+@pytest.mark.parametrize("weights,dtype", [("unit", np.float64), ("random", np.float64), ("relu", np.float32)])
+def test_c_restatement_matches_python_twin(weights, dtype):
+    G = grid_graph((9, 7), weights, seed=3, dtype=dtype)
+    seeds = np.random.RandomState(5).permutation(G.shape[0])[:6].astype(np.int32)
+    d1, z1 = pr.bellman_ford(G, seeds)
+    d2, z2 = pr.bellman_ford_py(G, seeds)
+    assert np.array_equal(d1, d2) and np.array_equal(z1, z2) and d1.dtype == dtype
+    a = pr.lloyd_cluster(G, seeds.copy(), 10)
+    b = pr.lloyd_cluster_py(G, seeds.copy(), 10)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+def test_gauss_seidel_c_matches_python_twin_and_triangular_solve():
+    A = oml.poisson((7, 6))
+    rs = np.random.RandomState(0)
+    b, x0 = rs.randn(42), rs.randn(42)
+    x1, x2 = x0.copy(), x0.copy()
+    pr.gauss_seidel(A, x1, b, iterations=2)
+    pr.gauss_seidel_py(A, x2, b, iterations=2)
+    assert np.array_equal(x1, x2)
+    # reference's own scipy form (multigrid.py:58-90) agrees to rounding
+    import scipy.sparse.linalg as spla
+    L, U = sp.tril(A).tocsr(), sp.triu(A, k=1).tocsr()
+    x3 = x0.copy()
+    for _ in range(2):
+        x3 = spla.spsolve_triangular(L, b - U @ x3)
+    assert np.allclose(x1, x3, rtol=1e-13)
+
+
+def test_unreachable_nodes_and_keyerror():
+    # two disconnected components, seeds only in the first: labels -1, Agg rows empty, KeyError in the BF path
+    A = sp.block_diag([oml.poisson((4,)), oml.poisson((3,))]).tocsr()
+    G = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
+    d, z = pr.bellman_ford(G, np.array([1], dtype=np.int32))
+    assert (z[4:] == -1).all() and (z[:4] == 1).all() and (d[4:] == np.finfo(float).max).all()
+    with pytest.raises(KeyError):
+        rp.nearest_center_to_agg(np.array([1]), z)
+    _, w, _ = pr.lloyd_cluster(G, np.array([1], dtype=np.int32), 5)
+    assert (w[4:] == -1).all()
+
+
+def test_multilevel_oracle_converges():
+    A = oml.poisson((32, 32))
+    lv = oml.build_hierarchy(A, ratio=0.1, lam_max=lambda M: 2.0, max_coarse=40)
+    assert len(lv) >= 3
+    b = np.random.RandomState(0).randn(A.shape[0])
+    x, res, it = oml.pcg(lv, b, tol=1e-8)
+    assert res[-1] <= 1e-8 * np.linalg.norm(b) and it < 60
+    assert np.linalg.norm(b - A @ x) <= 2e-8 * np.linalg.norm(b)
+
+
+def test_error_conventions():
+    A = oml.poisson((6, 6))
+    with pytest.raises(ValueError):
+        rp.lloyd_aggregation(A, ratio=0.0)
+    with pytest.raises(ValueError):
+        rp.lloyd_aggregation(A, ratio=0.5, distance="bogus")
+    with pytest.raises(TypeError):
+        rp.lloyd_aggregation(A.tocoo(), ratio=0.5)
+    with pytest.raises(TypeError):
+        rp.lloyd_aggregation(A, ratio=0.5, rand="x")
+    with pytest.raises(RuntimeError):
+        rp.amg_2_v(A, A, np.zeros(36), np.zeros(36))
