@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the aggregation-AMG hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 256]
+
+Workload (config.workload): 3D 7-point Dirichlet Poisson, 256^3 DOF per GPU, fp64; full hierarchy
+(Lloyd aggregation ratio 0.027 'unit' distances, smoothed-aggregation P, Galerkin RAP), one *step* =
+one V(1,1) weighted-Jacobi cycle applied as a preconditioner (zero initial guess) to a resident
+right-hand side.  metric = GDOF/s (fine DOFs x cycles / s / 1e9; V-cycles/s reported beside it).
+
+  value     : cycles timed with CUDA events, inputs resident in HBM, CUDA-graph replay of the cycle
+  e2e       : the same cycle through the C-ABI host-buffer entry point (mlamg_vcycle_host): pinned host
+              b -> H2D -> V-cycle -> D2H -> host x, copies inside the timed region
+  roofline  : the dominant kernel (fused Jacobi sweep on the fine level), CUDA-event duration per launch
+              from an instrumented repeat of the timed steps, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the oracle's scipy V-cycle on the SAME hierarchy (downloaded), 1 host core (scipy
+              sparsetools is single-threaded), a bounded number of cycles
+  --impl reference : the oracle port end to end on the host (own CPU setup at a bounded size).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ml-amg_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+RATIO = 0.027
+METRIC = "vcycle_gdof_per_s"
+UNIT = "GDOF/s"
+
+
+def workload_name(n, ngpu):
+    return (f"poisson3d_7pt_{n}^3_per_gpu_fp64_lloyd{RATIO}_SA_V(1,1)_jacobi" + (f"_x{ngpu}gpu_zslab" if ngpu > 1 else ""))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def lam_fn_factory(n):
+    import mlamg
+    exact = 1.0 + np.cos(np.pi / (n + 1))          # rho(D^-1 A) of the Dirichlet 7-point stencil, analytic
+
+    def lam(A):
+        return exact if A.shape[0] == n ** 3 else mlamg.lambda_max(A, iters=30)
+    return lam
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import mlamg
+    from mlamg import core
+    n = args.n
+    if world > 1:
+        from mlamg import distributed as mdist
+        return mdist.bench_weak_scaling(args, rank, world, local, workload_name(n, world), METRIC, UNIT,
+                                        measured_peak, ClockSampler)
+    t_setup0 = time.time()
+    A = mlamg.poisson((n, n, n), torch.float64)
+    H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=RATIO, distance="unit", maxiter=10, rand=0,
+                              lam_max=lam_fn_factory(n), max_coarse=1000, max_levels=8)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t_setup0
+    N = A.shape[0]
+    b = torch.from_numpy(np.random.RandomState(0).randn(N)).cuda()
+    x = torch.empty_like(b)
+    s = core.stream()
+
+    def cycle():
+        core.check(core.lib.mlamg_vcycle(H._h, core.ptr(b), core.ptr(x), 1, 1, 1, s))
+
+    # kernels per cycle (plain launches are counted by the library)
+    c0 = mlamg.launch_count(); cycle(); torch.cuda.synchronize(); kernels_per_cycle = mlamg.launch_count() - c0
+    H.use_graph(True)
+    for _ in range(max(args.warmup, 3)):
+        cycle()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local); clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        cycle()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    H.use_graph(False)
+    value = N / ms / 1e6
+
+    # --- dominant kernel: fused Jacobi sweep on the fine level, per-launch CUDA-event time inside cycles
+    L0 = H.levels[0]
+    v = 8
+    B_jac = L0.A.nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
+    tmp = torch.empty_like(b)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):               # instrumented repeat: full cycle, then the fine post-smoothing sweep timed alone
+        cycle()
+        ev[k][0].record()
+        mlamg.jacobi_sweep(L0.A, L0.dw, b, x, tmp)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    jac_ms = float(np.mean([a.elapsed_time(c) for a, c in ev]))
+    peak, peak_kind = measured_peak()
+    achieved = B_jac / jac_ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "csr_rowop_kernel<double,8,JACOBI> (fine-level fused Jacobi sweep)",
+                "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "ms_per_launch": round(jac_ms, 4),
+                "algorithmic_bytes_per_launch": B_jac,
+                "cycle_bytes": H.cycle_bytes(1, 1, True),
+                "cycle_frac": round(H.cycle_bytes(1, 1, True) / ms / 1e6 / peak, 4)}
+    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("jacobi_fine_bytes_per_launch")
+        except Exception:
+            pass
+
+    # --- e2e: host buffers through the C ABI (H2D + cycle + D2H inside the timed region)
+    hb = torch.from_numpy(np.random.RandomState(1).randn(N)).pin_memory()
+    hx = torch.empty(N, dtype=torch.float64).pin_memory()
+    H.use_graph(True)
+    for _ in range(2):
+        H.apply_host(hb, hx, 1, 1, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        H.apply_host(hb, hx, 1, 1, 1)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    H.use_graph(False)
+    e2e = {"value": round(N / e2e_s / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
+           "ms_per_step": round(e2e_s * 1e3, 3)}
+
+    # --- CPU baseline: the oracle's scipy cycle on the same hierarchy, bounded sample
+    cpu = cpu_baseline_same_hierarchy(H, hb.numpy(), hx.numpy(), args.cpu_cycles)
+
+    out = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(n, 1), "dof": N, "nnz": L0.A.nnz, "levels": [l.A.shape[0] for l in H.levels],
+                      "operator_complexity": round(H.operator_complexity(), 4), "cycle": "V(1,1) zero-guess",
+                      "l2_policy": "inputs larger than L2 (fine operator 1.4 GB vs 126 MB L2)", "setup_s": round(setup_s, 2)},
+           "vcycles_per_s": round(1e3 / ms, 2), "clocks": clk, "e2e": e2e, "gpu_launches": kernels_per_cycle * args.steps,
+           "kernels_per_cycle": kernels_per_cycle, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out))
+
+
+def cpu_baseline_same_hierarchy(H, b, x_gpu, cycles):
+    """oracle.multilevel.vcycle (scipy, 1 core) on the hierarchy downloaded from the device; also the
+    full-size parity check of the GPU cycle (x_gpu = GPU result of one zero-guess V(1,1) on b)."""
+    from oracle import multilevel as oml
+    levels = []
+    for lev in H.levels:
+        L = oml.Level()
+        L.A = lev.A.to_scipy()
+        if lev.P is not None:
+            L.P, L.R, L.dw = lev.P.to_scipy(), lev.R.to_scipy(), lev.dw.cpu().numpy()
+        levels.append(L)
+    x = oml.vcycle(levels, b.copy(), None, 1, 1)           # warm-up + parity
+    rel = float(np.abs(x - x_gpu).max() / np.abs(x).max())
+    ts = []
+    for _ in range(max(1, cycles)):
+        t0 = time.perf_counter()
+        oml.vcycle(levels, b.copy(), None, 1, 1)
+        ts.append(time.perf_counter() - t0)
+    N = levels[0].A.shape[0]
+    return {"value": round(N / min(ts) / 1e9, 5), "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(),
+            "kind": "port", "sample": f"{len(ts)} full-size V(1,1) cycles of the oracle (scipy, single-threaded) on the "
+            f"same hierarchy, best of {len(ts)}; {min(ts):.2f} s per cycle", "parity_rel_err_vs_gpu_cycle": rel}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import multilevel as oml
+    n = args.ref_n
+    t0 = time.time()
+    A = oml.poisson((n, n, n))
+    exact = 1.0 + np.cos(np.pi / (n + 1))
+    levels = oml.build_hierarchy(A, ratio=RATIO, distance="unit", maxiter=10, rand=0,
+                                 lam_max=lambda M: exact if M.shape[0] == n ** 3 else 2.0, max_coarse=1000, max_levels=8)
+    setup_s = time.time() - t0
+    N = A.shape[0]
+    b = np.random.RandomState(0).randn(N)
+    for _ in range(max(args.warmup, 1)):
+        oml.vcycle(levels, b.copy(), None, 1, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oml.vcycle(levels, b.copy(), None, 1, 1)
+    s = (time.perf_counter() - t0) / args.steps
+    val = round(N / s / 1e9, 5)
+    sample = (f"each step = one oracle V(1,1) cycle on a {n}^3 sample of the workload (per-DOF throughput; "
+              f"CPU setup {setup_s:.1f} s untimed); scipy sparsetools is single-threaded")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": round(s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.n, args.gpus), "sample_dof": N},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(), "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="grid side per GPU")
+    ap.add_argument("--ref-n", type=int, default=128, help="grid side of the reference arm's bounded sample")
+    ap.add_argument("--cpu-cycles", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

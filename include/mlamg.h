@@ -97,9 +97,11 @@ int mlamg_agg_from_labels(int dtype, int n, const int *labels, int *rowptr, int 
  * MLAMG_EKEY if some nearest[i] is not a centre (reference raises KeyError). */
 int mlamg_center_rank_labels(int n, int k, const int *centers, const int *nearest, int *scratch_map,
                              int *labels, mlamg_stream_t stream);
-/* S = I - omega D^-1 A on A's pattern (multigrid.py:104-106); A must store its diagonal */
-int mlamg_sa_smoother_values(int dtype, int n, const int *rowptr, const int *col, const void *val,
-                             double omega, void *sval, mlamg_stream_t stream);
+/* S = I - omega D^-1 A (multigrid.py:104-106); A must store its diagonal.  S shares A's rowptr; every
+ * row is emitted in scipy's stored order for `eye - omega*Dinv@A` (off-diagonals in A's order, the
+ * diagonal LAST) because that order fixes the rounding of P = S @ Agg. */
+int mlamg_sa_smoother(int dtype, int n, const int *rowptr, const int *col, const void *val, double omega,
+                      int *scol, void *sval, mlamg_stream_t stream);
 
 /* C = A(m x k) * B(k x n), two-phase hash SpGEMM (scipy csr_matmat at multigrid.py:107,165;
  * torch.sparse.mm at agg_interp.py:484; torch_sparse.spspmm at loss.py:54).

@@ -114,6 +114,15 @@ __device__ __forceinline__ unsigned long long f2key(float v) {
     return (unsigned long long)u;
 }
 
+// explicitly non-fused arithmetic: the sequential CPU loops of the reference (x86-64, no FMA) round
+// every product and every sum separately; kernels that must be bit-identical use these
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
 template <typename T> struct Limits;
 template <> struct Limits<float> { static __host__ __device__ float max() { return 3.402823466e+38f; } };
 template <> struct Limits<double> { static __host__ __device__ double max() { return 1.7976931348623157e+308; } };

@@ -42,12 +42,6 @@ __global__ void __launch_bounds__(256) gs_level_fill_kernel(int n, const int *__
     order[atomicAdd(&cursor[level[i]], 1)] = (int)i;
 }
 
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 
 template <typename T>
 __global__ void __launch_bounds__(128) gs_rows_kernel(int count, const int *__restrict__ rows,

@@ -217,30 +217,35 @@ __global__ void __launch_bounds__(256) center_rank_kernel(int n, const int *__re
 }
 
 // ------------------------------------------------------------------ S = I - omega D^-1 A
-// warp per row; the expression order is scipy's at multigrid.py:104-106:
+// warp per row; values follow scipy's expression order at multigrid.py:104-106:
 //   t = (omega * (1/a_ii)) * a_ij ;  s_ij = (i==j) ? 1 - t : -t
+// and the row is stored as scipy stores `eye - omega*Dinv@A`: off-diagonals in A's order, diagonal last.
 template <typename T>
 __global__ void __launch_bounds__(256) sa_smoother_kernel(int n, const int *__restrict__ rowptr,
                                                           const int *__restrict__ col, const T *__restrict__ val,
-                                                          T omega, T *__restrict__ sval, int *__restrict__ bad) {
+                                                          T omega, int *__restrict__ scol, T *__restrict__ sval,
+                                                          int *__restrict__ bad) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
     const int start = rowptr[row], end = rowptr[row + 1];
     T d = (T)0;
-    int found = 0;
+    int pd = 0x7fffffff;
     for (int j = start + lane; j < end; j += 32)
-        if (col[j] == row) { d += val[j]; found = 1; }
-    d = warp_sum(d);
-    found = __any_sync(0xffffffffu, found);
-    if (!found) {
+        if (col[j] == row) { d = val[j]; pd = min(pd, j); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pd = min(pd, __shfl_xor_sync(0xffffffffu, pd, o));
+    if (pd == 0x7fffffff) {
         if (lane == 0) atomicExch(bad, 1);
         return;
     }
-    const T w = omega * ((T)1 / d);
+    d = __shfl_sync(0xffffffffu, d, (pd - start) & 31);   // the lane that read position pd
+    const T w = mul_rn(omega, div_rn((T)1, d));
     for (int j = start + lane; j < end; j += 32) {
-        const T t = w * val[j];
-        sval[j] = (col[j] == row) ? (T)1 - t : -t;
+        const T t = mul_rn(w, val[j]);
+        const int c = col[j];
+        if (j == pd) { scol[end - 1] = c; sval[end - 1] = add_rn((T)1, -t); }
+        else { const int q = j < pd ? j : j - 1; scol[q] = c; sval[q] = -t; }
     }
 }
 
@@ -470,21 +475,21 @@ int mlamg_center_rank_labels(int n, int k, const int *centers, const int *neares
     return MLAMG_OK;
 }
 
-int mlamg_sa_smoother_values(int dtype, int n, const int *rowptr, const int *col, const void *val, double omega,
-                             void *sval, mlamg_stream_t stream) {
+int mlamg_sa_smoother(int dtype, int n, const int *rowptr, const int *col, const void *val, double omega, int *scol,
+                      void *sval, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
-    if (n < 0) return set_error(MLAMG_EINVAL, "sa_smoother_values: n < 0");
+    if (n < 0) return set_error(MLAMG_EINVAL, "sa_smoother: n < 0");
     if (n == 0) return MLAMG_OK;
     Scratch bad(sizeof(int), s);
     MLAMG_SCRATCH_OK(bad);
     MLAMG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
     MLAMG_DISPATCH(dtype, (sa_smoother_kernel<T><<<cdiv((long long)n * 32, 256), 256, 0, s>>>(
-                              n, rowptr, col, (const T *)val, (T)omega, (T *)sval, bad.as<int>())));
+                              n, rowptr, col, (const T *)val, (T)omega, scol, (T *)sval, bad.as<int>())));
     MLAMG_LAUNCHED();
     int h = 0;
     MLAMG_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     MLAMG_CUDA(cudaStreamSynchronize(s));
-    if (h) return set_error(MLAMG_EINVAL, "sa_smoother_values: a row stores no diagonal entry");
+    if (h) return set_error(MLAMG_EINVAL, "sa_smoother: a row stores no diagonal entry");
     return MLAMG_OK;
 }
 

@@ -36,7 +36,7 @@ SIGNATURES = {
     "mlamg_scan_i32": (I, [P, P, I, P]),
     "mlamg_agg_from_labels": (I, [I, I, P, P, P, P, P, P]),
     "mlamg_center_rank_labels": (I, [I, I, P, P, P, P, P]),
-    "mlamg_sa_smoother_values": (I, [I, I, P, P, P, D, P, P]),
+    "mlamg_sa_smoother": (I, [I, I, P, P, P, D, P, P, P]),
     "mlamg_spgemm_symbolic": (I, [I, I, I, P, P, P, P, P, P, P]),
     "mlamg_spgemm_numeric": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
     "mlamg_csr_transpose": (I, [I, I, I, I, P, P, P, P, P, P, P]),

@@ -66,9 +66,9 @@ class DeviceCSR:
     def from_scipy(cls, A, dtype=None, device="cuda"):
         require_cuda()
         A = sp.csr_matrix(A)
-        if not A.has_sorted_indices:
+        if not A.has_canonical_format:
             A = A.copy()
-            A.sort_indices()
+            A.sum_duplicates()          # sorted, unique columns: the ordered SpGEMM relies on it
         if A.indptr[-1] >= 2 ** 31 or max(A.shape) >= 2 ** 31:
             raise OverflowError("matrix exceeds int32 indexing")
         if dtype is None:
@@ -298,11 +298,12 @@ def center_rank_labels(centers, nearest):
 
 
 def sa_smoother(A, omega):
-    """S = I - omega D^-1 A on A's pattern."""
+    """S = I - omega D^-1 A, rows stored in scipy's order for `eye - omega*Dinv@A` (diagonal last)."""
     sval = torch.empty_like(A.val)
-    check(lib.mlamg_sa_smoother_values(dt(A.val), A.shape[0], ptr(A.rowptr), ptr(A.col), ptr(A.val), float(omega),
-                                       ptr(sval), stream()))
-    return A.with_values(sval)
+    scol = torch.empty_like(A.col)
+    check(lib.mlamg_sa_smoother(dt(A.val), A.shape[0], ptr(A.rowptr), ptr(A.col), ptr(A.val), float(omega), ptr(scol),
+                                ptr(sval), stream()))
+    return DeviceCSR(A.rowptr, scol, sval, A.shape)
 
 
 def spgemm(A, B):

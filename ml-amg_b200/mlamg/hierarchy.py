@@ -73,11 +73,17 @@ def learned_prolongator(P_hat, Agg, drop=False):
     return core.drop_zeros(P) if drop else P
 
 
-def galerkin(A, P, R=None, drop=True):
-    """A_H = P^T A P (R = P^T reused when given)."""
+def galerkin(A, P, R=None, drop=True, symmetric=False):
+    """A_H = P^T A P, evaluated in the order scipy evaluates `P.T @ A @ P` (multigrid.py:165): P.T is a CSC
+    view, so scipy computes X^T = A^T P row by row, then A_H^T = P^T X^T, each entry summed sequentially
+    over the sorted outer index; with the ordered SpGEMM the result is bit-identical to scipy's.
+    symmetric=True skips the transpose of A (caller asserts A == A^T bitwise)."""
     if R is None:
         R = core.transpose(P)
-    AH = core.spgemm(R, core.spgemm(A, P))
+    At = A if symmetric else core.transpose(A)
+    AHt = core.spgemm(R, core.spgemm(At, P))
+    del At
+    AH = core.transpose(AHt)
     return core.drop_zeros(AH) if drop else AH
 
 

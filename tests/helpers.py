@@ -44,6 +44,15 @@ def assert_csr_close(X, Y, rtol):
     assert err <= rtol, f"max relative value error {err:.3e} > {rtol:.1e}"
 
 
+def assert_csr_bitwise(X, Y):
+    """canonical pattern AND values bit-identical (ordered SpGEMM reproduces scipy's summation order)"""
+    assert_same_pattern(X, Y)
+    X, Y = canonical(X), canonical(Y)
+    assert X.data.dtype == Y.data.dtype, (X.data.dtype, Y.data.dtype)
+    bad = np.nonzero(X.data != Y.data)[0]
+    assert bad.size == 0, f"{bad.size} of {X.nnz} values differ in their bits; first: {X.data[bad[0]]!r} vs {Y.data[bad[0]]!r}"
+
+
 def rel_hist_err(a, b):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     n = min(len(a), len(b))

@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, rel_hist_err, canonical
+from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, assert_csr_bitwise, rel_hist_err, canonical
 from oracle import reference_path as rp, multilevel as oml, pyamg_restated as pr
 
 pytestmark = pytest.mark.gpu
@@ -24,10 +24,10 @@ def test_sa_prolongator_and_galerkin_vs_reference_golden(name):
     omega = (4.0 / 3.0) / float(z["lam_max"])
     P = mg.smoothed_aggregation_jacobi(A, Agg, omega=omega)
     assert sp.isspmatrix_csr(P)
-    assert_csr_close(P, csr_from(z, "P"), RTOL64)
+    assert_csr_bitwise(P, csr_from(z, "P"))             # stronger than the 1e-12 bar: same bits as scipy
     Pd = mlamg.DeviceCSR.from_scipy(csr_from(z, "P"))
     AH = mlamg.galerkin(mlamg.DeviceCSR.from_scipy(A), Pd).to_scipy()
-    assert_csr_close(AH, csr_from(z, "AH"), RTOL64)
+    assert_csr_bitwise(AH, csr_from(z, "AH"))
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -85,11 +85,11 @@ def test_multilevel_setup_and_cycles_fp64(shape, ratio, smoother):
                               smoother=smoother)
     assert len(H.levels) == len(ref) >= 3
     for Lg, Lr in zip(H.levels, ref):
-        assert_csr_close(Lg.A.to_scipy(), Lr.A, RTOL64)
+        assert_csr_bitwise(Lg.A.to_scipy(), Lr.A)        # pattern and values identical at every level
         if Lr.P is not None:
             assert np.array_equal(Lg.labels.cpu().numpy(), Lr.labels), "aggregate labels must be bit-exact"
-            assert_csr_close(Lg.P.to_scipy(), Lr.P, RTOL64)
-            assert_csr_close(Lg.R.to_scipy(), Lr.R, RTOL64)
+            assert_csr_bitwise(Lg.P.to_scipy(), Lr.P)
+            assert_csr_bitwise(Lg.R.to_scipy(), Lr.R)
             assert np.allclose(Lg.dw.cpu().numpy(), Lr.dw, rtol=1e-15)
     n = A.shape[0]
     b = np.random.RandomState(0).randn(n)

@@ -6,7 +6,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import random_csr, assert_csr_close, assert_same_pattern
+from helpers import random_csr, assert_csr_close, assert_csr_bitwise, assert_same_pattern
 from oracle import multilevel as oml
 
 pytestmark = pytest.mark.gpu
@@ -134,9 +134,11 @@ def test_spgemm(name, dtype):
     scale = (abs(A).astype(np.float64) @ abs(B).astype(np.float64))
     err = abs(Cs.astype(np.float64) - ref).max() / max(scale.max(), 1e-300) if ref.nnz else 0.0
     assert err <= (1e-14 if dtype == np.float64 else 1e-6)
-    # scipy semantics: exact zeros dropped
+    # scipy semantics: exact zeros dropped; ordered accumulation => the same bits as scipy's csr_matmat
     Cz = mlamg.drop_zeros(C).to_scipy()
-    assert_csr_close(Cz, A @ B, 1e-12 if dtype == np.float64 else 1e-5)
+    assert_csr_bitwise(Cz, A @ B)
+    C2 = mlamg.spgemm(mlamg.DeviceCSR.from_scipy(A), mlamg.DeviceCSR.from_scipy(B))
+    assert torch.equal(C2.val, C.val) and torch.equal(C2.col, C.col)      # run-to-run deterministic
 
 
 def test_drop_zeros_and_sort_rows():
