@@ -67,6 +67,17 @@ int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, 
 /* smoother diagonal: mode 0 -> omega / a_ii, mode 1 -> 1 / sum_j |a_ij| (omega ignored) */
 int mlamg_smoother_diag(int dtype, int mode, double omega, int n, const int *rowptr, const int *col,
                         const void *val, void *dw, mlamg_stream_t stream);
+/* SELL-32 storage of an operator for the apply kernels (rows in slices of 32, column-major inside a
+ * slice, padded with col = -1): thread-per-row kernels whose every col/val load is one coalesced warp
+ * transaction.  slice_ptr has ceil(n/32)+1 entries (element offsets); *padded_nnz_host sizes scol/sval. */
+int mlamg_sell_slice_ptr(int n, const int *rowptr, int *slice_ptr, long long *padded_nnz_host, mlamg_stream_t stream);
+int mlamg_sell_fill(int dtype, int n, const int *rowptr, const int *col, const void *val, const int *slice_ptr,
+                    int *scol, void *sval, mlamg_stream_t stream);
+/* op: 0 y = A x | 1 y += A x | 2 y = b - A x (+ *norm2 = ||y||^2 if norm2 != NULL) | 3 y = x + dw.*(b - A x) */
+int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *scol, const void *sval,
+                     const void *x, const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream);
+/* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32), -1 = heuristic */
+int mlamg_set_csr_lanes(int lanes);
 /* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
 int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *val,
                    const void *X, void *Y, double alpha, double beta, mlamg_stream_t stream);
@@ -170,6 +181,9 @@ int mlamg_hierarchy_create(int dtype, int nlevels, mlamg_hierarchy_t *out);
 /* Level l operator and smoother diagonal (non-owning device pointers; caller keeps them alive). */
 int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz, const int *rowptr,
                                  const int *col, const void *val, const void *dw);
+/* optional SELL-32 copy of level l's operator; when present the smoother and residual kernels use it */
+int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int *slice_ptr, const int *scol,
+                                      const void *sval);
 /* P (n_l x n_{l+1}) and R = P^T (n_{l+1} x n_l) between level l and l+1 */
 int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, const int *p_rowptr,
                                  const int *p_col, const void *p_val, const int *r_rowptr,

@@ -12,8 +12,28 @@ enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3 };
 
 constexpr int ROW_THREADS = 256;
 
-// LANES threads cooperate on one row (LANES = 2..32, power of two): coalesced reads of col/val across
-// the warp because consecutive rows are contiguous in CSR; segmented shuffle reduction.
+template <typename T, int OP, bool NORM>
+__device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__restrict__ x, const T *__restrict__ b,
+                                               const T *__restrict__ dw, T *__restrict__ y) {
+    double rr = 0.0;
+    if (OP == OP_SPMV) {
+        y[row] = sum;
+    } else if (OP == OP_SPMV_ADD) {
+        y[row] += sum;
+    } else if (OP == OP_RESIDUAL) {
+        const T r = b[row] - sum;
+        y[row] = r;
+        if (NORM) rr = (double)r * (double)r;
+    } else {  // OP_JACOBI
+        y[row] = x[row] + dw[row] * (b[row] - sum);
+    }
+    return rr;
+}
+
+// CSR: LANES threads cooperate on one row (LANES = 1..32, power of two).  Consecutive rows are
+// contiguous in CSR, so a warp always reads one contiguous span of col/val; the inner loop is
+// unrolled 4x so every thread keeps 4 (col,val) pairs and 4 gathers of x in flight (HBM latency is
+// hidden by memory-level parallelism, not by occupancy alone).  Segmented shuffle reduction.
 template <typename T, int LANES, int OP, bool NORM>
 __global__ void __launch_bounds__(ROW_THREADS)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
@@ -26,23 +46,21 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     if (row < n) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
-        for (int j = start + lane; j < end; j += LANES) sum += val[j] * x[col[j]];
-    }
-    sum = group_sum<LANES>(sum);
-    double rr = 0.0;
-    if (row < n && lane == 0) {
-        if (OP == OP_SPMV) {
-            y[row] = sum;
-        } else if (OP == OP_SPMV_ADD) {
-            y[row] += sum;
-        } else if (OP == OP_RESIDUAL) {
-            const T r = b[row] - sum;
-            y[row] = r;
-            if (NORM) rr = (double)r * (double)r;
-        } else {  // OP_JACOBI
-            y[row] = x[row] + dw[row] * (b[row] - sum);
+        int j = start + lane;
+        for (; j + 3 * LANES < end; j += 4 * LANES) {
+            const int c0 = col[j], c1 = col[j + LANES], c2 = col[j + 2 * LANES], c3 = col[j + 3 * LANES];
+            const T v0 = val[j], v1 = val[j + LANES], v2 = val[j + 2 * LANES], v3 = val[j + 3 * LANES];
+            const T x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+            sum += v0 * x0;
+            sum += v1 * x1;
+            sum += v2 * x2;
+            sum += v3 * x3;
         }
+        for (; j < end; j += LANES) sum += val[j] * x[col[j]];
     }
+    if (LANES > 1) sum = group_sum<LANES>(sum);
+    double rr = 0.0;
+    if (row < n && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
     if (NORM) {
         __shared__ double sm[32];
         rr = block_sum(rr, sm);
@@ -50,12 +68,59 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     }
 }
 
+// SELL-32: rows are grouped in slices of 32; a slice stores width = max row length columns, column-
+// major inside the slice (entry k of lane l at slice_ptr[s] + 32 k + l), padded with col = -1.  One
+// thread per row, every load of col/val is a fully coalesced 128/256-byte warp transaction and the
+// loop carries no reduction across lanes.
+template <typename T, int OP, bool NORM>
+__global__ void __launch_bounds__(ROW_THREADS)
+sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restrict__ col, const T *__restrict__ val,
+                  const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *__restrict__ y,
+                  double *__restrict__ partial) {
+    const long long row = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    T sum = (T)0;
+    if (row < n) {
+        const long long slice = row >> 5;
+        const int base = slice_ptr[slice];
+        const int width = (slice_ptr[slice + 1] - base) >> 5;
+        const int *c = col + base + lane;
+        const T *v = val + base + lane;
+        int k = 0;
+        for (; k + 4 <= width; k += 4) {
+            const int c0 = c[32 * k], c1 = c[32 * (k + 1)], c2 = c[32 * (k + 2)], c3 = c[32 * (k + 3)];
+            const T v0 = v[32 * k], v1 = v[32 * (k + 1)], v2 = v[32 * (k + 2)], v3 = v[32 * (k + 3)];
+            const T x0 = c0 >= 0 ? x[c0] : (T)0, x1 = c1 >= 0 ? x[c1] : (T)0;
+            const T x2 = c2 >= 0 ? x[c2] : (T)0, x3 = c3 >= 0 ? x[c3] : (T)0;
+            sum += v0 * x0;
+            sum += v1 * x1;
+            sum += v2 * x2;
+            sum += v3 * x3;
+        }
+        for (; k < width; k++) {
+            const int c0 = c[32 * k];
+            if (c0 >= 0) sum += v[32 * k] * x[c0];
+        }
+    }
+    double rr = 0.0;
+    if (row < n) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
+    if (NORM) {
+        __shared__ double sm[32];
+        rr = block_sum(rr, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+    }
+}
+
+static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic
+
 static int pick_lanes(int n, long long nnz) {
+    if (g_force_lanes > 0) return g_force_lanes;
     const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
-    if (mean <= 3.0) return 2;
-    if (mean <= 6.0) return 4;
-    if (mean <= 12.0) return 8;
-    if (mean <= 24.0) return 16;
+    if (mean <= 4.0) return 1;
+    if (mean <= 8.0) return 2;
+    if (mean <= 16.0) return 4;
+    if (mean <= 32.0) return 8;
+    if (mean <= 64.0) return 16;
     return 32;
 }
 
@@ -77,6 +142,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
 #define LAUNCH(L)                                                                                       \
     csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial)
     switch (lanes) {
+        case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
         case 4: LAUNCH(4); break;
         case 8: LAUNCH(8); break;
@@ -87,6 +153,74 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
     MLAMG_LAUNCHED();
     if (NORM) return reduce_partials(partial, (int)blocks, norm2, s);
     return MLAMG_OK;
+}
+
+template <typename T, int OP, bool NORM>
+static int launch_sell(int n, const int *slice_ptr, const int *col, const T *val, const T *x, const T *b, const T *dw,
+                       T *y, double *norm2, cudaStream_t s) {
+    if (n <= 0) {
+        if (NORM && norm2) MLAMG_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double), s));
+        return MLAMG_OK;
+    }
+    const unsigned blocks = cdiv(n, ROW_THREADS);
+    double *partial = nullptr;
+    Scratch part(NORM ? (size_t)blocks * sizeof(double) : 16, s);
+    if (NORM) {
+        MLAMG_SCRATCH_OK(part);
+        partial = part.as<double>();
+    }
+    sell_rowop_kernel<T, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, slice_ptr, col, val, x, b, dw, y, partial);
+    MLAMG_LAUNCHED();
+    if (NORM) return reduce_partials(partial, (int)blocks, norm2, s);
+    return MLAMG_OK;
+}
+
+// op: 0 spmv, 1 spmv_add, 2 residual (+norm2), 3 jacobi
+template <typename T>
+int sell_rowop_t(int op, int n, const int *slice_ptr, const int *col, const T *val, const T *x, const T *b,
+                 const T *dw, T *y, double *norm2, cudaStream_t s) {
+    switch (op) {
+        case OP_SPMV: return launch_sell<T, OP_SPMV, false>(n, slice_ptr, col, val, x, b, dw, y, nullptr, s);
+        case OP_SPMV_ADD: return launch_sell<T, OP_SPMV_ADD, false>(n, slice_ptr, col, val, x, b, dw, y, nullptr, s);
+        case OP_RESIDUAL:
+            if (norm2) return launch_sell<T, OP_RESIDUAL, true>(n, slice_ptr, col, val, x, b, dw, y, norm2, s);
+            return launch_sell<T, OP_RESIDUAL, false>(n, slice_ptr, col, val, x, b, dw, y, nullptr, s);
+        case OP_JACOBI: return launch_sell<T, OP_JACOBI, false>(n, slice_ptr, col, val, x, b, dw, y, nullptr, s);
+        default: return set_error(MLAMG_EINVAL, "sell_rowop: bad op %d", op);
+    }
+}
+template int sell_rowop_t<float>(int, int, const int *, const int *, const float *, const float *, const float *,
+                                 const float *, float *, double *, cudaStream_t);
+template int sell_rowop_t<double>(int, int, const int *, const int *, const double *, const double *, const double *,
+                                  const double *, double *, double *, cudaStream_t);
+
+// ---- CSR -> SELL-32 conversion ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sell_width_kernel(int n, const int *__restrict__ rowptr, int *__restrict__ sizes) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (row < n) len = rowptr[row + 1] - rowptr[row];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && row < n) sizes[row >> 5] = len * 32;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sell_fill_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                        const T *__restrict__ val, const int *__restrict__ slice_ptr,
+                                                        int *__restrict__ scol, T *__restrict__ sval) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long slice = row >> 5;
+    if (slice * 32 >= n) return;   // whole warp
+    const int base = slice_ptr[slice];
+    const int width = (slice_ptr[slice + 1] - base) >> 5;
+    int start = 0, len = 0;
+    if (row < n) { start = rowptr[row]; len = rowptr[row + 1] - start; }
+    for (int k = 0; k < width; k++) {
+        const bool live = k < len;
+        scol[base + 32 * k + lane] = live ? col[start + k] : -1;
+        sval[base + 32 * k + lane] = live ? val[start + k] : (T)0;
+    }
 }
 
 // ---- internal entry points used by hierarchy.cu (nnz known, no host sync) -------------------
@@ -276,6 +410,50 @@ int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, c
     MLAMG_DISPATCH(dtype, (spmm_kernel<T><<<cdiv((long long)n * 32, 256), 256, 0, s>>>(
                               n, k, rowptr, col, (const T *)val, (const T *)X, (T *)Y, (T)alpha, (T)beta)));
     MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_set_csr_lanes(int lanes) {
+    if (lanes != -1 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return set_error(MLAMG_EINVAL, "set_csr_lanes: lanes must be -1 or a power of two <= 32");
+    g_force_lanes = lanes;
+    return MLAMG_OK;
+}
+
+int mlamg_sell_slice_ptr(int n, const int *rowptr, int *slice_ptr, long long *padded_nnz_host, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "sell_slice_ptr: n < 0");
+    const int nslices = (n + 31) / 32;
+    if (n > 0) {
+        sell_width_kernel<<<cdiv((long long)nslices * 32, 256), 256, 0, s>>>(n, rowptr, slice_ptr);
+        MLAMG_LAUNCHED();
+    }
+    MLAMG_TRY(exclusive_scan_i32(slice_ptr, slice_ptr, nslices, s));
+    int h = 0;
+    MLAMG_CUDA(cudaMemcpyAsync(&h, slice_ptr + nslices, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    if (h < 0) return set_error(MLAMG_ELIMIT, "sell: padded size overflows int32");
+    if (padded_nnz_host) *padded_nnz_host = h;
+    return MLAMG_OK;
+}
+
+int mlamg_sell_fill(int dtype, int n, const int *rowptr, const int *col, const void *val, const int *slice_ptr,
+                    int *scol, void *sval, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n <= 0) return n == 0 ? MLAMG_OK : set_error(MLAMG_EINVAL, "sell_fill: n < 0");
+    const int nslices = (n + 31) / 32;
+    MLAMG_DISPATCH(dtype, (sell_fill_kernel<T><<<cdiv((long long)nslices * 32, 256), 256, 0, s>>>(
+                              n, rowptr, col, (const T *)val, slice_ptr, scol, (T *)sval)));
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *scol, const void *sval, const void *x,
+                     const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream) {
+    if (n < 0) return set_error(MLAMG_EINVAL, "sell_rowop: n < 0");
+    if (x == y) return set_error(MLAMG_EINVAL, "sell_rowop: x aliases y");
+    MLAMG_DISPATCH(dtype, return sell_rowop_t<T>(op, n, slice_ptr, scol, (const T *)sval, (const T *)x, (const T *)b,
+                                                 (const T *)dw, (T *)y, norm2, as_stream(stream)));
     return MLAMG_OK;
 }
 

@@ -21,6 +21,9 @@ int residual_t(int, long long, const int *, const int *, const T *, const T *, c
 template <typename T>
 int jacobi_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
 template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStream_t);
+template <typename T>
+int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
+                 cudaStream_t);
 template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
 
 struct Csr {
@@ -34,6 +37,8 @@ struct Csr {
 struct LevelData {
     Csr A, P, R;
     const void *dw = nullptr;
+    const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A
+    const void *sell_val = nullptr;
     bool has_A = false, has_PR = false;
     void *x = nullptr, *tmp = nullptr, *b = nullptr, *r = nullptr;   // owned work vectors
 };
@@ -67,6 +72,23 @@ static int check_handle(mlamg_hierarchy_t h) {
     return MLAMG_OK;
 }
 
+// smoother sweep / residual on level `lev`, SELL-32 when the level carries one, CSR otherwise
+template <typename T>
+static int level_jacobi(const LevelData &lev, const T *b, const T *xin, T *xout, cudaStream_t s) {
+    const Csr &A = lev.A;
+    if (lev.sell_ptr)
+        return sell_rowop_t<T>(3, A.n, lev.sell_ptr, lev.sell_col, (const T *)lev.sell_val, xin, b, (const T *)lev.dw,
+                               xout, nullptr, s);
+    return jacobi_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, (const T *)lev.dw, b, xin, xout, s);
+}
+template <typename T>
+static int level_residual(const LevelData &lev, const T *b, const T *x, T *r, double *norm2, cudaStream_t s) {
+    const Csr &A = lev.A;
+    if (lev.sell_ptr)
+        return sell_rowop_t<T>(2, A.n, lev.sell_ptr, lev.sell_col, (const T *)lev.sell_val, x, b, nullptr, r, norm2, s);
+    return residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, x, b, r, norm2, s);
+}
+
 template <typename T>
 static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
     const int L = (int)h->lv.size();
@@ -98,11 +120,11 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
         }
         for (int k = 0; k < pre_pp; k++) {
             T *o = (c == xa) ? xb : xa;
-            MLAMG_TRY(jacobi_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, o, s));
+            MLAMG_TRY(level_jacobi<T>(lev, rhs[l], c, o, s));
             c = o;
         }
         cur[l] = c;
-        MLAMG_TRY(residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, c, rhs[l], (T *)lev.r, nullptr, s));
+        MLAMG_TRY(level_residual<T>(lev, rhs[l], c, (T *)lev.r, nullptr, s));
         const Csr &R = lev.R;
         T *bc = (T *)h->lv[l + 1].b;
         MLAMG_TRY(spmv_t<T>(R.n, R.nnz, R.rowptr, R.col, (const T *)R.val, (const T *)lev.r, bc, s));
@@ -118,14 +140,13 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
     for (int l = L - 2; l >= 0; l--) {
         LevelData &lev = h->lv[l];
         const Csr &A = lev.A, &P = lev.P;
-        const T *dw = (const T *)lev.dw;
         T *xa = (l == 0) ? x : (T *)lev.x;
         T *xb = (T *)lev.tmp;
         T *c = cur[l];
         MLAMG_TRY(spmv_add_t<T>(P.n, P.nnz, P.rowptr, P.col, (const T *)P.val, cur[l + 1], c, s));
         for (int k = 0; k < nu2; k++) {
             T *o = (c == xa) ? xb : xa;
-            MLAMG_TRY(jacobi_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, o, s));
+            MLAMG_TRY(level_jacobi<T>(lev, rhs[l], c, o, s));
             c = o;
         }
         if (l == 0 && c != x) {   // non-zero guess with an odd sweep count: one copy back
@@ -212,6 +233,17 @@ int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz,
     lev.A.n = n; lev.A.nnz = nnz; lev.A.rowptr = rowptr; lev.A.col = col; lev.A.val = val;
     lev.dw = dw;
     lev.has_A = true;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int *slice_ptr, const int *scol,
+                                      const void *sval) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level >= (int)h->lv.size() || !h->lv[level].has_A)
+        return set_error(MLAMG_EINVAL, "set_operator_sell: set the CSR operator of the level first");
+    LevelData &lev = h->lv[level];
+    lev.sell_ptr = slice_ptr; lev.sell_col = scol; lev.sell_val = sval;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     return MLAMG_OK;
 }
 

@@ -28,6 +28,11 @@ SIGNATURES = {
     "mlamg_jacobi_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_zero": (I, [I, I, P, P, P, P]),
     "mlamg_smoother_diag": (I, [I, I, D, I, P, P, P, P, P]),
+    "mlamg_sell_slice_ptr": (I, [I, P, P, P, P]),
+    "mlamg_sell_fill": (I, [I, I, P, P, P, P, P, P, P]),
+    "mlamg_sell_rowop": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
+    "mlamg_set_csr_lanes": (I, [I]),
+    "mlamg_hierarchy_set_operator_sell": (I, [P, I, P, P, P]),
     "mlamg_spmm_csr": (I, [I, I, I, P, P, P, P, P, D, D, P]),
     "mlamg_axpby": (I, [I, I, D, P, D, P, P]),
     "mlamg_dot": (I, [I, I, P, P, P, P]),

@@ -159,6 +159,50 @@ class DeviceCSR:
         return transpose(self)
 
 
+class DeviceSELL:
+    """SELL-32 copy of a DeviceCSR for the apply kernels (slice_ptr int32[ceil(n/32)+1], col/val padded)."""
+
+    __slots__ = ("slice_ptr", "col", "val", "shape", "nnz")
+
+    def __init__(self, A):
+        n = A.shape[0]
+        dev = A.val.device
+        self.shape, self.nnz = A.shape, A.nnz
+        self.slice_ptr = torch.empty((n + 31) // 32 + 1, dtype=torch.int32, device=dev)
+        padded = ctypes.c_longlong(0)
+        check(lib.mlamg_sell_slice_ptr(n, ptr(A.rowptr), ptr(self.slice_ptr), ctypes.byref(padded), stream()))
+        self.col = torch.empty(max(padded.value, 1), dtype=torch.int32, device=dev)
+        self.val = torch.empty(max(padded.value, 1), dtype=A.dtype, device=dev)
+        check(lib.mlamg_sell_fill(dt(A.val), n, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(self.slice_ptr), ptr(self.col),
+                                  ptr(self.val), stream()))
+
+    @property
+    def padding(self):
+        return self.col.numel() / max(self.nnz, 1)
+
+    def rowop(self, op, x, b=None, dw=None, out=None, norm=False):
+        n = self.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=self.val.dtype, device=x.device)
+        nrm = torch.zeros(1, dtype=torch.float64, device=x.device) if norm else None
+        check(lib.mlamg_sell_rowop(dt(self.val), op, n, ptr(self.slice_ptr), ptr(self.col), ptr(self.val), ptr(x), ptr(b),
+                                   ptr(dw), ptr(out), ptr(nrm), stream()))
+        return (out, float(nrm.sqrt().item())) if norm else out
+
+    def spmv(self, x, out=None):
+        return self.rowop(0, x, out=out)
+
+    def residual(self, x, b, out=None, norm=False):
+        return self.rowop(2, x, b=b, out=out, norm=norm)
+
+    def jacobi_sweep(self, dw, b, x_in, x_out=None):
+        return self.rowop(3, x_in, b=b, dw=dw, out=x_out)
+
+
+def set_csr_lanes(lanes=-1):
+    check(lib.mlamg_set_csr_lanes(int(lanes)))
+
+
 # ------------------------------------------------------------------ V-cycle apply kernels
 def spmv(A, x, out=None):
     n, m = A.shape

@@ -88,17 +88,20 @@ def galerkin(A, P, R=None, drop=True, symmetric=False):
 
 
 class Level:
-    __slots__ = ("A", "P", "R", "dw", "labels", "omega_sa", "seeds", "roots")
+    __slots__ = ("A", "P", "R", "dw", "labels", "omega_sa", "seeds", "roots", "sell")
 
     def __init__(self, A):
         self.A = A
-        self.P = self.R = self.dw = self.labels = self.omega_sa = self.seeds = self.roots = None
+        self.P = self.R = self.dw = self.labels = self.omega_sa = self.seeds = self.roots = self.sell = None
 
 
 class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
-    def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False):
+    def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="auto",
+                 sell_max_padding=1.5):
+        """sell: 'auto' -> levels whose SELL-32 padding stays below sell_max_padding get a SELL copy of A for the
+        smoother/residual kernels; 'never' -> CSR kernels only; 'always'."""
         core.require_cuda()
         self.levels = levels
         self.dtype = levels[0].A.dtype
@@ -113,6 +116,12 @@ class Hierarchy:
             A = lev.A
             check(lib.mlamg_hierarchy_set_operator(self._h, l, A.shape[0], A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val),
                                                    ptr(lev.dw)))
+        if sell != "never":
+            for l, lev in enumerate(levels[:-1]):
+                sl = core.DeviceSELL(lev.A)
+                if sell == "always" or sl.padding <= sell_max_padding:
+                    lev.sell = sl
+                    check(lib.mlamg_hierarchy_set_operator_sell(self._h, l, ptr(sl.slice_ptr), ptr(sl.col), ptr(sl.val)))
         for l, lev in enumerate(levels[:-1]):
             P, R = lev.P, lev.R
             check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
@@ -213,7 +222,7 @@ class Hierarchy:
 
 def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
                     P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
-                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000):
+                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="auto"):
     """Build the multilevel hierarchy on the device.
 
     A           : scipy / torch sparse / DeviceCSR
@@ -268,4 +277,4 @@ def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxite
     if levels[-1].A.shape[0] > max_dense:
         raise _lib.MlamgError(_lib.ELIMIT, f"coarsest level has {levels[-1].A.shape[0]} rows; raise max_levels or "
                                            f"lower max_coarse (dense coarse solve limit {max_dense})")
-    return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph)
+    return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph, sell=sell)

@@ -220,3 +220,43 @@ def test_gauss_seidel_bit_exact(dtype):
         xd = dev(x0, dtype)
         sched.sweep(dev(b, dtype), xd, iterations=3)
         assert np.array_equal(xd.cpu().numpy(), ref), "forward Gauss-Seidel must be bit-identical to the sequential loop"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["poisson2d", "poisson3d", "random_sparse", "random_dense_rows"])
+def test_sell32_rowops(name, dtype):
+    import mlamg
+    A = MATS[name]().astype(dtype)
+    if A.shape[0] != A.shape[1]:
+        A = sp.csr_matrix(A[:, :A.shape[0]]) if A.shape[1] > A.shape[0] else A
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    n, m = A.shape
+    rs = np.random.RandomState(0)
+    x, b, dw = rs.randn(m).astype(dtype), rs.randn(n).astype(dtype), rs.rand(n).astype(dtype)
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    S = mlamg.DeviceSELL(Ad)
+    assert S.col.numel() % 32 == 0 and S.padding >= 1.0
+    xd, bd, dwd = dev(x, dtype), dev(b, dtype), dev(dw, dtype)
+    scale = (abs(A) @ np.abs(x)).max() + np.abs(b).max()
+    close(S.spmv(xd), A @ x, dtype, scale)
+    r, nrm = S.residual(xd, bd, norm=True)
+    close(r, b - A @ x, dtype, scale)
+    assert abs(nrm - np.linalg.norm((b - A @ x).astype(np.float64))) <= 10 * TOL[dtype] * max(nrm, 1e-30)
+    if n == m:
+        close(S.jacobi_sweep(dwd, bd, xd), x + dw * (b - A @ x), dtype, scale)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_csr_lane_variants(lanes):
+    import mlamg
+    try:
+        mlamg.set_csr_lanes(lanes)
+        for name in ("poisson3d", "random_dense_rows", "single_row"):
+            A = MATS[name]()
+            rs = np.random.RandomState(1)
+            x = rs.randn(A.shape[1])
+            y = mlamg.spmv(mlamg.DeviceCSR.from_scipy(A), dev(x, np.float64))
+            close(y, A @ x, np.float64, (abs(A) @ np.abs(x)).max())
+    finally:
+        mlamg.set_csr_lanes(-1)

@@ -34,12 +34,24 @@ def main():
         dw = mlamg.smoother_diag(A, "jacobi", 2 / 3)
         B_spmv = nnz * (v + 4) + 4 * (N + 1) + 2 * v * N
         B_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
+        timeit(lambda: mlamg.spmv(A, x, y), reps=30)     # clock ramp
         t = timeit(lambda: mlamg.spmv(A, x, y))
         out[f"spmv_{v*8}"] = dict(ms=t, gbs=B_spmv / t / 1e6)
         t = timeit(lambda: mlamg.jacobi_sweep(A, dw, b, x, y))
         out[f"jacobi_{v*8}"] = dict(ms=t, gbs=B_jac / t / 1e6)
         t = timeit(lambda: mlamg.residual(A, x, b, y))
         out[f"residual_{v*8}"] = dict(ms=t, gbs=(B_spmv + v * N) / t / 1e6)
+        S = mlamg.DeviceSELL(A)
+        t = timeit(lambda: S.spmv(x, y))
+        out[f"sell_spmv_{v*8}"] = dict(ms=t, gbs=B_spmv / t / 1e6, padding=S.padding)
+        t = timeit(lambda: S.jacobi_sweep(dw, b, x, y))
+        out[f"sell_jacobi_{v*8}"] = dict(ms=t, gbs=B_jac / t / 1e6)
+        for lanes in (1, 2, 4, 8):
+            mlamg.set_csr_lanes(lanes)
+            t = timeit(lambda: mlamg.jacobi_sweep(A, dw, b, x, y))
+            out[f"csr_jacobi_L{lanes}_{v*8}"] = dict(ms=t, gbs=B_jac / t / 1e6)
+        mlamg.set_csr_lanes(-1)
+        del S
         t = timeit(lambda: y.copy_(x))
         out[f"copy_{v*8}"] = dict(ms=t, gbs=2 * v * N / t / 1e6)
         print(json.dumps({k: out[k] for k in out if k.endswith(str(v * 8))}), flush=True)
@@ -76,6 +88,17 @@ def main():
     H.use_graph(True)
     t = timeit(cyc, reps=10)
     print(json.dumps(dict(vcycle_graph_ms=t, gbs=H.cycle_bytes() / t / 1e6)))
+    H.use_graph(False)
+    # per-kernel times on the fine level and the transfer operators
+    L0 = H.levels[0]
+    N = A.shape[0]
+    r = torch.empty_like(b); bc = torch.empty(L0.R.shape[0], dtype=b.dtype, device="cuda")
+    for name, fn in [("L0 jacobi(sell)" if L0.sell else "L0 jacobi(csr)", (lambda: L0.sell.jacobi_sweep(L0.dw, b, xo, r)) if L0.sell else (lambda: mlamg.jacobi_sweep(L0.A, L0.dw, b, xo, r))),
+                     ("L0 restrict R", lambda: mlamg.spmv(L0.R, r, bc)),
+                     ("L0 prolong P", lambda: mlamg.spmv_add(L0.P, bc, xo)),
+                     ("L0 jacobi_zero", lambda: mlamg.jacobi_zero(L0.dw, b, xo))]:
+        print(name, "ms", round(timeit(fn), 4))
+    print("P nnz", L0.P.nnz, "mean row", L0.P.nnz / N, "R mean row", L0.R.nnz / L0.R.shape[0])
     x, res = H.solve(b, tol=1e-8, maxiter=100, accel="cg", return_residuals=True)
     print("pcg iters", len(res) - 1, "final rel res", res[-1] / res[0])
 
