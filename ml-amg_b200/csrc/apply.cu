@@ -46,17 +46,26 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     if (row < n) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
-        int j = start + lane;
-        for (; j + 3 * LANES < end; j += 4 * LANES) {
-            const int c0 = col[j], c1 = col[j + LANES], c2 = col[j + 2 * LANES], c3 = col[j + 3 * LANES];
-            const T v0 = val[j], v1 = val[j + LANES], v2 = val[j + 2 * LANES], v3 = val[j + 3 * LANES];
-            const T x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+        // batches of 4 predicated entries per lane: all col/val loads, then all x gathers, then the FMAs
+        for (int j = start + lane; j < end; j += 4 * LANES) {
+            const bool p1 = j + LANES < end, p2 = j + 2 * LANES < end, p3 = j + 3 * LANES < end;
+            const int c0 = col[j];
+            const int c1 = p1 ? col[j + LANES] : 0;
+            const int c2 = p2 ? col[j + 2 * LANES] : 0;
+            const int c3 = p3 ? col[j + 3 * LANES] : 0;
+            const T v0 = val[j];
+            const T v1 = p1 ? val[j + LANES] : (T)0;
+            const T v2 = p2 ? val[j + 2 * LANES] : (T)0;
+            const T v3 = p3 ? val[j + 3 * LANES] : (T)0;
+            const T x0 = x[c0];
+            const T x1 = p1 ? x[c1] : (T)0;
+            const T x2 = p2 ? x[c2] : (T)0;
+            const T x3 = p3 ? x[c3] : (T)0;
             sum += v0 * x0;
             sum += v1 * x1;
             sum += v2 * x2;
             sum += v3 * x3;
         }
-        for (; j < end; j += LANES) sum += val[j] * x[col[j]];
     }
     if (LANES > 1) sum = group_sum<LANES>(sum);
     double rr = 0.0;
@@ -86,20 +95,24 @@ sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restric
         const int width = (slice_ptr[slice + 1] - base) >> 5;
         const int *c = col + base + lane;
         const T *v = val + base + lane;
-        int k = 0;
-        for (; k + 4 <= width; k += 4) {
-            const int c0 = c[32 * k], c1 = c[32 * (k + 1)], c2 = c[32 * (k + 2)], c3 = c[32 * (k + 3)];
-            const T v0 = v[32 * k], v1 = v[32 * (k + 1)], v2 = v[32 * (k + 2)], v3 = v[32 * (k + 3)];
-            const T x0 = c0 >= 0 ? x[c0] : (T)0, x1 = c1 >= 0 ? x[c1] : (T)0;
-            const T x2 = c2 >= 0 ? x[c2] : (T)0, x3 = c3 >= 0 ? x[c3] : (T)0;
+        for (int k = 0; k < width; k += 4) {
+            const bool p1 = k + 1 < width, p2 = k + 2 < width, p3 = k + 3 < width;
+            const int c0 = c[32 * k];
+            const int c1 = p1 ? c[32 * (k + 1)] : -1;
+            const int c2 = p2 ? c[32 * (k + 2)] : -1;
+            const int c3 = p3 ? c[32 * (k + 3)] : -1;
+            const T v0 = v[32 * k];
+            const T v1 = p1 ? v[32 * (k + 1)] : (T)0;
+            const T v2 = p2 ? v[32 * (k + 2)] : (T)0;
+            const T v3 = p3 ? v[32 * (k + 3)] : (T)0;
+            const T x0 = c0 >= 0 ? x[c0] : (T)0;
+            const T x1 = c1 >= 0 ? x[c1] : (T)0;
+            const T x2 = c2 >= 0 ? x[c2] : (T)0;
+            const T x3 = c3 >= 0 ? x[c3] : (T)0;
             sum += v0 * x0;
             sum += v1 * x1;
             sum += v2 * x2;
             sum += v3 * x3;
-        }
-        for (; k < width; k++) {
-            const int c0 = c[32 * k];
-            if (c0 >= 0) sum += v[32 * k] * x[c0];
         }
     }
     double rr = 0.0;
@@ -115,12 +128,13 @@ static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1
 
 static int pick_lanes(int n, long long nnz) {
     if (g_force_lanes > 0) return g_force_lanes;
+    // ~8-12 entries per lane: enough independent loads per thread to cover HBM latency
     const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
-    if (mean <= 4.0) return 1;
-    if (mean <= 8.0) return 2;
-    if (mean <= 16.0) return 4;
-    if (mean <= 32.0) return 8;
-    if (mean <= 64.0) return 16;
+    if (mean <= 12.0) return 1;
+    if (mean <= 24.0) return 2;
+    if (mean <= 48.0) return 4;
+    if (mean <= 128.0) return 8;
+    if (mean <= 384.0) return 16;
     return 32;
 }
 

@@ -59,6 +59,15 @@ def rel_hist_err(a, b):
     return np.max(np.abs(a[:n] - b[:n]) / np.maximum(np.abs(b[:n]), 1e-300))
 
 
+def hist_err0(a, b):
+    """residual-history parity measure: max |a_i - b_i| / b_0.  Deep into convergence the residual
+    b - A x is itself only known to eps*||A|| ||x||, so parity is stated relative to the initial
+    residual (the 1e-12 north-star bar); early entries are also checked entry-relative."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    n = min(len(a), len(b))
+    return np.max(np.abs(a[:n] - b[:n])) / max(abs(b[0]), 1e-300)
+
+
 def random_csr(n, m, density, seed, dtype=np.float64, empty_rows=True):
     rs = np.random.RandomState(seed)
     A = sp.random(n, m, density=density, random_state=rs, format="csr", dtype=np.float64)

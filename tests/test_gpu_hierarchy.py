@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, assert_csr_bitwise, rel_hist_err, canonical
+from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, assert_csr_bitwise, rel_hist_err, hist_err0, canonical
 from oracle import reference_path as rp, multilevel as oml, pyamg_restated as pr
 
 pytestmark = pytest.mark.gpu
@@ -42,13 +42,13 @@ def test_amg_2_v_mirror_vs_reference_golden(name):
     x0 /= np.linalg.norm(x0, 2)
     x, conv, err, nit = mg.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-10)
     assert nit == int(z["gs_nit"])
-    assert rel_hist_err(err, z["gs_err"]) < 1e-9        # 40+ iterations down to 1e-10: see DESIGN.md parity notes
+    assert hist_err0(err, z["gs_err"]) < RTOL64          # whole history, relative to the initial residual
     assert rel_hist_err(err[:10], z["gs_err"][:10]) < RTOL64 * 10
     assert abs(conv - float(z["gs_conv"])) < 1e-9
     assert np.abs(x - z["gs_x"]).max() < 1e-12
     b2 = np.random.RandomState(1).randn(n)
     x, conv, err, nit = mg.amg_2_v(A, P, b2, np.zeros(n), res_tol=1e-8, pre_smoothing_steps=2, post_smoothing_steps=2)
-    assert nit == int(z["gs2_nit"]) and rel_hist_err(err[:10], z["gs2_err"][:10]) < RTOL64 * 10
+    assert nit == int(z["gs2_nit"]) and hist_err0(err, z["gs2_err"]) < RTOL64
     xj = mg.jacobi(A, b2, x0.copy(), omega=0.666, nu=3)
     assert np.abs(xj - z["jacobi_x"]).max() <= 1e-13 * np.abs(z["jacobi_x"]).max()
 
@@ -65,7 +65,7 @@ def test_amg_2_v_jacobi_and_error_tol_and_singular():
         got = mg.amg_2_v(A, P, np.zeros(n), x0, smoother="jacobi", jacobi_weight=2 / 3, **kw)
         assert got[3] == ref[3]
         assert rel_hist_err(got[2][:12], ref[2][:12]) < RTOL64 * 10
-        assert rel_hist_err(got[2], ref[2]) < 1e-8
+        assert hist_err0(got[2], ref[2]) < RTOL64
     with pytest.raises(RuntimeError):
         mg.amg_2_v(A, P, np.zeros(n), x0)
     # singular coarse operator: (x, 1.0, err, 0) without raising (multigrid.py:166-170)
@@ -116,11 +116,11 @@ def test_multilevel_setup_and_cycles_fp64(shape, ratio, smoother):
     xr, res_r = oml.solve(ref, b, tol=1e-8, maxiter=60)
     xg, res_g = H.solve(b, tol=1e-8, maxiter=60, return_residuals=True)
     assert len(res_g) == len(res_r)
-    assert rel_hist_err(res_g, res_r) < 1e-10 and rel_hist_err(res_g[:8], res_r[:8]) < RTOL64 * 10
+    assert hist_err0(res_g, res_r) < RTOL64 and rel_hist_err(res_g[:8], res_r[:8]) < RTOL64 * 10
     xr, res_r, it_r = oml.pcg(ref, b, tol=1e-8, maxiter=100)
     xg, res_g = H.solve(b, tol=1e-8, maxiter=100, accel="cg", return_residuals=True)
     assert len(res_g) - 1 == it_r
-    assert rel_hist_err(res_g[:6], res_r[:6]) < RTOL64 * 100
+    assert hist_err0(res_g, res_r) < RTOL64 * 10 and rel_hist_err(res_g[:6], res_r[:6]) < RTOL64 * 100
     assert np.linalg.norm(b - A @ xg) <= 2e-8 * np.linalg.norm(b)
     # preconditioner through host buffers and scipy CG
     import scipy.sparse.linalg as spla

@@ -34,7 +34,7 @@ def main():
         dw = mlamg.smoother_diag(A, "jacobi", 2 / 3)
         B_spmv = nnz * (v + 4) + 4 * (N + 1) + 2 * v * N
         B_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
-        timeit(lambda: mlamg.spmv(A, x, y), reps=30)     # clock ramp
+        timeit(lambda: mlamg.spmv(A, x, y), reps=600)    # ~1 s busy: let the clocks settle
         t = timeit(lambda: mlamg.spmv(A, x, y))
         out[f"spmv_{v*8}"] = dict(ms=t, gbs=B_spmv / t / 1e6)
         t = timeit(lambda: mlamg.jacobi_sweep(A, dw, b, x, y))
@@ -98,6 +98,23 @@ def main():
                      ("L0 prolong P", lambda: mlamg.spmv_add(L0.P, bc, xo)),
                      ("L0 jacobi_zero", lambda: mlamg.jacobi_zero(L0.dw, b, xo))]:
         print(name, "ms", round(timeit(fn), 4))
+    for lanes in (2, 4, 8, 16, 32):
+        mlamg.set_csr_lanes(lanes)
+        print("R lanes", lanes, "ms", round(timeit(lambda: mlamg.spmv(L0.R, r, bc)), 4))
+    for lanes in (1, 2, 4):
+        mlamg.set_csr_lanes(lanes)
+        print("P lanes", lanes, "ms", round(timeit(lambda: mlamg.spmv_add(L0.P, bc, xo)), 4))
+    for lanes in (1, 2, 4):
+        mlamg.set_csr_lanes(lanes)
+        print("A csr jacobi lanes", lanes, "ms", round(timeit(lambda: mlamg.jacobi_sweep(L0.A, L0.dw, b, xo, r)), 4))
+    mlamg.set_csr_lanes(-1)
+    L1 = H.levels[1]
+    b1 = torch.randn(L1.A.shape[0], dtype=b.dtype, device="cuda"); x1 = torch.randn_like(b1); y1 = torch.empty_like(b1)
+    print("L1 jacobi sell" if L1.sell else "L1 (no sell)", "ms", round(timeit(lambda: L1.sell.jacobi_sweep(L1.dw, b1, x1, y1)), 4) if L1.sell else "", "padding", L1.sell.padding if L1.sell else None)
+    for lanes in (1, 2, 4, 8):
+        mlamg.set_csr_lanes(lanes)
+        print("L1 csr jacobi lanes", lanes, "ms", round(timeit(lambda: mlamg.jacobi_sweep(L1.A, L1.dw, b1, x1, y1)), 4))
+    mlamg.set_csr_lanes(-1)
     print("P nnz", L0.P.nnz, "mean row", L0.P.nnz / N, "R mean row", L0.R.nnz / L0.R.shape[0])
     x, res = H.solve(b, tol=1e-8, maxiter=100, accel="cg", return_residuals=True)
     print("pcg iters", len(res) - 1, "final rel res", res[-1] / res[0])
