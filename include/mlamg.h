@@ -49,6 +49,10 @@ long long mlamg_launch_count(void);
 /* y = A x.              multigrid.py:44,181,191  MLAMG.py:145,191,194 (scipy csr_matvec) */
 int mlamg_spmv_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                    const void *x, void *y, mlamg_stream_t stream);
+/* y = A x with the rows visited in the order row_order[0..n) (a permutation; NULL = natural order).
+ * Same result as mlamg_spmv_csr; the order only steers cache reuse of the gathers. */
+int mlamg_spmv_csr_perm(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                        const void *x, void *y, const int *row_order, mlamg_stream_t stream);
 /* y += A x.             prolongation x += P e_c: multigrid.py:181, MLAMG.py:191 */
 int mlamg_spmv_add_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                        const void *x, void *y, mlamg_stream_t stream);
@@ -181,6 +185,8 @@ int mlamg_hierarchy_create(int dtype, int nlevels, mlamg_hierarchy_t *out);
 /* Level l operator and smoother diagonal (non-owning device pointers; caller keeps them alive). */
 int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz, const int *rowptr,
                                  const int *col, const void *val, const void *dw);
+/* optional processing order of the rows of R between level l and l+1 (see mlamg_spmv_csr_perm) */
+int mlamg_hierarchy_set_restrict_order(mlamg_hierarchy_t h, int level, const int *row_order);
 /* optional SELL-32 copy of level l's operator; when present the smoother and residual kernels use it */
 int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int *slice_ptr, const int *scol,
                                       const void *sval);

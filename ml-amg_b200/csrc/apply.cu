@@ -38,11 +38,16 @@ template <typename T, int LANES, int OP, bool NORM>
 __global__ void __launch_bounds__(ROW_THREADS)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
-                 const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial) {
+                 const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial,
+                 const int *__restrict__ row_order) {
     const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
-    const long long row = gtid / LANES;
+    long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
     T sum = (T)0;
+    // row_order: optional processing order (a permutation of the rows).  Used by the restriction, whose
+    // rows (aggregates) are numbered randomly by the reference's seeding: visiting them in spatial order
+    // lets neighbouring aggregates share the fine-vector sectors they gather through L2.
+    if (row < n && row_order) row = row_order[row];
     if (row < n) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
@@ -130,17 +135,20 @@ static int pick_lanes(int n, long long nnz) {
     if (g_force_lanes > 0) return g_force_lanes;
     // ~8-12 entries per lane: enough independent loads per thread to cover HBM latency
     const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
-    if (mean <= 12.0) return 1;
-    if (mean <= 24.0) return 2;
-    if (mean <= 48.0) return 4;
-    if (mean <= 128.0) return 8;
-    if (mean <= 384.0) return 16;
-    return 32;
+    int lanes = 32;
+    if (mean <= 12.0) lanes = 1;
+    else if (mean <= 24.0) lanes = 2;
+    else if (mean <= 48.0) lanes = 4;
+    else if (mean <= 128.0) lanes = 8;
+    else if (mean <= 384.0) lanes = 16;
+    // small levels: not enough rows to fill 148 SMs -> spend more lanes per row (up to the row length)
+    while (lanes < 32 && (long long)n * lanes < 148LL * 1024 && 2.0 * lanes <= mean) lanes *= 2;
+    return lanes;
 }
 
 template <typename T, int OP, bool NORM>
 static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *x,
-                        const T *b, const T *dw, T *y, double *norm2, cudaStream_t s) {
+                        const T *b, const T *dw, T *y, double *norm2, cudaStream_t s, const int *row_order = nullptr) {
     if (n <= 0) {
         if (NORM && norm2) MLAMG_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double), s));
         return MLAMG_OK;
@@ -154,7 +162,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
         partial = part.as<double>();
     }
 #define LAUNCH(L)                                                                                       \
-    csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial)
+    csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row_order)
     switch (lanes) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -242,6 +250,13 @@ template <typename T>
 int spmv_t(int n, long long nnz, const int *rowptr, const int *col, const T *val, const T *x, T *y, cudaStream_t s) {
     return launch_rowop<T, OP_SPMV, false>(n, nnz, rowptr, col, val, x, nullptr, nullptr, y, nullptr, s);
 }
+template <typename T>
+int spmv_perm_t(int n, long long nnz, const int *rowptr, const int *col, const T *val, const T *x, T *y,
+                const int *row_order, cudaStream_t s) {
+    return launch_rowop<T, OP_SPMV, false>(n, nnz, rowptr, col, val, x, nullptr, nullptr, y, nullptr, s, row_order);
+}
+template int spmv_perm_t<float>(int, long long, const int *, const int *, const float *, const float *, float *, const int *, cudaStream_t);
+template int spmv_perm_t<double>(int, long long, const int *, const int *, const double *, const double *, double *, const int *, cudaStream_t);
 template <typename T>
 int spmv_add_t(int n, long long nnz, const int *rowptr, const int *col, const T *val, const T *x, T *y,
                cudaStream_t s) {
@@ -367,6 +382,15 @@ int mlamg_spmv_csr(int dtype, int n, int nnz, const int *rowptr, const int *col,
     if (n < 0) return set_error(MLAMG_EINVAL, "spmv: n < 0");
     if (x == y) return set_error(MLAMG_EINVAL, "spmv: x aliases y");
     MLAMG_DISPATCH(dtype, return spmv_t<T>(n, nnz, rowptr, col, (const T *)val, (const T *)x, (T *)y, s));
+    return MLAMG_OK;
+}
+
+int mlamg_spmv_csr_perm(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val, const void *x,
+                        void *y, const int *row_order, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "spmv_perm: n < 0");
+    if (x == y) return set_error(MLAMG_EINVAL, "spmv_perm: x aliases y");
+    MLAMG_DISPATCH(dtype, return spmv_perm_t<T>(n, nnz, rowptr, col, (const T *)val, (const T *)x, (T *)y, row_order, s));
     return MLAMG_OK;
 }
 

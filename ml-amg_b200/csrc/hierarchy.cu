@@ -15,6 +15,8 @@
 namespace mlamg {
 
 template <typename T> int spmv_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
+template <typename T>
+int spmv_perm_t(int, long long, const int *, const int *, const T *, const T *, T *, const int *, cudaStream_t);
 template <typename T> int spmv_add_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
 template <typename T>
 int residual_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, double *, cudaStream_t);
@@ -37,6 +39,7 @@ struct Csr {
 struct LevelData {
     Csr A, P, R;
     const void *dw = nullptr;
+    const int *r_order = nullptr;                           // optional processing order of the rows of R
     const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A
     const void *sell_val = nullptr;
     bool has_A = false, has_PR = false;
@@ -127,7 +130,7 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
         MLAMG_TRY(level_residual<T>(lev, rhs[l], c, (T *)lev.r, nullptr, s));
         const Csr &R = lev.R;
         T *bc = (T *)h->lv[l + 1].b;
-        MLAMG_TRY(spmv_t<T>(R.n, R.nnz, R.rowptr, R.col, (const T *)R.val, (const T *)lev.r, bc, s));
+        MLAMG_TRY(spmv_perm_t<T>(R.n, R.nnz, R.rowptr, R.col, (const T *)R.val, (const T *)lev.r, bc, lev.r_order, s));
         rhs[l + 1] = bc;
     }
     // ---- coarsest level: exact solve with the dense inverse
@@ -233,6 +236,14 @@ int mlamg_hierarchy_set_operator(mlamg_hierarchy_t h, int level, int n, int nnz,
     lev.A.n = n; lev.A.nnz = nnz; lev.A.rowptr = rowptr; lev.A.col = col; lev.A.val = val;
     lev.dw = dw;
     lev.has_A = true;
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_restrict_order(mlamg_hierarchy_t h, int level, const int *row_order) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level + 1 >= (int)h->lv.size()) return set_error(MLAMG_EINVAL, "set_restrict_order: bad level");
+    h->lv[level].r_order = row_order;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     return MLAMG_OK;
 }
 

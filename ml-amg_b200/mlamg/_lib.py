@@ -24,6 +24,8 @@ SIGNATURES = {
     "mlamg_launch_count": (LL, []),
     "mlamg_spmv_csr": (I, [I, I, I, P, P, P, P, P, P]),
     "mlamg_spmv_add_csr": (I, [I, I, I, P, P, P, P, P, P]),
+    "mlamg_spmv_csr_perm": (I, [I, I, I, P, P, P, P, P, P, P]),
+    "mlamg_hierarchy_set_restrict_order": (I, [P, I, P]),
     "mlamg_residual_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_zero": (I, [I, I, P, P, P, P]),

@@ -213,6 +213,17 @@ def spmv(A, x, out=None):
     return out
 
 
+def spmv_perm(A, x, row_order, out=None):
+    """y = A x, rows visited in `row_order` (int32 permutation) — same result, different cache behaviour."""
+    n, m = A.shape
+    assert x.numel() == m and row_order.numel() == n and row_order.dtype == torch.int32
+    if out is None:
+        out = torch.empty(n, dtype=A.dtype, device=x.device)
+    check(lib.mlamg_spmv_csr_perm(dt(A.val), n, A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(x), ptr(out),
+                                  ptr(row_order), stream()))
+    return out
+
+
 def spmv_add(A, x, y):
     """y += A x (prolongation-and-correct)."""
     n, m = A.shape

@@ -98,10 +98,12 @@ class Level:
 class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
-    def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="auto",
-                 sell_max_padding=1.5):
-        """sell: 'auto' -> levels whose SELL-32 padding stays below sell_max_padding get a SELL copy of A for the
-        smoother/residual kernels; 'never' -> CSR kernels only; 'always'."""
+    def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
+                 sell_max_padding=1.5, restrict_order=True):
+        """sell: 'never' (default) -> CSR kernels only: measured on B200 at 256^3 the thread-per-row CSR kernel
+        with predicated 4-entry batches (0.322 ms/sweep) is as fast as SELL-32 (0.337 ms), so the second copy
+        of A is not worth its HBM; 'auto' -> levels whose SELL-32 padding stays below sell_max_padding get a
+        SELL copy of A for the smoother/residual kernels; 'always'."""
         core.require_cuda()
         self.levels = levels
         self.dtype = levels[0].A.dtype
@@ -126,6 +128,16 @@ class Hierarchy:
             P, R = lev.P, lev.R
             check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
                                                    ptr(R.rowptr), ptr(R.col), ptr(R.val)))
+        # Restriction rows (aggregates) carry the reference's random seed numbering; visit them in the order
+        # of their first fine node so neighbouring aggregates share the sectors of r they gather (L2 reuse).
+        self._r_order = []
+        if restrict_order:
+            for l, lev in enumerate(levels[:-1]):
+                R = lev.R
+                first = R.col[R.rowptr[:-1].long().clamp(max=max(R.nnz - 1, 0))]
+                order = torch.argsort(first, stable=True).to(torch.int32).contiguous()
+                self._r_order.append(order)
+                check(lib.mlamg_hierarchy_set_restrict_order(self._h, l, ptr(order)))
         check(lib.mlamg_hierarchy_set_coarse_inverse(self._h, ptr(self.coarse_inv)))
         check(lib.mlamg_hierarchy_finalize(self._h, stream()))
         if use_graph:
@@ -222,7 +234,7 @@ class Hierarchy:
 
 def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
                     P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
-                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="auto"):
+                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never"):
     """Build the multilevel hierarchy on the device.
 
     A           : scipy / torch sparse / DeviceCSR

@@ -260,3 +260,14 @@ def test_csr_lane_variants(lanes):
             close(y, A @ x, np.float64, (abs(A) @ np.abs(x)).max())
     finally:
         mlamg.set_csr_lanes(-1)
+
+
+def test_spmv_row_order_is_result_invariant():
+    import mlamg
+    A = random_csr(700, 300, 0.05, 21)
+    x = np.random.RandomState(3).randn(300)
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    order = torch.from_numpy(np.random.RandomState(4).permutation(700).astype(np.int32)).cuda()
+    y0 = mlamg.spmv(Ad, dev(x, np.float64))
+    y1 = mlamg.spmv_perm(Ad, dev(x, np.float64), order)
+    assert torch.equal(y0, y1)
