@@ -80,6 +80,14 @@ int mlamg_sell_fill(int dtype, int n, const int *rowptr, const int *col, const v
 /* op: 0 y = A x | 1 y += A x | 2 y = b - A x (+ *norm2 = ||y||^2 if norm2 != NULL) | 3 y = x + dw.*(b - A x) */
 int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *scol, const void *sval,
                      const void *x, const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream);
+/* generic row-op over all rows (row_list == NULL) or the subset row_list[0..nrows):
+ * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax).  Used by the row-partitioned multi-GPU levels
+ * to run interior rows while the halo exchange of x is in flight, then the boundary rows. */
+int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
+                    const void *x, const void *b, const void *dw, void *y, const int *row_list, double *norm2,
+                    mlamg_stream_t stream);
+/* halo pack: dst[i] = src[idx[i]] */
+int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, mlamg_stream_t stream);
 /* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32), -1 = heuristic */
 int mlamg_set_csr_lanes(int lanes);
 /* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
@@ -158,6 +166,10 @@ int mlamg_lambda_max(int dtype, int n, const int *rowptr, const int *col, const 
 long long mlamg_poisson_nnz(int nx, int ny, int nz);
 int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, void *val,
                       mlamg_stream_t stream);
+/* rows of the z-slab [z0, z0+nz_local) of the global grid, GLOBAL column ids (weak-scaling generator);
+ * col/val capacity 7*nx*ny*nz_local, *nnz_host = entries written */
+int mlamg_poisson_csr_slab(int dtype, int nx, int ny, int nz, int z0, int nz_local, int *rowptr, int *col,
+                           void *val, long long *nnz_host, mlamg_stream_t stream);
 
 /* ------------------------------------------------------------------ aggregation */
 

@@ -324,6 +324,14 @@ __global__ void __launch_bounds__(256) smoother_diag_kernel(int mode, T omega, i
     if (row < n && lane == 0) dw[row] = (mode == 0) ? omega / d : (T)1 / l1;
 }
 
+// halo pack: dst[i] = src[idx[i]]
+template <typename T>
+__global__ void __launch_bounds__(256) gather_kernel(int n, const int *__restrict__ idx, const T *__restrict__ src,
+                                                     T *__restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
 // ---- SpMM: Y = alpha * A X + beta * Y, X/Y row-major N x k (k small) --------------------------
 // one warp per row; lanes span the k columns (k <= 32 per pass), coalesced reads of X rows.
 template <typename T>
@@ -447,6 +455,40 @@ int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, c
     if (X == Y) return set_error(MLAMG_EINVAL, "spmm: X aliases Y");
     MLAMG_DISPATCH(dtype, (spmm_kernel<T><<<cdiv((long long)n * 32, 256), 256, 0, s>>>(
                               n, k, rowptr, col, (const T *)val, (const T *)X, (T *)Y, (T)alpha, (T)beta)));
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+// generic row-op entry: op 0 spmv | 1 spmv_add | 2 residual(+norm2) | 3 jacobi, over all rows
+// (row_list == NULL, nrows = n) or over the subset row_list[0..nrows) (interior / boundary splits of
+// the row-partitioned multi-GPU levels: interior rows run while the halo exchange is in flight).
+int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
+                    const void *x, const void *b, const void *dw, void *y, const int *row_list, double *norm2,
+                    mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (nrows < 0) return set_error(MLAMG_EINVAL, "rowop: nrows < 0");
+    if (x == y) return set_error(MLAMG_EINVAL, "rowop: x aliases y");
+#define ROWOP_CASE(OPC, NRM) \
+    MLAMG_DISPATCH(dtype, return (launch_rowop<T, OPC, NRM>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x, \
+                                                             (const T *)b, (const T *)dw, (T *)y, norm2, s, row_list)))
+    switch (op) {
+        case OP_SPMV: ROWOP_CASE(OP_SPMV, false); break;
+        case OP_SPMV_ADD: ROWOP_CASE(OP_SPMV_ADD, false); break;
+        case OP_RESIDUAL:
+            if (norm2) { ROWOP_CASE(OP_RESIDUAL, true); } else { ROWOP_CASE(OP_RESIDUAL, false); }
+            break;
+        case OP_JACOBI: ROWOP_CASE(OP_JACOBI, false); break;
+        default: return set_error(MLAMG_EINVAL, "rowop: bad op %d", op);
+    }
+#undef ROWOP_CASE
+    return MLAMG_OK;
+}
+
+int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n <= 0) return n == 0 ? MLAMG_OK : set_error(MLAMG_EINVAL, "gather: n < 0");
+    unsigned blocks = cdiv(n, 256);
+    MLAMG_DISPATCH(dtype, (gather_kernel<T><<<blocks, 256, 0, s>>>(n, idx, (const T *)src, (T *)dst)));
     MLAMG_LAUNCHED();
     return MLAMG_OK;
 }

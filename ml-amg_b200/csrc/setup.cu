@@ -266,24 +266,27 @@ __device__ __forceinline__ int stencil_count(int x, int y, int z, int nx, int ny
     return 1 + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
 }
 
-__global__ void __launch_bounds__(256) poisson_count_kernel(int nx, int ny, int nz, int *__restrict__ cnt) {
+// rows of the z-slab [z0, z0+nzl) of the global nx x ny x nz grid; i is the LOCAL row index
+__global__ void __launch_bounds__(256) poisson_count_kernel(int nx, int ny, int nz, int z0, int nzl, int *__restrict__ cnt) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long N = (long long)nx * ny * nz;
+    const long long N = (long long)nx * ny * nzl;
     if (i >= N) return;
-    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = z0 + (int)(i / ((long long)nx * ny));
     cnt[i] = stencil_count(x, y, z, nx, ny, nz);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) poisson_fill_kernel(int nx, int ny, int nz, const int *__restrict__ rowptr,
-                                                           int *__restrict__ col, T *__restrict__ val) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long N = (long long)nx * ny * nz;
-    if (i >= N) return;
-    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
-    const T diag = (T)(2 * ((nx > 1) + (ny > 1) + (nz > 1)));
-    int p = rowptr[i];
+__global__ void __launch_bounds__(256) poisson_fill_kernel(int nx, int ny, int nz, int z0, int nzl,
+                                                           const int *__restrict__ rowptr, int *__restrict__ col,
+                                                           T *__restrict__ val) {
+    const long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long N = (long long)nx * ny * nzl;
+    if (il >= N) return;
     const long long sxy = (long long)nx * ny;
+    const long long i = il + (long long)z0 * sxy;     // GLOBAL row = global column of the diagonal
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / sxy);
+    const T diag = (T)(2 * ((nx > 1) + (ny > 1) + (nz > 1)));
+    int p = rowptr[il];
     if (z > 0) { col[p] = (int)(i - sxy); val[p++] = (T)-1; }
     if (y > 0) { col[p] = (int)(i - nx); val[p++] = (T)-1; }
     if (x > 0) { col[p] = (int)(i - 1); val[p++] = (T)-1; }
@@ -511,18 +514,31 @@ long long mlamg_poisson_nnz(int nx, int ny, int nz) {
     return X * Y * Z + 2 * ((X - 1) * Y * Z + X * (Y - 1) * Z + X * Y * (Z - 1));
 }
 
-int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, void *val, mlamg_stream_t stream) {
+int mlamg_poisson_csr_slab(int dtype, int nx, int ny, int nz, int z0, int nz_local, int *rowptr, int *col, void *val,
+                           long long *nnz_host, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
-    if (nx < 1 || ny < 1 || nz < 1) return set_error(MLAMG_EINVAL, "poisson: bad shape");
-    const long long N = (long long)nx * ny * nz;
-    if (N > 0x7fffffffLL || mlamg_poisson_nnz(nx, ny, nz) > 0x7fffffffLL)
+    if (nx < 1 || ny < 1 || nz < 1 || z0 < 0 || nz_local < 1 || z0 + nz_local > nz)
+        return set_error(MLAMG_EINVAL, "poisson: bad shape / slab");
+    const long long N = (long long)nx * ny * nz_local;
+    if ((long long)nx * ny * nz > 0x7fffffffLL || 7 * N > 0x7fffffffLL)
         return set_error(MLAMG_ELIMIT, "poisson: int32 index overflow");
-    poisson_count_kernel<<<cdiv(N, 256), 256, 0, s>>>(nx, ny, nz, rowptr);
+    poisson_count_kernel<<<cdiv(N, 256), 256, 0, s>>>(nx, ny, nz, z0, nz_local, rowptr);
     MLAMG_LAUNCHED();
     MLAMG_TRY(exclusive_scan_i32(rowptr, rowptr, (int)N, s));
-    MLAMG_DISPATCH(dtype, (poisson_fill_kernel<T><<<cdiv(N, 256), 256, 0, s>>>(nx, ny, nz, rowptr, col, (T *)val)));
+    MLAMG_DISPATCH(dtype, (poisson_fill_kernel<T><<<cdiv(N, 256), 256, 0, s>>>(nx, ny, nz, z0, nz_local, rowptr, col,
+                                                                            (T *)val)));
     MLAMG_LAUNCHED();
+    if (nnz_host) {
+        int h = 0;
+        MLAMG_CUDA(cudaMemcpyAsync(&h, rowptr + N, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MLAMG_CUDA(cudaStreamSynchronize(s));
+        *nnz_host = h;
+    }
     return MLAMG_OK;
+}
+
+int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, void *val, mlamg_stream_t stream) {
+    return mlamg_poisson_csr_slab(dtype, nx, ny, nz, 0, nz, rowptr, col, val, nullptr, stream);
 }
 
 int mlamg_lambda_max(int dtype, int n, const int *rowptr, const int *col, const void *val, int iters, void *work,

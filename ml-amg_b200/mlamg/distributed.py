@@ -1,0 +1,565 @@
+"""Row-partitioned multi-GPU levels: one process per GPU, contiguous row blocks,
+halo exchange over NCCL (NVLink 5 / NVSwitch) overlapped with the interior rows, coarse levels
+agglomerated (replicated on every rank) below a size threshold.  The reference has no distributed
+solve (its only parallelism is a task farm of independent CPU solves, ns/parallel/), so the distributed
+algorithm is DEFINED here and mirrored on the CPU by `oracle.multilevel.build_hierarchy(partition=…)`:
+
+  * aggregation: Lloyd on each rank's diagonal block (aggregates never straddle ranks; coarse dofs are
+    numbered rank by rank, so every coarse level is again a contiguous row partition);
+  * P = (I - w D^-1 A) Agg and A_H = P^T A P are the GLOBAL matrices, each rank computing its rows with
+    the same ordered SpGEMM (rows keep their ascending-global stored order, so values are bit-identical
+    to the single-domain scipy computation on the same aggregates);
+  * cycle: per operator application one halo exchange of vector entries (`all_to_all_single` =
+    grouped ncclSend/ncclRecv) issued on a side stream while the interior rows run; boundary rows
+    follow.  Norms/dots: one 8-byte allreduce.  Below `replicate_below` global rows the level is
+    all-gathered and every rank runs the single-GPU hierarchy for the levels beneath it (one
+    all-gather of the restricted residual per cycle, no further communication).
+
+The plumbing below (partition, halo plans, row fetch, distributed transpose) is plain torch tensor
+code and works on CPU tensors with the gloo backend — that is how `tests/test_dist_cpu.py` covers it
+with world_size 2.  Everything numerical runs in libmlamg_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import core
+from . import hierarchy as hmod
+from ._lib import lib, check
+
+
+# =====================================================================================================
+# communicator helpers
+# =====================================================================================================
+class Comm:
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def all_gather_int(self, v):
+        """python int per rank -> list of ints"""
+        if self.world == 1:
+            return [int(v)]
+        out = [None] * self.world
+        dist.all_gather_object(out, int(v), group=self.group)
+        return out
+
+    def a2a(self, send, send_splits, recv_splits, out=None):
+        """variable all-to-all of a 1-D tensor; splits are python int lists (elements per peer)"""
+        n_recv = int(sum(recv_splits))
+        if out is None:
+            out = torch.empty(n_recv, dtype=send.dtype, device=send.device)
+        if self.world == 1:
+            if n_recv:
+                out.copy_(send)
+            return out
+        dist.all_to_all_single(out, send.contiguous(), list(recv_splits), list(send_splits), group=self.group)
+        return out
+
+    def a2a_counts(self, counts):
+        """counts[p] = elements I send to p  ->  elements I receive from each p"""
+        if self.world == 1:
+            return list(counts)
+        t = torch.tensor(counts, dtype=torch.int64)
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = t.to(dev)
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t, group=self.group)
+        return [int(v) for v in out.cpu()]
+
+    def all_gather_cat(self, t):
+        """concatenate 1-D tensors of different length in rank order"""
+        if self.world == 1:
+            return t
+        sizes = self.all_gather_int(t.numel())
+        pad = max(max(sizes), 1)                      # equal-size collective (gloo and NCCL both take it)
+        mine = torch.zeros(pad, dtype=t.dtype, device=t.device)
+        mine[:t.numel()] = t
+        outs = [torch.empty(pad, dtype=t.dtype, device=t.device) for _ in sizes]
+        dist.all_gather(outs, mine, group=self.group)
+        return torch.cat([o[:s] for o, s in zip(outs, sizes)])
+
+    def allreduce_sum(self, value):
+        if self.world == 1:
+            return float(value)
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, group=self.group)
+        return float(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+def partition_offsets(n_local, comm):
+    counts = comm.all_gather_int(n_local)
+    return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+
+def owners_of(ids, offsets):
+    """rank owning each global id (ids: int tensor)"""
+    bounds = torch.as_tensor(offsets[1:], dtype=torch.int64, device=ids.device)
+    return torch.searchsorted(bounds, ids.to(torch.int64), right=True)
+
+
+# =====================================================================================================
+# CSR plumbing on raw tensors (rowptr int32, col int32 GLOBAL ids, val)
+# =====================================================================================================
+def row_lengths(rowptr):
+    return (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+
+
+def rowptr_from_lengths(lengths):
+    rp = torch.zeros(lengths.numel() + 1, dtype=torch.int64, device=lengths.device)
+    rp[1:] = torch.cumsum(lengths, 0)
+    return rp.to(torch.int32)
+
+
+def localize(col_global, n_own, lo, offsets=None):
+    """global column ids -> local ext numbering [owned 0..n_own) | halo n_own..); stored order kept.
+    Returns (col_local int32, halo_ids int64 sorted unique)."""
+    c = col_global.to(torch.int64)
+    own = (c >= lo) & (c < lo + n_own)
+    halo_ids = torch.unique(c[~own])           # sorted
+    loc = torch.where(own, c - lo, n_own + torch.searchsorted(halo_ids, c))
+    return loc.to(torch.int32), halo_ids
+
+
+def csr_vstack(parts):
+    """stack row blocks [(rowptr, col, val), …] (same column space)"""
+    lens = torch.cat([row_lengths(p[0]) for p in parts])
+    return rowptr_from_lengths(lens), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts])
+
+
+def select_rows(rowptr, col, val, rows):
+    """rows (int64 local indices, any order) -> CSR of those rows"""
+    lens = row_lengths(rowptr)[rows]
+    starts = rowptr.to(torch.int64)[rows]
+    total = int(lens.sum())
+    excl = torch.cumsum(lens, 0) - lens
+    ent = torch.repeat_interleave(starts - excl, lens) + torch.arange(total, device=col.device)
+    return rowptr_from_lengths(lens), col[ent], val[ent], lens
+
+
+class HaloPlan:
+    """Who sends which owned entries to whom so that x_ext[n_own:] = x_global[halo_ids]."""
+
+    def __init__(self, halo_ids, offsets, comm):
+        self.comm = comm
+        self.halo_ids = halo_ids
+        self.n_halo = int(halo_ids.numel())
+        lo = int(offsets[comm.rank])
+        own = owners_of(halo_ids, offsets)
+        self.recv_counts = [int(v) for v in torch.bincount(own, minlength=comm.world).cpu()]
+        self.send_counts = comm.a2a_counts(self.recv_counts)
+        req = comm.a2a(halo_ids.to(torch.int64), self.recv_counts, self.send_counts)   # ids others need from me
+        self.send_idx = (req - lo).to(torch.int32).contiguous()
+        self.n_send = int(self.send_idx.numel())
+        self._buf = {}
+
+    def exchange(self, x_ext, n_own):
+        """fill x_ext[n_own:] from the owners (x_ext[:n_own] must be final)"""
+        if self.comm.world == 1:
+            return          # (never skipped on world > 1: the all-to-all is a collective)
+        key = (x_ext.dtype, x_ext.device)
+        buf = self._buf.get(key)
+        if buf is None:
+            buf = self._buf[key] = torch.empty(max(self.n_send, 1), dtype=x_ext.dtype, device=x_ext.device)
+        send = buf[:self.n_send]
+        if x_ext.is_cuda and x_ext.dtype in (torch.float32, torch.float64):
+            check(lib.mlamg_gather(core.dt(x_ext), self.n_send, core.ptr(self.send_idx), core.ptr(x_ext), core.ptr(send),
+                                   core.stream()))
+        else:
+            torch.index_select(x_ext[:n_own], 0, self.send_idx.long(), out=send)
+        self.comm.a2a(send, self.send_counts, self.recv_counts, out=x_ext[n_own:n_own + self.n_halo])
+
+
+def fetch_rows(rowptr, col, val, offsets, needed_ids, comm):
+    """CSR rows `needed_ids` (sorted unique global row ids owned by other ranks), in that order."""
+    plan = HaloPlan(needed_ids, offsets, comm)
+    _, scol, sval, slens = select_rows(rowptr, col, val, plan.send_idx.long())
+    # rows per peer are contiguous in send order; entries per peer = sum of their lengths
+    lens_recv = comm.a2a(slens, plan.send_counts, plan.recv_counts)
+    def per_peer(lens, counts):
+        l = lens.cpu().numpy()
+        out, k = [], 0
+        for n in counts:
+            out.append(int(l[k:k + n].sum()))
+            k += n
+        return out
+    send_e = per_peer(slens, plan.send_counts)
+    recv_e = per_peer(lens_recv, plan.recv_counts)
+    rcol = comm.a2a(scol, send_e, recv_e)
+    rval = comm.a2a(sval, send_e, recv_e)
+    return rowptr_from_lengths(lens_recv), rcol, rval
+
+
+def dist_transpose(rowptr, col, val, row_offsets, col_offsets, comm):
+    """Row-partitioned M (global column ids) -> row-partitioned M^T (rows = my block of the column
+    partition, global column ids = row ids of M), sorted rows."""
+    rank = comm.rank
+    n_own = rowptr.numel() - 1
+    lo_r = int(row_offsets[rank])
+    lo_c, hi_c = int(col_offsets[rank]), int(col_offsets[rank + 1])
+    n_rows_global = int(row_offsets[-1])
+    rows = torch.repeat_interleave(torch.arange(n_own, device=col.device, dtype=torch.int64) + lo_r, row_lengths(rowptr))
+    c = col.to(torch.int64)
+    dest = owners_of(c, col_offsets)
+    order = torch.argsort(dest, stable=True)
+    counts = [int(v) for v in torch.bincount(dest, minlength=comm.world).cpu()]
+    rcounts = comm.a2a_counts(counts)
+    r_rows = comm.a2a(rows[order], counts, rcounts)
+    r_cols = comm.a2a(c[order], counts, rcounts)
+    r_vals = comm.a2a(val[order], counts, rcounts)
+    j = r_cols - lo_c
+    key = j * n_rows_global + r_rows
+    perm = torch.argsort(key, stable=True)
+    lens = torch.bincount(j, minlength=hi_c - lo_c)
+    return rowptr_from_lengths(lens), r_rows[perm].to(torch.int32), r_vals[perm]
+
+
+def diag_block(rowptr, col, val, n_own, lo):
+    """entries whose column is owned, as a local CSR (the graph each rank aggregates on)"""
+    c = col.to(torch.int64)
+    own = (c >= lo) & (c < lo + n_own)
+    rows = torch.repeat_interleave(torch.arange(n_own, device=col.device), row_lengths(rowptr))
+    lens = torch.bincount(rows[own], minlength=n_own)
+    return rowptr_from_lengths(lens), (c[own] - lo).to(torch.int32), val[own]
+
+
+def gather_csr(rowptr, col, val, comm):
+    """all ranks receive the whole matrix (rows in rank order, global column ids)"""
+    lens = comm.all_gather_cat(row_lengths(rowptr))
+    return rowptr_from_lengths(lens), comm.all_gather_cat(col), comm.all_gather_cat(val)
+
+
+# =====================================================================================================
+# distributed level + hierarchy (GPU)
+# =====================================================================================================
+class DistOperator:
+    """Local rows of a row-partitioned operator, columns in ext numbering, with its halo plan."""
+
+    def __init__(self, rowptr, col_global, val, n_cols_own, col_lo, col_offsets, comm):
+        col_loc, halo = localize(col_global, n_cols_own, col_lo)
+        self.plan = HaloPlan(halo, col_offsets, comm)
+        self.n_rows = rowptr.numel() - 1
+        self.n_cols_own = n_cols_own
+        self.n_ext = n_cols_own + self.plan.n_halo
+        self.csr = core.DeviceCSR(rowptr.contiguous(), col_loc.contiguous(), val.contiguous(), (self.n_rows, self.n_ext))
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=col_loc.device), row_lengths(rowptr))
+        brows = torch.unique(rows[col_loc.long() >= n_cols_own])
+        mask = torch.ones(self.n_rows, dtype=torch.bool, device=col_loc.device)
+        mask[brows] = False
+        self.interior = torch.nonzero(mask).flatten().to(torch.int32).contiguous()
+        self.boundary = brows.to(torch.int32).contiguous()
+
+    def rowop(self, op, x_ext, y, b=None, dw=None, rows=None):
+        A = self.csr
+        n = A.shape[0] if rows is None else rows.numel()
+        if n == 0:
+            return
+        nnz_hint = A.nnz if rows is None else max(1, int(A.nnz * n / max(A.shape[0], 1)))
+        check(lib.mlamg_rowop_csr(core.dt(A.val), op, n, nnz_hint, core.ptr(A.rowptr), core.ptr(A.col), core.ptr(A.val),
+                                  core.ptr(x_ext), core.ptr(b), core.ptr(dw), core.ptr(y),
+                                  core.ptr(rows) if rows is not None else None, None, core.stream()))
+
+    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None):
+        """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange"""
+        plan = self.plan
+        if plan.comm.world == 1:
+            self.rowop(op, x_ext, y, b, dw)
+            return
+        if not overlap or comm_stream is None or self.interior.numel() == 0:
+            plan.exchange(x_ext, self.n_cols_own)
+            self.rowop(op, x_ext, y, b, dw)
+            return
+        main = torch.cuda.current_stream()
+        comm_stream.wait_stream(main)
+        with torch.cuda.stream(comm_stream):
+            plan.exchange(x_ext, self.n_cols_own)
+        self.rowop(op, x_ext, y, b, dw, rows=self.interior)
+        main.wait_stream(comm_stream)
+        self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
+
+
+class DistLevel:
+    pass
+
+
+class DistHierarchy:
+    """Distributed levels followed by a replicated single-GPU hierarchy."""
+
+    def __init__(self, rowptr, col_global, val, comm=None, *, ratio=0.1, distance="unit", maxiter=10, rand=0,
+                 lam_max=None, max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
+                 jacobi_weight=2.0 / 3.0, overlap=True):
+        core.require_cuda()
+        self.comm = comm or Comm()
+        comm = self.comm
+        self.dtype = val.dtype
+        self.overlap = overlap
+        self.comm_stream = torch.cuda.Stream() if comm.world > 1 else None
+        self.levels = []
+        self.offsets = []
+        lvl = 0
+        cur = (rowptr, col_global, val)
+        offs = partition_offsets(rowptr.numel() - 1, comm)
+        while True:
+            n_glob = int(offs[-1])
+            if n_glob <= replicate_below or lvl >= max_levels - 1:
+                break
+            L, nxt, coffs = self._build_level(cur, offs, lvl, ratio, distance, maxiter, rand, lam_max, smoother,
+                                              jacobi_weight)
+            self.levels.append(L)
+            self.offsets.append(offs)
+            cur, offs = nxt, coffs
+            lvl += 1
+        self.offsets.append(offs)
+        # replicated tail
+        g_rowptr, g_col, g_val = gather_csr(*cur, comm)
+        n_glob = int(offs[-1])
+        Ag = core.DeviceCSR(g_rowptr, g_col.to(torch.int32), g_val, (n_glob, n_glob))
+        lam_tail = lam_max
+        if isinstance(lam_max, (list, tuple)):
+            rest = list(lam_max[lvl:])
+            lam_tail = (lambda A, _r=rest, _k=[0]: (_r[_k[0]] if _k[0] < len(_r) and _r[_k[0]] is not None
+                                                     else core.lambda_max(A), _k.__setitem__(0, _k[0] + 1))[0])
+        self.tail = hmod.build_hierarchy(Ag, aggregates="lloyd", ratio=ratio, distance=distance, maxiter=maxiter, rand=rand,
+                                         lam_max=lam_tail, max_levels=max(1, max_levels - lvl), max_coarse=max_coarse,
+                                         smoother=smoother, jacobi_weight=jacobi_weight)
+        self.tail_offsets = offs
+        self._alloc()
+
+    # ---------------------------------------------------------------------------------------------
+    def _build_level(self, cur, offs, lvl, ratio, distance, maxiter, rand, lam_max, smoother, jacobi_weight):
+        comm = self.comm
+        rank = comm.rank
+        rowptr, colg, val = cur
+        n_own = rowptr.numel() - 1
+        lo = int(offs[rank])
+        L = DistLevel()
+        L.n = n_own
+        # 1. aggregates on the diagonal block
+        b_rp, b_col, b_val = diag_block(rowptr, colg, val, n_own, lo)
+        G = core.DeviceCSR(b_rp, b_col, b_val, (n_own, n_own))
+        labels, nc_local, roots, seeds = hmod.lloyd_labels(G, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand)
+        coffs = partition_offsets(nc_local, comm)
+        clo = int(coffs[rank])
+        nc_glob = int(coffs[-1])
+        L.labels = labels
+        # 2. A in ext numbering, halo labels
+        L.A = DistOperator(rowptr, colg, val, n_own, lo, offs, comm)
+        lab_ext = torch.full((L.A.n_ext,), -1, dtype=torch.int32, device=val.device)
+        lab_ext[:n_own] = torch.where(labels >= 0, labels + clo, labels)
+        L.A.plan.exchange(lab_ext, n_own)
+        Agg_ext = core.agg_from_labels(lab_ext, nc_glob, val.dtype)
+        # 3. P = (I - w D^-1 A) Agg   (rows: owned fine, columns: GLOBAL coarse ids)
+        if lam_max is None:
+            lam = self._lambda_max(L)
+        elif np.isscalar(lam_max):
+            lam = float(lam_max)
+        else:
+            lam = lam_max[lvl] if lvl < len(lam_max) else None
+            lam = self._lambda_max(L) if lam is None else float(lam)
+        L.omega_sa = (4.0 / 3.0) / lam
+        Pg = core.drop_zeros(core.spgemm(core.sa_smoother(L.A.csr, L.omega_sa), Agg_ext))
+        # 4. Galerkin product in scipy's evaluation order: X^T = A^T P ; A_H^T = P^T X^T ; transpose
+        t_rp, t_col, t_val = dist_transpose(rowptr, colg, val, offs, offs, comm)
+        At = DistOperator(t_rp, t_col, t_val, n_own, lo, offs, comm)
+        f_rp, f_col, f_val = fetch_rows(Pg.rowptr, Pg.col, Pg.val, offs, At.plan.halo_ids, comm)
+        e_rp, e_col, e_val = csr_vstack([(Pg.rowptr, Pg.col, Pg.val), (f_rp, f_col, f_val)])
+        Xt = core.spgemm(At.csr, core.DeviceCSR(e_rp, e_col, e_val, (At.n_ext, nc_glob)))
+        r_rp, r_col, r_val = dist_transpose(Pg.rowptr, Pg.col, Pg.val, offs, coffs, comm)
+        L.R = DistOperator(r_rp, r_col, r_val, n_own, lo, offs, comm)
+        f_rp, f_col, f_val = fetch_rows(Xt.rowptr, Xt.col, Xt.val, offs, L.R.plan.halo_ids, comm)
+        e_rp, e_col, e_val = csr_vstack([(Xt.rowptr, Xt.col, Xt.val), (f_rp, f_col, f_val)])
+        AHt = core.spgemm(L.R.csr, core.DeviceCSR(e_rp, e_col, e_val, (L.R.n_ext, nc_glob)))
+        h_rp, h_col, h_val = dist_transpose(AHt.rowptr, AHt.col, AHt.val, coffs, coffs, comm)
+        AH = core.drop_zeros(core.DeviceCSR(h_rp, h_col, h_val, (nc_local, nc_glob)))
+        # 5. apply structures
+        L.P = DistOperator(Pg.rowptr, Pg.col, Pg.val, nc_local, clo, coffs, comm)
+        L.P_global = Pg
+        L.dw = core.smoother_diag(L.A.csr, smoother, jacobi_weight)
+        L.nc = nc_local
+        return L, (AH.rowptr, AH.col, AH.val), coffs
+
+    def _lambda_max(self, L, iters=30):
+        """power iteration on D^-1 A with the distributed SpMV (replaces ARPACK, multigrid.py:105)"""
+        n = L.n
+        dinv = core.smoother_diag(L.A.csr, "jacobi", 1.0)
+        g = torch.Generator(device="cpu").manual_seed(1234 + self.comm.rank)
+        x = torch.zeros(L.A.n_ext, dtype=self.dtype, device="cuda")
+        x[:n] = torch.rand(n, generator=g, dtype=torch.float64).to(device="cuda", dtype=self.dtype) + 0.5
+        y = torch.empty(n, dtype=self.dtype, device="cuda")
+        lam = 0.0
+        for _ in range(iters):
+            nrm = np.sqrt(self.comm.allreduce_sum(core.dot(x[:n], x[:n])))
+            x[:n] /= nrm
+            L.A.apply(0, x, y, overlap=False)
+            y *= dinv
+            lam = self.comm.allreduce_sum(core.dot(x[:n], y))
+            x[:n] = y
+        return abs(lam)
+
+    # ---------------------------------------------------------------------------------------------
+    def _alloc(self):
+        dev, dt_ = "cuda", self.dtype
+        for L in self.levels:
+            L.x = [torch.zeros(L.A.n_ext, dtype=dt_, device=dev) for _ in range(2)]
+            L.b = torch.zeros(L.n, dtype=dt_, device=dev)
+            L.r = torch.zeros(L.R.n_ext, dtype=dt_, device=dev)
+            L.e = torch.zeros(L.P.n_ext, dtype=dt_, device=dev)
+        n_tail = int(self.tail_offsets[-1])
+        self.tail_b = torch.zeros(n_tail, dtype=dt_, device=dev)
+        self.tail_x = torch.zeros(n_tail, dtype=dt_, device=dev)
+        self._tail_sizes = [int(self.tail_offsets[i + 1] - self.tail_offsets[i]) for i in range(self.comm.world)]
+        # equal-size all-gather of the restricted residual: padded per-rank slots + one index map back
+        self._tail_pad = max(max(self._tail_sizes), 1)
+        self._tail_in = torch.zeros(self._tail_pad, dtype=dt_, device=dev)
+        self._tail_out = torch.zeros(self._tail_pad * self.comm.world, dtype=dt_, device=dev)
+        self._tail_map = torch.cat([torch.arange(s, device=dev) + r * self._tail_pad
+                                    for r, s in enumerate(self._tail_sizes)]).to(torch.int32).contiguous()
+        self._graph = None
+
+    @property
+    def n_local(self):
+        return self.levels[0].n if self.levels else int(self.tail_offsets[-1])
+
+    def vcycle(self, b, x_out, nu1=1, nu2=1):
+        """x_out = V(nu1,nu2)(b) from a zero guess (preconditioner apply).  b, x_out: local slices."""
+        comm = self.comm
+        cs = self.comm_stream if self.overlap else None
+        rhs = b
+        cur = []
+        for l, L in enumerate(self.levels):
+            xa, xb = L.x
+            n = L.n
+            c = xa
+            if nu1 > 0:
+                core.jacobi_zero(L.dw, rhs, c[:n])
+            else:
+                c[:n].zero_()
+            for _ in range(max(nu1 - 1, 0)):
+                o = xb if c is xa else xa
+                L.A.apply(3, c, o, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs)
+                c = o
+            L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs)       # r[:n] = b - A x
+            nxt_b = self.levels[l + 1].b if l + 1 < len(self.levels) else None
+            if nxt_b is None:
+                nxt_b = self._tail_local_b()
+            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs)          # b_c = R r
+            cur.append(c)
+            rhs = nxt_b
+        # replicated tail: all-gather the restricted residual, every rank solves, keep my slice
+        xc = self._tail_solve(rhs, nu1, nu2)
+        for l in range(len(self.levels) - 1, -1, -1):
+            L = self.levels[l]
+            xa, xb = L.x
+            n = L.n
+            c = cur[l]
+            L.e[:L.nc].copy_(xc)
+            rhs_l = b if l == 0 else self.levels[l].b
+            L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs)              # x += P e
+            for _ in range(nu2):
+                o = xb if c is xa else xa
+                L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs)
+                c = o
+            xc = c[:n]
+        x_out.copy_(xc)
+        return x_out
+
+    def _tail_local_b(self):
+        lo = int(self.tail_offsets[self.comm.rank])
+        hi = int(self.tail_offsets[self.comm.rank + 1])
+        return self.tail_b[lo:hi]
+
+    def _tail_solve(self, b_local, nu1, nu2):
+        comm = self.comm
+        lo = int(self.tail_offsets[comm.rank])
+        hi = int(self.tail_offsets[comm.rank + 1])
+        if comm.world > 1:
+            self._tail_in[:hi - lo].copy_(b_local)
+            dist.all_gather_into_tensor(self._tail_out, self._tail_in, group=comm.group)
+            check(lib.mlamg_gather(core.dt(self.tail_b), n_tail_all(self), core.ptr(self._tail_map), core.ptr(self._tail_out),
+                                   core.ptr(self.tail_b), core.stream()))
+        elif b_local.data_ptr() != self.tail_b.data_ptr():
+            self.tail_b.copy_(b_local)
+        check(lib.mlamg_vcycle(self.tail._h, core.ptr(self.tail_b), core.ptr(self.tail_x), nu1, nu2, 1, core.stream()))
+        return self.tail_x[lo:hi]
+
+    # -- solvers --------------------------------------------------------------------------------------
+    def matvec(self, x_local, out):
+        L = self.levels[0]
+        L.x[0][:L.n].copy_(x_local)
+        L.A.apply(0, L.x[0], out, overlap=self.overlap, comm_stream=self.comm_stream if self.overlap else None)
+        return out
+
+    def gdot(self, x, y):
+        return self.comm.allreduce_sum(core.dot(x, y))
+
+    def pcg(self, b, x0=None, tol=1e-8, maxiter=200, nu1=1, nu2=1):
+        """V-cycle preconditioned CG on the local slices; returns (x, residual history, iterations)."""
+        n = b.numel()
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        r = torch.empty_like(b)
+        ap = torch.empty_like(b)
+        z = torch.empty_like(b)
+        self.matvec(x, ap)
+        r.copy_(b)
+        core.axpby(-1.0, ap, 1.0, r)
+        res = [np.sqrt(self.gdot(r, r))]
+        nb = np.sqrt(self.gdot(b, b))
+        stop = tol * (nb if nb != 0 else 1.0)
+        if res[0] <= stop:
+            return x, np.array(res), 0
+        self.vcycle(r, z, nu1, nu2)
+        p = z.clone()
+        rz = self.gdot(r, z)
+        it = 0
+        for it in range(1, maxiter + 1):
+            self.matvec(p, ap)
+            alpha = rz / self.gdot(p, ap)
+            core.axpby(alpha, p, 1.0, x)
+            core.axpby(-alpha, ap, 1.0, r)
+            res.append(np.sqrt(self.gdot(r, r)))
+            if res[-1] <= stop:
+                break
+            self.vcycle(r, z, nu1, nu2)
+            rz_new = self.gdot(r, z)
+            core.axpby(1.0, z, rz_new / rz, p)
+            rz = rz_new
+        return x, np.array(res), it
+
+    def cycle_bytes(self, nu1=1, nu2=1):
+        """algorithmic bytes one rank moves per cycle on its distributed levels (+ the replicated tail)"""
+        v = 8 if self.dtype == torch.float64 else 4
+        tot = 0.0
+        for L in self.levels:
+            N, nnz, Nc, pn = L.n, L.A.csr.nnz, L.nc, L.P.csr.nnz
+            b_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
+            b_res = nnz * (v + 4) + 4 * (N + 1) + 3 * v * N
+            pre = (nu1 - 1) * b_jac + 3 * v * N if nu1 > 0 else 0
+            tot += pre + nu2 * b_jac + b_res + (pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc) + \
+                (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
+        return tot + self.tail.cycle_bytes(nu1, nu2, True)
+
+
+def n_tail_all(h):
+    return int(h.tail_offsets[-1])
+
+
+def poisson_slab(n, world, rank, dtype=torch.float64):
+    """rows of rank's z-slab of the global n x n x (n*world) Dirichlet 7-point grid, GLOBAL column ids"""
+    nzg = n * world
+    z0 = n * rank
+    N = n * n * n
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device="cuda")
+    col = torch.empty(7 * N, dtype=torch.int32, device="cuda")
+    val = torch.empty(7 * N, dtype=dtype, device="cuda")
+    nnz = ctypes.c_longlong(0)
+    check(lib.mlamg_poisson_csr_slab(core.dt(val), n, n, nzg, z0, n, core.ptr(rowptr), core.ptr(col), core.ptr(val),
+                                     ctypes.byref(nnz), core.stream()))
+    return rowptr, col[:nnz.value].clone(), val[:nnz.value].clone()

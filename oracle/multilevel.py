@@ -179,3 +179,62 @@ def poisson(shape, dtype=np.float64):
     A.sum_duplicates()
     A.sort_indices()
     return A
+
+
+# ------------------------------------------------------------------ row-partitioned variant
+def build_hierarchy_partitioned(A, offsets, *, ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
+                                max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
+                                jacobi_weight=2.0 / 3.0):
+    """CPU statement of the multi-GPU algorithm of ml-amg_b200/mlamg/distributed.py (the reference has no
+    distributed solve — PARITY UNPINNED by construction; this defines it).  While the level has more than
+    `replicate_below` rows: each block [offsets[r], offsets[r+1]) is aggregated on its own diagonal block
+    (reference seeding rule per block), coarse dofs are numbered block by block, and P / A_H are the plain
+    global expressions of ns/lib/multigrid.py:102-108,165.  Below the threshold the ordinary single-domain
+    hierarchy continues.  Returns (levels, list of per-level offsets of the partitioned levels)."""
+    A = sp.csr_matrix(A)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    levels, all_offsets = [], []
+    lvl = 0
+    lam_list = list(lam_max) if isinstance(lam_max, (list, tuple)) else None
+    while A.shape[0] > replicate_below and lvl < max_levels - 1:
+        n = A.shape[0]
+        labels = np.full(n, -1, dtype=np.int64)
+        coffs = [0]
+        for r in range(len(offsets) - 1):
+            lo, hi = int(offsets[r]), int(offsets[r + 1])
+            blk = sp.csr_matrix(A[lo:hi, lo:hi])
+            blk.sort_indices()
+            Agg_r, _, _ = rp.lloyd_aggregation(blk, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand)
+            lab = np.full(hi - lo, -1, dtype=np.int64)
+            coo = Agg_r.tocoo()
+            lab[coo.row] = coo.col
+            labels[lo:hi] = np.where(lab >= 0, lab + coffs[-1], -1)
+            coffs.append(coffs[-1] + Agg_r.shape[1])
+        L = Level()
+        L.A = A
+        L.dw = smoother_diag(A, smoother, jacobi_weight).astype(A.dtype)
+        L.labels = labels
+        Agg = labels_to_agg(labels, coffs[-1])
+        if lam_list is not None:
+            lam = lam_list[lvl] if lvl < len(lam_list) and lam_list[lvl] is not None else rp.lambda_max_dinv_a(A)
+        elif lam_max is None:
+            lam = rp.lambda_max_dinv_a(A)
+        else:
+            lam = lam_max
+        L.omega_sa = (4.0 / 3.0) / lam
+        L.P = rp.canonical_csr(sp.csr_matrix(rp.smoothed_aggregation_jacobi(A, Agg, omega=L.omega_sa)))
+        L.R = sp.csr_matrix(L.P.T)
+        levels.append(L)
+        all_offsets.append(offsets)
+        A = rp.canonical_csr(rp.galerkin(L.A, L.P))
+        offsets = np.asarray(coffs, dtype=np.int64)
+        lvl += 1
+    all_offsets.append(offsets)
+    tail_lam = lam_list[lvl:] if lam_list is not None else lam_max
+    if lam_list is not None:
+        it = iter(tail_lam)
+        tail_lam = lambda M, _it=it: next(_it)       # noqa: E731  (one value per tail level, in order)
+    tail = build_hierarchy(A, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand, lam_max=tail_lam,
+                           max_levels=max(1, max_levels - lvl), max_coarse=max_coarse, smoother=smoother,
+                           jacobi_weight=jacobi_weight)
+    return levels + tail, all_offsets

@@ -1,0 +1,135 @@
+"""CPU, world_size 2, gloo: the host-side plumbing of the row-partitioned multi-GPU levels
+(partition, halo plan + exchange, row fetch, distributed transpose, gather) against scipy, and the
+partitioned oracle itself.  No kernel runs here (there is no GPU in this container)."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT, random_csr
+from oracle import multilevel as oml
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _global_matrix(n=97, seed=5):
+    A = random_csr(n, n, 0.08, seed, empty_rows=True) + sp.diags(np.arange(1.0, n + 1))
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    return A
+
+
+def _worker(rank, world, port, q):
+    try:
+        for p in (ROOT, os.path.join(ROOT, "ml-amg_b200")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from mlamg import distributed as md
+        comm = md.Comm()
+        A = _global_matrix()
+        n = A.shape[0]
+        cut = [0, 41, n]
+        lo, hi = cut[rank], cut[rank + 1]
+        Al = sp.csr_matrix(A[lo:hi])
+        rowptr = torch.from_numpy(Al.indptr.astype(np.int32))
+        col = torch.from_numpy(Al.indices.astype(np.int32))
+        val = torch.from_numpy(Al.data.copy())
+        offs = md.partition_offsets(hi - lo, comm)
+        assert list(offs) == cut
+        # localize + halo exchange of a vector
+        col_loc, halo = md.localize(col, hi - lo, lo)
+        plan = md.HaloPlan(halo, offs, comm)
+        xg = np.random.RandomState(0).randn(n)
+        x_ext = torch.zeros(hi - lo + plan.n_halo, dtype=torch.float64)
+        x_ext[:hi - lo] = torch.from_numpy(xg[lo:hi])
+        plan.exchange(x_ext, hi - lo)
+        assert np.array_equal(x_ext[hi - lo:].numpy(), xg[halo.numpy()])
+        y = sp.csr_matrix((Al.data, col_loc.numpy(), Al.indptr), shape=(hi - lo, x_ext.numel())) @ x_ext.numpy()
+        assert np.allclose(y, (A @ xg)[lo:hi], rtol=1e-14)
+        lab = torch.zeros(x_ext.numel(), dtype=torch.int32)
+        lab[:hi - lo] = torch.arange(lo, hi, dtype=torch.int32)
+        plan.exchange(lab, hi - lo)
+        assert np.array_equal(lab[hi - lo:].numpy(), halo.numpy())
+        # distributed transpose
+        t_rp, t_col, t_val = md.dist_transpose(rowptr, col, val, offs, offs, comm)
+        At = sp.csr_matrix(A.T)
+        At.sort_indices()
+        ref = sp.csr_matrix(At[lo:hi])
+        assert np.array_equal(t_rp.numpy(), ref.indptr) and np.array_equal(t_col.numpy(), ref.indices)
+        assert np.array_equal(t_val.numpy(), ref.data)
+        # rectangular transpose (row partition != column partition)
+        B = random_csr(n, 31, 0.2, 9)
+        ccut = [0, 12, 31]
+        Bl = sp.csr_matrix(B[lo:hi])
+        b_rp, b_col, b_val = md.dist_transpose(torch.from_numpy(Bl.indptr.astype(np.int32)),
+                                               torch.from_numpy(Bl.indices.astype(np.int32)), torch.from_numpy(Bl.data.copy()),
+                                               offs, np.array(ccut), comm)
+        Bt = sp.csr_matrix(B.T)
+        Bt.sort_indices()
+        refb = sp.csr_matrix(Bt[ccut[rank]:ccut[rank + 1]])
+        assert np.array_equal(b_rp.numpy(), refb.indptr) and np.array_equal(b_col.numpy(), refb.indices)
+        assert np.array_equal(b_val.numpy(), refb.data)
+        # fetch rows owned by the other rank
+        f_rp, f_col, f_val = md.fetch_rows(rowptr, col, val, offs, halo, comm)
+        reff = sp.csr_matrix(A[halo.numpy()])
+        assert np.array_equal(f_rp.numpy(), reff.indptr) and np.array_equal(f_col.numpy(), reff.indices)
+        assert np.array_equal(f_val.numpy(), reff.data)
+        # diagonal block and gather
+        d_rp, d_col, d_val = md.diag_block(rowptr, col, val, hi - lo, lo)
+        refd = sp.csr_matrix(A[lo:hi, lo:hi])
+        refd.sort_indices()
+        assert np.array_equal(d_rp.numpy(), refd.indptr) and np.array_equal(d_col.numpy(), refd.indices)
+        g_rp, g_col, g_val = md.gather_csr(rowptr, col, val, comm)
+        assert np.array_equal(g_rp.numpy(), A.indptr) and np.array_equal(g_col.numpy(), A.indices) and np.array_equal(g_val.numpy(), A.data)
+        assert abs(comm.allreduce_sum(rank + 1.0) - 3.0) < 1e-15
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+def test_distributed_plumbing_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def test_partitioned_oracle_reduces_to_single_domain_and_converges():
+    A = oml.poisson((24, 20))
+    n = A.shape[0]
+    lam = [2.0, 1.9, 1.8, 1.7]
+    one, offs = oml.build_hierarchy_partitioned(A, [0, n], ratio=0.1, lam_max=lam, max_coarse=20, replicate_below=100)
+    ref = oml.build_hierarchy(A, ratio=0.1, lam_max=lam, max_coarse=20)
+    assert len(one) == len(ref)
+    for a, b in zip(one, ref):
+        assert (a.A != b.A).nnz == 0
+    two, offs2 = oml.build_hierarchy_partitioned(A, [0, 240, n], ratio=0.1, lam_max=lam, max_coarse=20, replicate_below=100)
+    assert len(offs2[0]) == 3 and offs2[1][-1] == two[1].A.shape[0]
+    # aggregates never straddle the partition
+    lab = two[0].labels
+    assert lab[:240].max() < offs2[1][1] <= lab[240:].min()
+    b = np.random.RandomState(0).randn(n)
+    x, res, it = oml.pcg(two, b, tol=1e-8)
+    assert res[-1] <= 1e-8 * np.linalg.norm(b)

@@ -1,0 +1,30 @@
+"""GPU: the row-partitioned hierarchy.  world_size 1 runs in-process; world_size 2 is launched with
+torchrun when two GPUs are visible (skipped otherwise) — the same script the round's 2-GPU gpurun used."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(nproc, n):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "dist_check.py"), str(n)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+def test_dist_hierarchy_world1_matches_partitioned_oracle():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dist_check.py"), "14"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dist_hierarchy_world2_matches_partitioned_oracle():
+    out = _run(2, 12)
+    assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]
