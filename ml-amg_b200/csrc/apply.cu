@@ -44,11 +44,13 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
     T sum = (T)0;
-    // row_order: optional processing order (a permutation of the rows).  Used by the restriction, whose
-    // rows (aggregates) are numbered randomly by the reference's seeding: visiting them in spatial order
-    // lets neighbouring aggregates share the fine-vector sectors they gather through L2.
-    if (row < n && row_order) row = row_order[row];
-    if (row < n) {
+    // row_order: optional list of the n rows to process (a permutation of all rows, or a subset).  Used by
+    // the restriction, whose rows (aggregates) are numbered randomly by the reference's seeding — visiting
+    // them in spatial order lets neighbouring aggregates share the fine-vector sectors they gather through
+    // L2 — and by the multi-GPU levels (interior rows while the halo is in flight, then boundary rows).
+    const bool valid = row < n;
+    if (valid && row_order) row = row_order[row];
+    if (valid) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
         // batches of 4 predicated entries per lane: all col/val loads, then all x gathers, then the FMAs
@@ -74,7 +76,7 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     }
     if (LANES > 1) sum = group_sum<LANES>(sum);
     double rr = 0.0;
-    if (row < n && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
+    if (valid && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
     if (NORM) {
         __shared__ double sm[32];
         rr = block_sum(rr, sm);

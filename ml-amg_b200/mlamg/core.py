@@ -224,6 +224,14 @@ def spmv_perm(A, x, row_order, out=None):
     return out
 
 
+def rowop(A, op, x, y, b=None, dw=None, rows=None):
+    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax)) over all rows or the int32 list `rows`"""
+    n = A.shape[0] if rows is None else rows.numel()
+    check(lib.mlamg_rowop_csr(dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))), ptr(A.rowptr), ptr(A.col),
+                              ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(rows), None, stream()))
+    return y
+
+
 def spmv_add(A, x, y):
     """y += A x (prolongation-and-correct)."""
     n, m = A.shape

@@ -271,3 +271,26 @@ def test_spmv_row_order_is_result_invariant():
     y0 = mlamg.spmv(Ad, dev(x, np.float64))
     y1 = mlamg.spmv_perm(Ad, dev(x, np.float64), order)
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("op", [0, 1, 2, 3])
+def test_rowop_on_row_subset(op):
+    """interior / boundary splits of the multi-GPU levels: only the listed rows are touched"""
+    from mlamg import core
+    import mlamg
+    A = oml.poisson((12, 11, 10))
+    n = A.shape[0]
+    rs = np.random.RandomState(op)
+    x, b, dw, y0 = rs.randn(n), rs.randn(n), rs.rand(n), rs.randn(n)
+    rows = np.sort(rs.permutation(n)[: n // 3]).astype(np.int32)      # includes rows > len(rows)
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    yd = dev(y0, np.float64)
+    core.rowop(Ad, op, dev(x, np.float64), yd, b=dev(b, np.float64), dw=dev(dw, np.float64), rows=torch.from_numpy(rows).cuda())
+    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x)}[op]
+    ref = y0.copy()
+    ref[rows] = full[rows]
+    got = yd.cpu().numpy()
+    mask = np.ones(n, bool)
+    mask[rows] = False
+    assert np.array_equal(got[mask], y0[mask]), "rows outside the list were modified"
+    assert np.abs(got[rows] - ref[rows]).max() <= 1e-13 * np.abs(full).max()
