@@ -158,7 +158,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
     const int lanes = pick_lanes(n, nnz_hint);
     const unsigned blocks = cdiv((long long)n * lanes, ROW_THREADS);
     double *partial = nullptr;
-    Scratch part(NORM ? (size_t)blocks * sizeof(double) : 16, s);
+    Scratch part(NORM ? (size_t)blocks * sizeof(double) : (size_t)-1, s);
     if (NORM) {
         MLAMG_SCRATCH_OK(part);
         partial = part.as<double>();
@@ -188,7 +188,7 @@ static int launch_sell(int n, const int *slice_ptr, const int *col, const T *val
     }
     const unsigned blocks = cdiv(n, ROW_THREADS);
     double *partial = nullptr;
-    Scratch part(NORM ? (size_t)blocks * sizeof(double) : 16, s);
+    Scratch part(NORM ? (size_t)blocks * sizeof(double) : (size_t)-1, s);
     if (NORM) {
         MLAMG_SCRATCH_OK(part);
         partial = part.as<double>();

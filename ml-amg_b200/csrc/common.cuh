@@ -47,7 +47,10 @@ struct Scratch {
     void *p = nullptr;
     cudaStream_t s = nullptr;
     cudaError_t err = cudaSuccess;
+    // bytes == SIZE_MAX: no allocation at all (lets a call site skip the alloc/free pair, which would
+    // otherwise become two extra nodes per kernel inside a captured CUDA graph)
     Scratch(size_t bytes, cudaStream_t stream) : s(stream) {
+        if (bytes == (size_t)-1) return;
         err = cudaMallocAsync(&p, bytes ? bytes : 16, s);
         if (err != cudaSuccess) p = nullptr;
     }

@@ -471,6 +471,20 @@ class DistHierarchy:
         x_out.copy_(xc)
         return x_out
 
+    def capture(self, b, x_out, nu1=1, nu2=1):
+        """Capture one cycle (kernels + NCCL exchanges + side-stream fork/joins) into a CUDA graph and return a
+        replay callable.  b / x_out are baked in (update them in place).  All ranks must call this together."""
+        self.vcycle(b, x_out, nu1, nu2)          # warm-up: every lazy buffer exists before capture
+        self.vcycle(b, x_out, nu1, nu2)
+        torch.cuda.synchronize()
+        self.comm.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.vcycle(b, x_out, nu1, nu2)
+        torch.cuda.synchronize()
+        self._graph = g
+        return g.replay
+
     def _tail_local_b(self):
         lo = int(self.tail_offsets[self.comm.rank])
         hi = int(self.tail_offsets[self.comm.rank + 1])
