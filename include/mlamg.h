@@ -80,12 +80,13 @@ int mlamg_sell_fill(int dtype, int n, const int *rowptr, const int *col, const v
 /* op: 0 y = A x | 1 y += A x | 2 y = b - A x (+ *norm2 = ||y||^2 if norm2 != NULL) | 3 y = x + dw.*(b - A x) */
 int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *scol, const void *sval,
                      const void *x, const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream);
-/* generic row-op over all rows (row_list == NULL) or the subset row_list[0..nrows):
+/* generic row-op over the row range [row_begin, row_begin + nrows) (row_list == NULL) or the listed rows
+ * row_list[0..nrows):
  * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax).  Used by the row-partitioned multi-GPU levels
  * to run interior rows while the halo exchange of x is in flight, then the boundary rows. */
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
-                    const void *x, const void *b, const void *dw, void *y, const int *row_list, double *norm2,
-                    mlamg_stream_t stream);
+                    const void *x, const void *b, const void *dw, void *y, const int *row_list, int row_begin,
+                    double *norm2, mlamg_stream_t stream);
 /* halo pack: dst[i] = src[idx[i]] */
 int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, mlamg_stream_t stream);
 /* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32), -1 = heuristic */

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
                  const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial,
-                 const int *__restrict__ row_order) {
+                 const int *__restrict__ row_order, int row0) {
     const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
     long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
@@ -49,7 +49,7 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     // them in spatial order lets neighbouring aggregates share the fine-vector sectors they gather through
     // L2 — and by the multi-GPU levels (interior rows while the halo is in flight, then boundary rows).
     const bool valid = row < n;
-    if (valid && row_order) row = row_order[row];
+    if (valid) row = row_order ? row_order[row] : row + row0;   // listed rows, or the range [row0, row0 + n)
     if (valid) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
@@ -150,7 +150,8 @@ static int pick_lanes(int n, long long nnz) {
 
 template <typename T, int OP, bool NORM>
 static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *x,
-                        const T *b, const T *dw, T *y, double *norm2, cudaStream_t s, const int *row_order = nullptr) {
+                        const T *b, const T *dw, T *y, double *norm2, cudaStream_t s, const int *row_order = nullptr,
+                        int row0 = 0) {
     if (n <= 0) {
         if (NORM && norm2) MLAMG_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double), s));
         return MLAMG_OK;
@@ -164,7 +165,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
         partial = part.as<double>();
     }
 #define LAUNCH(L)                                                                                       \
-    csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row_order)
+    csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row_order, row0)
     switch (lanes) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -465,14 +466,14 @@ int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, c
 // (row_list == NULL, nrows = n) or over the subset row_list[0..nrows) (interior / boundary splits of
 // the row-partitioned multi-GPU levels: interior rows run while the halo exchange is in flight).
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
-                    const void *x, const void *b, const void *dw, void *y, const int *row_list, double *norm2,
-                    mlamg_stream_t stream) {
+                    const void *x, const void *b, const void *dw, void *y, const int *row_list, int row_begin,
+                    double *norm2, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
     if (nrows < 0) return set_error(MLAMG_EINVAL, "rowop: nrows < 0");
     if (x == y) return set_error(MLAMG_EINVAL, "rowop: x aliases y");
 #define ROWOP_CASE(OPC, NRM) \
     MLAMG_DISPATCH(dtype, return (launch_rowop<T, OPC, NRM>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x, \
-                                                             (const T *)b, (const T *)dw, (T *)y, norm2, s, row_list)))
+                                                             (const T *)b, (const T *)dw, (T *)y, norm2, s, row_list, row_begin)))
     switch (op) {
         case OP_SPMV: ROWOP_CASE(OP_SPMV, false); break;
         case OP_SPMV_ADD: ROWOP_CASE(OP_SPMV_ADD, false); break;

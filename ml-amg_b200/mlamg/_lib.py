@@ -57,7 +57,7 @@ SIGNATURES = {
     "mlamg_poisson_nnz": (LL, [I, I, I]),
     "mlamg_poisson_csr": (I, [I, I, I, I, P, P, P, P]),
     "mlamg_poisson_csr_slab": (I, [I, I, I, I, I, I, P, P, P, P, P]),
-    "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
+    "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, I, P, P]),
     "mlamg_gather": (I, [I, I, P, P, P, P]),
     "mlamg_bellman_ford": (I, [I, I, P, P, P, I, P, P, P, P, P]),
     "mlamg_lloyd_cluster": (I, [I, I, P, P, P, I, P, I, P, P, P, P]),

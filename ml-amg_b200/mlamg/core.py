@@ -224,11 +224,20 @@ def spmv_perm(A, x, row_order, out=None):
     return out
 
 
-def rowop(A, op, x, y, b=None, dw=None, rows=None):
-    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax)) over all rows or the int32 list `rows`"""
-    n = A.shape[0] if rows is None else rows.numel()
+def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None):
+    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax)) over all rows, the int32 list `rows`,
+    or the contiguous range row_range=(begin, end)"""
+    begin = 0
+    if rows is not None:
+        n = rows.numel()
+    elif row_range is not None:
+        begin, n = int(row_range[0]), int(row_range[1] - row_range[0])
+    else:
+        n = A.shape[0]
+    if n <= 0:
+        return y
     check(lib.mlamg_rowop_csr(dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))), ptr(A.rowptr), ptr(A.col),
-                              ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(rows), None, stream()))
+                              ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(rows), begin, None, stream()))
     return y
 
 

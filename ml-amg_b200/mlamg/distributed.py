@@ -33,6 +33,9 @@ from ._lib import lib, check
 # =====================================================================================================
 # communicator helpers
 # =====================================================================================================
+OVERLAP_MIN_ROWS = 2_000_000
+
+
 class Comm:
     def __init__(self, group=None):
         self.group = group
@@ -256,16 +259,18 @@ class DistOperator:
         mask[brows] = False
         self.interior = torch.nonzero(mask).flatten().to(torch.int32).contiguous()
         self.boundary = brows.to(torch.int32).contiguous()
+        # contiguous row partitions of banded operators have a contiguous interior: [i0, i1) can then be run
+        # as a plain row RANGE (coalesced, no index list) and the boundary as the two ranges around it
+        self.interior_range = None
+        if self.interior.numel() > 0:
+            i0, i1 = int(self.interior[0]), int(self.interior[-1]) + 1
+            if i1 - i0 == self.interior.numel():
+                self.interior_range = (i0, i1)
+        # overlap only pays when the interior kernel is much longer than an exchange (~40 us)
+        self.overlap_ok = self.interior.numel() >= OVERLAP_MIN_ROWS
 
-    def rowop(self, op, x_ext, y, b=None, dw=None, rows=None):
-        A = self.csr
-        n = A.shape[0] if rows is None else rows.numel()
-        if n == 0:
-            return
-        nnz_hint = A.nnz if rows is None else max(1, int(A.nnz * n / max(A.shape[0], 1)))
-        check(lib.mlamg_rowop_csr(core.dt(A.val), op, n, nnz_hint, core.ptr(A.rowptr), core.ptr(A.col), core.ptr(A.val),
-                                  core.ptr(x_ext), core.ptr(b), core.ptr(dw), core.ptr(y),
-                                  core.ptr(rows) if rows is not None else None, None, core.stream()))
+    def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None):
+        core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)
 
     def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None):
         """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange"""
@@ -273,7 +278,7 @@ class DistOperator:
         if plan.comm.world == 1:
             self.rowop(op, x_ext, y, b, dw)
             return
-        if not overlap or comm_stream is None or self.interior.numel() == 0:
+        if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
             self.rowop(op, x_ext, y, b, dw)
             return
@@ -281,9 +286,16 @@ class DistOperator:
         comm_stream.wait_stream(main)
         with torch.cuda.stream(comm_stream):
             plan.exchange(x_ext, self.n_cols_own)
-        self.rowop(op, x_ext, y, b, dw, rows=self.interior)
-        main.wait_stream(comm_stream)
-        self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
+        if self.interior_range is not None:
+            i0, i1 = self.interior_range
+            self.rowop(op, x_ext, y, b, dw, row_range=(i0, i1))
+            main.wait_stream(comm_stream)
+            self.rowop(op, x_ext, y, b, dw, row_range=(0, i0))
+            self.rowop(op, x_ext, y, b, dw, row_range=(i1, self.n_rows))
+        else:
+            self.rowop(op, x_ext, y, b, dw, rows=self.interior)
+            main.wait_stream(comm_stream)
+            self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
 
 
 class DistLevel:
