@@ -33,7 +33,7 @@ from ._lib import lib, check
 # =====================================================================================================
 # communicator helpers
 # =====================================================================================================
-OVERLAP_MIN_ROWS = 2_000_000
+OVERLAP_MIN_NNZ = 20_000_000      # overlap the halo exchange only when the interior kernel is >> ~40 us
 
 
 class Comm:
@@ -267,7 +267,7 @@ class DistOperator:
             if i1 - i0 == self.interior.numel():
                 self.interior_range = (i0, i1)
         # overlap only pays when the interior kernel is much longer than an exchange (~40 us)
-        self.overlap_ok = self.interior.numel() >= OVERLAP_MIN_ROWS
+        self.overlap_ok = self.interior.numel() > 0 and self.csr.nnz >= OVERLAP_MIN_NNZ
 
     def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None):
         core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)

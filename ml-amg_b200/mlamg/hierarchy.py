@@ -87,6 +87,25 @@ def galerkin(A, P, R=None, drop=True, symmetric=False):
     return core.drop_zeros(AH) if drop else AH
 
 
+def _permuted(M, row_new2old, col_old2new):
+    """rows gathered by row_new2old (None = keep), column ids mapped by col_old2new (None = keep), rows re-sorted"""
+    if row_new2old is None and col_old2new is None:
+        return M
+    rowptr, col, val = M.rowptr, M.col, M.val
+    if row_new2old is not None:
+        lens = (rowptr[1:] - rowptr[:-1]).long()[row_new2old]
+        starts = rowptr.long()[row_new2old]
+        excl = torch.cumsum(lens, 0) - lens
+        ent = torch.repeat_interleave(starts - excl, lens) + torch.arange(int(lens.sum()), device=col.device)
+        new_rowptr = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=col.device)
+        new_rowptr[1:] = torch.cumsum(lens, 0)
+        rowptr, col, val = new_rowptr.to(torch.int32), col[ent], val[ent]
+    if col_old2new is not None:
+        col = col_old2new[col.long()].to(torch.int32)
+    out = DeviceCSR(rowptr.contiguous(), col.contiguous().clone(), val.contiguous().clone(), M.shape)
+    return core.sort_rows(out)
+
+
 class Level:
     __slots__ = ("A", "P", "R", "dw", "labels", "omega_sa", "seeds", "roots", "sell")
 
@@ -99,11 +118,18 @@ class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
     def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
-                 sell_max_padding=1.5, restrict_order=True):
-        """sell: 'never' (default) -> CSR kernels only: measured on B200 at 256^3 the thread-per-row CSR kernel
+                 sell_max_padding=1.5, restrict_order=True, renumber=True):
+        """levels: list[Level] in the REFERENCE numbering (what setup produced and what parity is checked on).
+
+        renumber (default on): the cycle runs on apply copies whose coarse levels are renumbered spatially
+        (coarse dof c -> rank of its first fine node, recursively).  The reference numbers aggregates by a random
+        seed permutation, so with its numbering every gather of a coarse vector (prolongation, level-1 operator)
+        hits a different 32-byte L2 sector: measured at 256^3 the prolongation was L2-transaction bound
+        (211 us for 0.88 GB).  Coarse vectors are internal to the cycle, so the renumbering is invisible outside;
+        results change only by the re-ordered floating-point sums (within the 1e-12 parity bar).
+        sell: 'never' (default) -> CSR kernels only: measured on B200 at 256^3 the thread-per-row CSR kernel
         with predicated 4-entry batches (0.322 ms/sweep) is as fast as SELL-32 (0.337 ms), so the second copy
-        of A is not worth its HBM; 'auto' -> levels whose SELL-32 padding stays below sell_max_padding get a
-        SELL copy of A for the smoother/residual kernels; 'always'."""
+        of A is not worth its HBM; 'auto' / 'always' build SELL-32 copies for the smoother/residual kernels."""
         core.require_cuda()
         self.levels = levels
         self.dtype = levels[0].A.dtype
@@ -112,28 +138,29 @@ class Hierarchy:
             if lev.dw is None:
                 lev.dw = core.smoother_diag(lev.A, smoother, jacobi_weight)
         self.coarse_inv = core.dense_inverse(levels[-1].A)
+        self.renumbered = bool(renumber) and len(levels) > 2
+        self._apply = self._renumbered_copies() if self.renumbered else [(l.A, l.P, l.R, l.dw) for l in levels]
         self._h = ctypes.c_void_p()
         check(lib.mlamg_hierarchy_create(core.dt(self.dtype), len(levels), ctypes.byref(self._h)))
-        for l, lev in enumerate(levels):
-            A = lev.A
+        for l, (A, P, R, dw) in enumerate(self._apply):
             check(lib.mlamg_hierarchy_set_operator(self._h, l, A.shape[0], A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val),
-                                                   ptr(lev.dw)))
+                                                   ptr(dw)))
         if sell != "never":
             for l, lev in enumerate(levels[:-1]):
-                sl = core.DeviceSELL(lev.A)
+                sl = core.DeviceSELL(self._apply[l][0])
                 if sell == "always" or sl.padding <= sell_max_padding:
                     lev.sell = sl
                     check(lib.mlamg_hierarchy_set_operator_sell(self._h, l, ptr(sl.slice_ptr), ptr(sl.col), ptr(sl.val)))
-        for l, lev in enumerate(levels[:-1]):
-            P, R = lev.P, lev.R
+        for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
             check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
                                                    ptr(R.rowptr), ptr(R.col), ptr(R.val)))
-        # Restriction rows (aggregates) carry the reference's random seed numbering; visit them in the order
-        # of their first fine node so neighbouring aggregates share the sectors of r they gather (L2 reuse).
+        # Without renumbering the restriction rows keep the reference's random seed numbering; then at least
+        # VISIT them in the order of their first fine node so neighbouring aggregates share sectors of r.
         self._r_order = []
         if restrict_order:
-            for l, lev in enumerate(levels[:-1]):
-                R = lev.R
+            for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
+                if self.renumbered and l + 1 < len(levels) - 1:
+                    continue                       # rows of a renumbered level are already in spatial order
                 first = R.col[R.rowptr[:-1].long().clamp(max=max(R.nnz - 1, 0))]
                 order = torch.argsort(first, stable=True).to(torch.int32).contiguous()
                 self._r_order.append(order)
@@ -142,6 +169,38 @@ class Hierarchy:
         check(lib.mlamg_hierarchy_finalize(self._h, stream()))
         if use_graph:
             self.use_graph(True)
+
+    def _renumbered_copies(self):
+        """(A, P, R, dw) per level with levels 1..L-2 renumbered spatially (the coarsest keeps its numbering,
+        so the dense inverse is untouched)."""
+        levels = self.levels
+        L = len(levels)
+        dev = levels[0].A.val.device
+        old2new = [None] * L                      # None = identity
+        new2old = [None] * L
+        for l in range(1, L - 1):
+            R = levels[l - 1].R                   # rows: level-l dofs, cols: level l-1 dofs (reference numbering)
+            cols = R.col.long()
+            if old2new[l - 1] is not None:
+                cols = old2new[l - 1][cols]
+            rows = torch.repeat_interleave(torch.arange(R.shape[0], device=dev), (R.rowptr[1:] - R.rowptr[:-1]).long())
+            key = torch.full((R.shape[0],), 2 ** 62, dtype=torch.int64, device=dev)
+            key.scatter_reduce_(0, rows, cols, reduce="amin")
+            order = torch.argsort(key, stable=True)            # new -> old
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(order.numel(), device=dev)
+            new2old[l], old2new[l] = order, inv
+        out = []
+        for l, lev in enumerate(levels):
+            A = _permuted(lev.A, new2old[l], old2new[l])
+            dw = lev.dw if (new2old[l] is None or lev.dw is None) else lev.dw[new2old[l]].contiguous()
+            if l < L - 1:
+                P = _permuted(lev.P, new2old[l], old2new[l + 1])
+                R = core.transpose(P) if (new2old[l] is not None or old2new[l + 1] is not None) else lev.R
+            else:
+                P = R = None
+            out.append((A, P, R, dw))
+        return out
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -28,7 +28,7 @@ def main():
     import mlamg
     from mlamg import distributed as md
     from oracle import multilevel as oml
-    md.OVERLAP_MIN_ROWS = 0          # exercise the interior/boundary overlap path even on tiny levels
+    md.OVERLAP_MIN_NNZ = 0          # exercise the interior/boundary overlap path even on tiny levels
     comm = md.Comm()
     rowptr, col, val = md.poisson_slab(n, world, rank)
     N_loc = n ** 3
