@@ -253,9 +253,15 @@ class DistOperator:
         self.n_cols_own = n_cols_own
         self.n_ext = n_cols_own + self.plan.n_halo
         self.csr = core.DeviceCSR(rowptr.contiguous(), col_loc.contiguous(), val.contiguous(), (self.n_rows, self.n_ext))
-        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=col_loc.device), row_lengths(rowptr))
-        brows = torch.unique(rows[col_loc.long() >= n_cols_own])
-        mask = torch.ones(self.n_rows, dtype=torch.bool, device=col_loc.device)
+        self._split_rows()
+
+    def _split_rows(self):
+        """interior rows (no halo column) / boundary rows, as lists and — when contiguous — as ranges"""
+        A = self.csr
+        dev = A.col.device
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), row_lengths(A.rowptr))
+        brows = torch.unique(rows[A.col.long() >= self.n_cols_own])
+        mask = torch.ones(self.n_rows, dtype=torch.bool, device=dev)
         mask[brows] = False
         self.interior = torch.nonzero(mask).flatten().to(torch.int32).contiguous()
         self.boundary = brows.to(torch.int32).contiguous()
@@ -267,7 +273,20 @@ class DistOperator:
             if i1 - i0 == self.interior.numel():
                 self.interior_range = (i0, i1)
         # overlap only pays when the interior kernel is much longer than an exchange (~40 us)
-        self.overlap_ok = self.interior.numel() > 0 and self.csr.nnz >= OVERLAP_MIN_NNZ
+        self.overlap_ok = self.interior.numel() > 0 and A.nnz >= OVERLAP_MIN_NNZ
+
+    def renumber(self, row_new2old=None, col_old2new=None):
+        """Block-local renumbering: rows gathered by row_new2old, OWNED columns mapped by col_old2new (halo slots
+        keep their place in the ext vector; the entries this rank SENDS are re-addressed instead)."""
+        if col_old2new is not None:
+            n_own = self.n_cols_own
+            cmap = torch.cat([col_old2new.to(torch.int64),
+                              torch.arange(n_own, self.n_ext, device=col_old2new.device, dtype=torch.int64)])
+            self.plan.send_idx = col_old2new[self.plan.send_idx.long()].to(torch.int32).contiguous()
+        else:
+            cmap = None
+        self.csr = hmod._permuted(self.csr, row_new2old, cmap)
+        self._split_rows()
 
     def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None):
         core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)
@@ -307,7 +326,7 @@ class DistHierarchy:
 
     def __init__(self, rowptr, col_global, val, comm=None, *, ratio=0.1, distance="unit", maxiter=10, rand=0,
                  lam_max=None, max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
-                 jacobi_weight=2.0 / 3.0, overlap=True):
+                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True):
         core.require_cuda()
         self.comm = comm or Comm()
         comm = self.comm
@@ -343,6 +362,8 @@ class DistHierarchy:
                                          lam_max=lam_tail, max_levels=max(1, max_levels - lvl), max_coarse=max_coarse,
                                          smoother=smoother, jacobi_weight=jacobi_weight)
         self.tail_offsets = offs
+        if renumber:
+            self._renumber()
         self._alloc()
 
     # ---------------------------------------------------------------------------------------------
@@ -397,6 +418,30 @@ class DistHierarchy:
         L.dw = core.smoother_diag(L.A.csr, smoother, jacobi_weight)
         L.nc = nc_local
         return L, (AH.rowptr, AH.col, AH.val), coffs
+
+    def _renumber(self):
+        """Distributed levels l >= 1 get a block-local spatial numbering (dof -> rank of its first owned fine
+        node), for the same reason as Hierarchy(renumber=True): the reference's seed numbering is random, which
+        makes every gather of a coarse vector a separate L2 sector.  Only the apply operators change."""
+        for l in range(1, len(self.levels)):
+            Lf, Lc = self.levels[l - 1], self.levels[l]
+            R = Lf.R.csr
+            dev = R.col.device
+            rows = torch.repeat_interleave(torch.arange(R.shape[0], device=dev), row_lengths(R.rowptr))
+            cols = R.col.long()
+            own = cols < Lf.R.n_cols_own
+            key = torch.full((R.shape[0],), 2 ** 62, dtype=torch.int64, device=dev)
+            key.scatter_reduce_(0, rows[own], cols[own], reduce="amin")
+            order = torch.argsort(key, stable=True)            # new -> old
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(order.numel(), device=dev)
+            Lf.P.renumber(None, inv)
+            Lf.R.renumber(order, None)
+            Lc.A.renumber(order, inv)
+            Lc.P.renumber(order, None)
+            Lc.R.renumber(None, inv)
+            Lc.dw = Lc.dw[order].contiguous()
+            Lc.perm_new2old = order
 
     def _lambda_max(self, L, iters=30):
         """power iteration on D^-1 A with the distributed SpMV (replaces ARPACK, multigrid.py:105)"""

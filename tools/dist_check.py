@@ -64,10 +64,13 @@ def main():
         L = H.levels[l]
         lo, hi = int(H.offsets[l][rank]), int(H.offsets[l][rank + 1])
         Al = L.A.csr.to_scipy()
-        ext = np.concatenate([np.arange(lo, hi), L.A.plan.halo_ids.cpu().numpy()])
+        order = getattr(L, "perm_new2old", None)            # block-local apply renumbering (new -> old), if any
+        order = order.cpu().numpy() if order is not None else np.arange(hi - lo)
+        ext = np.concatenate([lo + order, L.A.plan.halo_ids.cpu().numpy()])
         Ag = sp.csr_matrix((Al.data, ext[Al.indices], Al.indptr), shape=(hi - lo, ref[l].A.shape[1]))
         Ag.sort_indices()
-        Ar = sp.csr_matrix(ref[l].A[lo:hi])
+        Ar = sp.csr_matrix(sp.csr_matrix(ref[l].A[lo:hi])[order])
+        Ar.sort_indices()
         check(f"L{l} A bits", np.array_equal(Ag.indptr, Ar.indptr) and np.array_equal(Ag.indices, Ar.indices)
               and np.array_equal(Ag.data, Ar.data))
     nd = len(H.levels)
