@@ -33,7 +33,10 @@ from ._lib import lib, check
 # =====================================================================================================
 # communicator helpers
 # =====================================================================================================
-OVERLAP_MIN_NNZ = 20_000_000      # overlap the halo exchange only when the interior kernel is >> ~40 us
+import os as _os
+
+# overlap the halo exchange only when the interior kernel is long compared with an exchange (~40 us)
+OVERLAP_MIN_NNZ = int(_os.environ.get("MLAMG_OVERLAP_MIN_NNZ", 20_000_000))
 
 
 class Comm:
