@@ -251,13 +251,15 @@ def run_ours_distributed(args, rank, world, local):
     c0 = mlamg.launch_count(); cycle_eager(); torch.cuda.synchronize(); kernels_per_cycle = mlamg.launch_count() - c0
     x_eager = x.clone()
     cycle, launch_mode = cycle_eager, "eager launches"
-    if os.environ.get("MLAMG_DIST_GRAPH", "0") == "1":   # opt-in: measured 1.62 ms vs 1.67 ms eager at 2 GPUs, but a
-        # captured graph holding NCCL work made process-group teardown hang once — not worth the risk by default
-        try:                                   # whole cycle (kernels + NCCL halo exchanges) as one CUDA graph
+    # peer transport: the cycle is kernels only (device-side flags over NVLink), so the whole cycle is captured as one
+    # CUDA graph.  NCCL transport: capture is opt-in (a graph holding NCCL work made process-group teardown hang once).
+    want_graph = os.environ.get("MLAMG_DIST_GRAPH", "1" if H.halo == "peer" else "0") == "1"
+    if want_graph:
+        try:
             replay = H.capture(b, x, 1, 1)
             x.zero_(); replay(); torch.cuda.synchronize()
             same = bool(torch.equal(x, x_eager))
-            cycle, launch_mode = replay, f"CUDA graph incl. NCCL exchanges (bitwise equal to eager: {same})"
+            cycle, launch_mode = replay, f"CUDA graph of the whole cycle (bitwise equal to eager: {same})"
         except Exception as exc:               # noqa: BLE001
             launch_mode = f"eager launches (graph capture failed: {type(exc).__name__})"
 
@@ -325,7 +327,10 @@ def run_ours_distributed(args, rank, world, local):
                "config": {"workload": workload_name(n, world), "dof": N_loc * world, "dof_per_gpu": N_loc,
                           "distributed_levels": [int(o[-1]) for o in H.offsets[:-1]],
                           "replicated_levels": [l.A.shape[0] for l in H.tail.levels], "cycle": "V(1,1) zero-guess",
-                          "halo_entries_fine": L0.A.plan.n_halo, "overlap": "interior rows during NCCL halo exchange",
+                          "halo_entries_fine": L0.A.plan.n_halo,
+                          "halo_transport": ("peer stores into CUDA-IPC windows over NVLink + device flags, interior rows "
+                                             "between push and wait (no collective in the cycle)" if H.halo == "peer"
+                                             else "NCCL all-to-all on a side stream overlapped with the interior rows"),
                           "launch_mode": launch_mode,
                           "l2_policy": "inputs larger than L2 (fine operator 1.4 GB per GPU vs 126 MB L2)",
                           "setup_s": round(setup_s, 2)},
@@ -340,9 +345,12 @@ def run_ours_distributed(args, rank, world, local):
                             "cycle_frac": round(cyc_bytes / ms / 1e6 / peak, 4)},
                "cpu_baseline": None}
         print(json.dumps(out), flush=True)
+    H.check_exchange()
     dist.barrier()
-    if launch_mode.startswith("CUDA graph"):
-        os._exit(0)                            # skip NCCL teardown with live captured graphs
+    if launch_mode.startswith("CUDA graph") and H.halo != "peer":
+        os._exit(0)                            # skip NCCL teardown with live captured graphs holding NCCL work
+    H._graph = None
+    H.close()
     dist.destroy_process_group()
 
 

@@ -235,6 +235,37 @@ int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, dou
 int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int nu1, int nu2,
                       int cycles, mlamg_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-GPU: peer-memory halo exchange
+ * (the reference has no distributed solve).  One process per GPU; each rank exports one
+ * window with CUDA IPC, its peers map it and write halo values straight into it over NVLink (no staging
+ * buffer, no collective call inside the cycle).  Device-side sequence numbers + flags order the transfer,
+ * so a whole cycle is a fixed list of kernel launches that replays from a CUDA graph. */
+
+/* cudaMalloc a zeroed window of `bytes` and export it: ipc_handle_host receives 64 bytes to ship to peers */
+int mlamg_peer_alloc(long long bytes, void **ptr, void *ipc_handle_host);
+/* map a peer's window from its 64-byte handle / unmap it / free an owned window */
+int mlamg_peer_open(const void *ipc_handle_host, void **ptr);
+int mlamg_peer_close(void *ptr);
+int mlamg_peer_free(void *ptr);
+
+typedef struct mlamg_channel *mlamg_channel_t;
+/* One exchange step.  Send side: n_send_peers segments of the send list (counts >= 0), each with the two
+ * remote destination addresses (sequence parity 0/1, already offset to this rank's segment of the peer's
+ * region) and the remote flag address.  Receive side: n_recv_peers segments laid out back to back in the
+ * local regions recv_region0/1, one local flag per source.  A zero-count segment only carries the flag
+ * (keeps two ranks in step).  state: 4 zeroed device u64 words owned by the caller (sequence number, two
+ * CTA counters, error word: non-zero after a 20 s spin timeout).  At most 16 peers per side. */
+int mlamg_channel_create(int n_send_peers, const int *send_counts_host, void *const *send_dst0_host,
+                         void *const *send_dst1_host, void *const *send_flag_host, int n_recv_peers,
+                         const int *recv_counts_host, const void *recv_region0, const void *recv_region1,
+                         void *const *recv_flag_host, void *state, mlamg_channel_t *out);
+int mlamg_channel_destroy(mlamg_channel_t ch);
+/* pack src[send_idx[i]] (send_idx == NULL: src[i]) into the peers' regions and publish the flags */
+int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src,
+                       mlamg_stream_t stream);
+/* wait for every source's flag, copy the region to dst[0..n_recv), advance the sequence number */
+int mlamg_channel_wait(mlamg_channel_t ch, int dtype, void *dst, mlamg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,14 @@ SIGNATURES = {
     "mlamg_solve": (I, [P, P, P, I, I, D, I, P, P, P]),
     "mlamg_pcg": (I, [P, P, P, I, I, D, I, P, P, P]),
     "mlamg_vcycle_host": (I, [P, P, P, I, I, I, P]),
+    "mlamg_peer_alloc": (I, [LL, P, P]),
+    "mlamg_peer_open": (I, [P, P]),
+    "mlamg_peer_close": (I, [P]),
+    "mlamg_peer_free": (I, [P]),
+    "mlamg_channel_create": (I, [I, P, P, P, P, I, P, P, P, P, P, P]),
+    "mlamg_channel_destroy": (I, [P]),
+    "mlamg_channel_push": (I, [P, I, P, P, P]),
+    "mlamg_channel_wait": (I, [P, I, P, P]),
 }
 
 

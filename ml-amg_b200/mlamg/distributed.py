@@ -53,6 +53,14 @@ class Comm:
         dist.all_gather_object(out, int(v), group=self.group)
         return out
 
+    def all_gather_obj(self, obj):
+        """picklable object per rank -> list in rank order"""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
     def a2a(self, send, send_splits, recv_splits, out=None):
         """variable all-to-all of a 1-D tensor; splits are python int lists (elements per peer)"""
         n_recv = int(sum(recv_splits))
@@ -184,6 +192,152 @@ class HaloPlan:
         self.comm.a2a(send, self.send_counts, self.recv_counts, out=x_ext[n_own:n_own + self.n_halo])
 
 
+# =====================================================================================================
+# peer-memory exchange (CUDA IPC windows + device-side flags): csrc/peer.cu
+# =====================================================================================================
+# split a row-op into interior / boundary rows around the wait only when the interior kernel is long
+# compared with the exchange latency (a few microseconds over NVLink)
+PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 4_000_000))
+_ALIGN = 256
+
+
+def _align(v):
+    return (int(v) + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+def plan_channels(specs, comm):
+    """Window layout of a list of channel specs and the remote offsets each rank writes to.
+
+    specs: [(send_counts[world], recv_counts[world], elem_bytes, connect_all)], identical in number and
+    order on every rank.  Pure host logic (one all_gather_object); returns
+      {'nbytes': window size, 'flag_off': lambda c, src -> byte offset of flag [c][src],
+       'region': [(off_parity0, off_parity1)] per channel (local),
+       'remote': remote[p][c] = (off_parity0, off_parity1) in rank p's window where MY segment starts}"""
+    world, me = comm.world, comm.rank
+    nch = len(specs)
+    flags_bytes = _align(nch * world * 8)
+    off = flags_bytes
+    region, table = [], []
+    for send_counts, recv_counts, esz, _ in specs:
+        assert len(send_counts) == world and len(recv_counts) == world
+        size = _align(max(int(sum(recv_counts)), 1) * esz)
+        region.append((off, off + size))
+        starts = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
+        table.append([(off + int(st) * esz, off + size + int(st) * esz) for st in starts])   # per source rank
+        off += 2 * size
+    tables = comm.all_gather_obj(table)           # tables[p][c][source] = offsets in p's window
+    counts = comm.all_gather_obj([list(map(int, sp_[1])) for sp_ in specs])     # counts[p][c][source]
+    for c, (send_counts, _, _, _) in enumerate(specs):
+        for p in range(world):
+            if int(send_counts[p]) != counts[p][c][me]:
+                raise RuntimeError(f"channel {c}: rank {me} sends {send_counts[p]} entries to {p}, which expects "
+                                   f"{counts[p][c][me]}")
+    remote = [[tables[p][c][me] for c in range(nch)] for p in range(world)]
+    return {"nbytes": off, "nflagbytes": flags_bytes, "region": region, "remote": remote,
+            "flag_off": (lambda c, src: (c * world + src) * 8)}
+
+
+class PeerWindow:
+    """One cudaMalloc block per rank, exported with CUDA IPC and mapped by every peer (collective)."""
+
+    def __init__(self, comm, nbytes):
+        self.comm = comm
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        h = ctypes.create_string_buffer(64)
+        check(lib.mlamg_peer_alloc(self.nbytes, ctypes.byref(p), h))
+        self.base = p.value
+        handles = comm.all_gather_obj(h.raw)       # every window is allocated and zeroed before anyone maps it
+        self.ptrs = []
+        for r, raw in enumerate(handles):
+            if r == comm.rank:
+                self.ptrs.append(self.base)
+            else:
+                q = ctypes.c_void_p()
+                check(lib.mlamg_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)))
+                self.ptrs.append(q.value)
+        comm.barrier()
+
+    def close(self):
+        """collective: unmap the peers' windows, then free the local one"""
+        if self.base is None:
+            return
+        torch.cuda.synchronize()
+        for r, q in enumerate(self.ptrs):
+            if r != self.comm.rank:
+                check(lib.mlamg_peer_close(ctypes.c_void_p(q)))
+        self.comm.barrier()
+        check(lib.mlamg_peer_free(ctypes.c_void_p(self.base)))
+        self.base, self.ptrs = None, []
+
+
+class Channel:
+    """One exchange step bound to its slots in the windows (see csrc/peer.cu)."""
+
+    def __init__(self, handle, send_idx, state, n_recv, name):
+        self._h, self.send_idx, self.state, self.n_recv, self.name = handle, send_idx, state, n_recv, name
+
+    def push(self, src):
+        check(lib.mlamg_channel_push(self._h, core.dt(src), core.ptr(self.send_idx), core.ptr(src), core.stream()))
+
+    def wait(self, dst):
+        assert dst.numel() == self.n_recv
+        check(lib.mlamg_channel_wait(self._h, core.dt(dst), ctypes.c_void_p(dst.data_ptr()), core.stream()))
+
+
+class ChannelSet:
+    """All channels of one cycle shape: one window, one flag row per channel (collective constructor).
+
+    specs: [(name, send_idx int32 cuda tensor | None, send_counts, recv_counts, dtype, connect_all)]"""
+
+    def __init__(self, comm, specs):
+        self.comm = comm
+        world, me = comm.world, comm.rank
+        if world > 16:
+            raise ValueError("peer channels support at most 16 ranks per node")
+        esz = {torch.float32: 4, torch.float64: 8}
+        lay = plan_channels([(sc, rc, esz[dt_], ca) for _, _, sc, rc, dt_, ca in specs], comm)
+        self.window = PeerWindow(comm, lay["nbytes"])
+        W = self.window
+        self.state = torch.zeros(len(specs), 4, dtype=torch.int64, device="cuda")
+        self.channels = {}
+        VP = ctypes.c_void_p
+        for c, (name, send_idx, sc, rc, dt_, connect_all) in enumerate(specs):
+            sp_ = [p for p in range(world) if connect_all or int(sc[p]) > 0]
+            rp_ = [p for p in range(world) if connect_all or int(rc[p]) > 0]
+            s_counts = (ctypes.c_int * max(len(sp_), 1))(*[int(sc[p]) for p in sp_])
+            s_dst0 = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["remote"][p][c][0] for p in sp_])
+            s_dst1 = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["remote"][p][c][1] for p in sp_])
+            s_flag = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["flag_off"](c, me) for p in sp_])
+            r_counts = (ctypes.c_int * max(len(rp_), 1))(*[int(rc[p]) for p in rp_])
+            r_flag = (VP * max(len(rp_), 1))(*[W.base + lay["flag_off"](c, p) for p in rp_])
+            h = VP()
+            check(lib.mlamg_channel_create(len(sp_), s_counts, s_dst0, s_dst1, s_flag, len(rp_), r_counts,
+                                           VP(W.base + lay["region"][c][0]), VP(W.base + lay["region"][c][1]), r_flag,
+                                           VP(self.state[c].data_ptr()), ctypes.byref(h)))
+            n_send = int(sum(int(sc[p]) for p in sp_))
+            assert send_idx is None or send_idx.numel() == n_send
+            self.channels[name] = Channel(h, send_idx, self.state[c], int(sum(int(rc[p]) for p in rp_)), name)
+        comm.barrier()
+
+    def __getitem__(self, name):
+        return self.channels[name]
+
+    def check(self):
+        """raise if a wait timed out (host sync)"""
+        err = self.state[:, 3].cpu()
+        bad = torch.nonzero(err).flatten().tolist()
+        if bad:
+            names = list(self.channels)
+            raise RuntimeError("peer exchange timed out on channel(s) " + ", ".join(names[i] for i in bad))
+
+    def close(self):
+        for ch in self.channels.values():
+            lib.mlamg_channel_destroy(ch._h)
+        self.channels = {}
+        self.window.close()
+
+
 def fetch_rows(rowptr, col, val, offsets, needed_ids, comm):
     """CSR rows `needed_ids` (sorted unique global row ids owned by other ranks), in that order."""
     plan = HaloPlan(needed_ids, offsets, comm)
@@ -277,6 +431,7 @@ class DistOperator:
                 self.interior_range = (i0, i1)
         # overlap only pays when the interior kernel is much longer than an exchange (~40 us)
         self.overlap_ok = self.interior.numel() > 0 and A.nnz >= OVERLAP_MIN_NNZ
+        self.peer_split_ok = self.interior.numel() > 0 and A.nnz >= PEER_SPLIT_MIN_NNZ
 
     def renumber(self, row_new2old=None, col_old2new=None):
         """Block-local renumbering: rows gathered by row_new2old, OWNED columns mapped by col_old2new (halo slots
@@ -294,11 +449,31 @@ class DistOperator:
     def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None):
         core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)
 
-    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None):
-        """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange"""
+    def channel_spec(self, name, dtype):
+        """(name, send list, per-rank counts, dtype, connect_all) of the halo exchange of this operator's input"""
+        return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype, False)
+
+    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None):
+        """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange.
+        chan: peer-memory channel (push -> interior rows -> wait+unpack -> boundary rows, one stream, no
+        collective); None: NCCL all-to-all on a side stream."""
         plan = self.plan
         if plan.comm.world == 1:
             self.rowop(op, x_ext, y, b, dw)
+            return
+        if chan is not None:
+            chan.push(x_ext)
+            halo = x_ext[self.n_cols_own:self.n_cols_own + plan.n_halo]
+            if overlap and self.peer_split_ok:
+                if self.interior_range is not None:
+                    self.rowop(op, x_ext, y, b, dw, row_range=self.interior_range)
+                else:
+                    self.rowop(op, x_ext, y, b, dw, rows=self.interior)
+                chan.wait(halo)
+                self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
+            else:
+                chan.wait(halo)
+                self.rowop(op, x_ext, y, b, dw)
             return
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
@@ -329,12 +504,17 @@ class DistHierarchy:
 
     def __init__(self, rowptr, col_global, val, comm=None, *, ratio=0.1, distance="unit", maxiter=10, rand=0,
                  lam_max=None, max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
-                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True):
+                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True, halo=None):
         core.require_cuda()
         self.comm = comm or Comm()
         comm = self.comm
         self.dtype = val.dtype
         self.overlap = overlap
+        # halo transport of the cycle: 'peer' = CUDA-IPC windows + device flags (csrc/peer.cu), 'nccl' = all-to-all
+        self.halo = halo or _os.environ.get("MLAMG_HALO", "peer")
+        if self.halo not in ("peer", "nccl"):
+            raise ValueError("halo must be 'peer' or 'nccl'")
+        self._chansets = {}
         self.comm_stream = torch.cuda.Stream() if comm.world > 1 else None
         self.levels = []
         self.offsets = []
@@ -488,10 +668,47 @@ class DistHierarchy:
     def n_local(self):
         return self.levels[0].n if self.levels else int(self.tail_offsets[-1])
 
+    def _channels(self, nu1, nu2):
+        """peer channels of a V(nu1,nu2) cycle, built on first use (collective); None on the NCCL transport"""
+        if self.halo != "peer" or self.comm.world == 1:
+            return None
+        cs = self._chansets.get((nu1, nu2))
+        if cs is None:
+            specs = []
+            for l, L in enumerate(self.levels):
+                for k in range(max(nu1 - 1, 0)):
+                    specs.append(L.A.channel_spec((l, "pre", k), self.dtype))
+                specs.append(L.A.channel_spec((l, "res"), self.dtype))
+                specs.append(L.R.channel_spec((l, "R"), self.dtype))
+                specs.append(L.P.channel_spec((l, "P"), self.dtype))
+                for k in range(nu2):
+                    specs.append(L.A.channel_spec((l, "post", k), self.dtype))
+            # coarse-level gather: every rank writes its slice of the restricted residual into every window
+            # (itself included); connect_all keeps every pair of ranks in step once per cycle
+            sizes = self._tail_sizes
+            mine = sizes[self.comm.rank]
+            idx = torch.arange(mine, dtype=torch.int32, device="cuda").repeat(self.comm.world).contiguous()
+            specs.append(("tail", idx, [mine] * self.comm.world, list(sizes), self.dtype, True))
+            cs = self._chansets[(nu1, nu2)] = ChannelSet(self.comm, specs)
+        return cs
+
+    def check_exchange(self):
+        """host sync + raise if any peer exchange timed out"""
+        for cs in self._chansets.values():
+            cs.check()
+
+    def close(self):
+        """collective: release the peer windows"""
+        for cs in self._chansets.values():
+            cs.close()
+        self._chansets = {}
+
     def vcycle(self, b, x_out, nu1=1, nu2=1):
         """x_out = V(nu1,nu2)(b) from a zero guess (preconditioner apply).  b, x_out: local slices."""
         comm = self.comm
         cs = self.comm_stream if self.overlap else None
+        chans = self._channels(nu1, nu2)
+        ch = (lambda *key: chans[key]) if chans is not None else (lambda *key: None)
         rhs = b
         cur = []
         for l, L in enumerate(self.levels):
@@ -502,19 +719,19 @@ class DistHierarchy:
                 core.jacobi_zero(L.dw, rhs, c[:n])
             else:
                 c[:n].zero_()
-            for _ in range(max(nu1 - 1, 0)):
+            for k in range(max(nu1 - 1, 0)):
                 o = xb if c is xa else xa
-                L.A.apply(3, c, o, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs)
+                L.A.apply(3, c, o, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "pre", k))
                 c = o
-            L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs)       # r[:n] = b - A x
+            L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))   # r[:n] = b - A x
             nxt_b = self.levels[l + 1].b if l + 1 < len(self.levels) else None
             if nxt_b is None:
                 nxt_b = self._tail_local_b()
-            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs)          # b_c = R r
+            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs, chan=ch(l, "R"))        # b_c = R r
             cur.append(c)
             rhs = nxt_b
-        # replicated tail: all-gather the restricted residual, every rank solves, keep my slice
-        xc = self._tail_solve(rhs, nu1, nu2)
+        # replicated tail: gather the restricted residual, every rank solves, keep my slice
+        xc = self._tail_solve(rhs, nu1, nu2, chans["tail"] if chans is not None else None)
         for l in range(len(self.levels) - 1, -1, -1):
             L = self.levels[l]
             xa, xb = L.x
@@ -522,10 +739,10 @@ class DistHierarchy:
             c = cur[l]
             L.e[:L.nc].copy_(xc)
             rhs_l = b if l == 0 else self.levels[l].b
-            L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs)              # x += P e
-            for _ in range(nu2):
+            L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"))            # x += P e
+            for k in range(nu2):
                 o = xb if c is xa else xa
-                L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs)
+                L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "post", k))
                 c = o
             xc = c[:n]
         x_out.copy_(xc)
@@ -550,11 +767,14 @@ class DistHierarchy:
         hi = int(self.tail_offsets[self.comm.rank + 1])
         return self.tail_b[lo:hi]
 
-    def _tail_solve(self, b_local, nu1, nu2):
+    def _tail_solve(self, b_local, nu1, nu2, chan=None):
         comm = self.comm
         lo = int(self.tail_offsets[comm.rank])
         hi = int(self.tail_offsets[comm.rank + 1])
-        if comm.world > 1:
+        if chan is not None:
+            chan.push(b_local)
+            chan.wait(self.tail_b)
+        elif comm.world > 1:
             self._tail_in[:hi - lo].copy_(b_local)
             dist.all_gather_into_tensor(self._tail_out, self._tail_in, group=comm.group)
             check(lib.mlamg_gather(core.dt(self.tail_b), n_tail_all(self), core.ptr(self._tail_map), core.ptr(self._tail_out),

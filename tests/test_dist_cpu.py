@@ -39,6 +39,7 @@ def _worker(rank, world, port, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         from mlamg import distributed as md
         comm = md.Comm()
+        world = comm.world
         A = _global_matrix()
         n = A.shape[0]
         cut = [0, 41, n]
@@ -95,6 +96,35 @@ def _worker(rank, world, port, q):
         g_rp, g_col, g_val = md.gather_csr(rowptr, col, val, comm)
         assert np.array_equal(g_rp.numpy(), A.indptr) and np.array_equal(g_col.numpy(), A.indices) and np.array_equal(g_val.numpy(), A.data)
         assert abs(comm.allreduce_sum(rank + 1.0) - 3.0) < 1e-15
+        # peer-window layout (host logic of csrc/peer.cu's channels): emulate every rank's pushes with the planned
+        # remote offsets into byte arrays standing in for the windows, then unpack like the wait kernel
+        specs = [(plan.send_counts, plan.recv_counts, 8, False),
+                 ([3 + rank] * world, [3 + r for r in range(world)], 4, True)]       # halo channel, gather channel
+        lay = md.plan_channels(specs, comm)
+        assert lay["nbytes"] % 256 == 0 and lay["region"][0][0] >= 2 * world * 8
+        srcs = [x_ext[:hi - lo].numpy()[plan.send_idx.numpy()], np.arange(3 + rank, dtype=np.float32).repeat(1) + 10 * rank]
+        writes = []                                   # (dest rank, byte offset, payload bytes) for parity 0 and 1
+        for c, (sc, rc, esz, _) in enumerate(specs):
+            start = 0
+            for pdst in range(world):
+                cnt = int(sc[pdst])
+                seg = srcs[c][start:start + cnt] if c == 0 else srcs[c]
+                start += cnt if c == 0 else 0
+                for par in (0, 1):
+                    writes.append((pdst, lay["remote"][pdst][c][par], np.ascontiguousarray(seg).tobytes()))
+        allw = comm.all_gather_obj(writes)
+        win = np.zeros(lay["nbytes"], dtype=np.uint8)
+        for ws in allw:
+            for pdst, off, payload in ws:
+                if pdst == rank:
+                    assert off + len(payload) <= lay["nbytes"]
+                    win[off:off + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+        for par in (0, 1):
+            got = win[lay["region"][0][par]:lay["region"][0][par] + 8 * plan.n_halo].view(np.float64)
+            assert np.array_equal(got, xg[halo.numpy()])
+            n_all = sum(3 + r for r in range(world))
+            got = win[lay["region"][1][par]:lay["region"][1][par] + 4 * n_all].view(np.float32)
+            assert np.array_equal(got, np.concatenate([np.arange(3 + r, dtype=np.float32) + 10 * r for r in range(world)]))
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))

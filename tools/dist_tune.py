@@ -1,5 +1,14 @@
-"""Timing of distributed-cycle variants (development aid). torchrun --nproc-per-node 2 tools/dist_tune.py [n]"""
-import os, sys, time, json
+"""Timing of distributed-cycle variants (development aid).
+
+    torchrun --nproc-per-node 2 tools/dist_tune.py [n]
+
+Prints one JSON line (rank 0): ms per V(1,1) cycle for the peer-window and NCCL halo transports, eager and
+replayed from a CUDA graph, with and without the interior/boundary row split, plus the cost of single pieces
+(one exchange, one fine sweep with and without its exchange, the replicated tail)."""
+import json
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "ml-amg_b200")]
 import numpy as np
@@ -30,34 +39,51 @@ def main():
         e1.record(); torch.cuda.synchronize(); dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return round(float(t.item()), 4)
 
-    for rb in (500000, 1200000 * world):
-        H = md.DistHierarchy(rowptr, col, val, comm, ratio=0.027, distance="unit", maxiter=10, rand=0, lam_max=[2.0],
-                             max_levels=8, max_coarse=1000, replicate_below=rb)
-        for _ in range(100):
-            H.vcycle(b, x, 1, 1)
-        res = {"replicate_below": rb, "dist_levels": len(H.levels), "tail": [l.A.shape[0] for l in H.tail.levels]}
-        H.overlap = True
-        res["overlap"] = timed(lambda: H.vcycle(b, x, 1, 1))
-        H.overlap = False
-        res["no_overlap"] = timed(lambda: H.vcycle(b, x, 1, 1))
-        H.overlap = True
-        H.tail.use_graph(True)
-        res["overlap_tailgraph"] = timed(lambda: H.vcycle(b, x, 1, 1))
-        # pieces: exchange alone, level-0 jacobi alone
-        L0 = H.levels[0]
-        res["exchange_L0"] = timed(lambda: L0.A.plan.exchange(L0.x[0], L0.n))
-        res["jacobi_L0_all_rows"] = timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw))
-        res["jacobi_L0_apply_overlap"] = timed(lambda: L0.A.apply(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, overlap=True, comm_stream=H.comm_stream))
-        res["tail_only"] = timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1))
-        if len(H.levels) > 1:
-            L1 = H.levels[1]
-            res["jacobi_L1_apply_overlap"] = timed(lambda: L1.A.apply(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw, overlap=True, comm_stream=H.comm_stream))
-            res["jacobi_L1_all_rows"] = timed(lambda: L1.A.rowop(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw))
-        if rank == 0:
-            print(json.dumps(res), flush=True)
-        del H
+    lam0 = 1.0 + (2.0 * np.cos(np.pi / (n + 1)) + np.cos(np.pi / (n * world + 1))) / 3.0
+    H = md.DistHierarchy(rowptr, col, val, comm, ratio=0.027, distance="unit", maxiter=10, rand=0, lam_max=[lam0],
+                         max_levels=8, max_coarse=1000, replicate_below=500000)
+    res = {"n": n, "world": world, "dist_levels": len(H.levels), "tail": [l.A.shape[0] for l in H.tail.levels]}
+    for _ in range(100):
+        H.vcycle(b, x, 1, 1)
+    res["peer_eager"] = timed(lambda: H.vcycle(b, x, 1, 1))
+    H.overlap = False
+    res["peer_eager_nosplit"] = timed(lambda: H.vcycle(b, x, 1, 1))
+    replay = H.capture(b, x, 1, 1)
+    res["peer_graph_nosplit"] = timed(replay)
+    H.overlap = True
+    replay = H.capture(b, x, 1, 1)
+    res["peer_graph"] = timed(replay)
+    H._graph = None
+    L0 = H.levels[0]
+    cs = H._channels(1, 1)
+    ch = cs[(0, "post", 0)]
+    halo = L0.x[0][L0.n:]
+
+    def exch():
+        ch.push(L0.x[0]); ch.wait(halo)
+    res["peer_exchange_L0"] = timed(exch)
+    res["jacobi_L0_all_rows"] = timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw))
+    res["jacobi_L0_peer_apply"] = timed(lambda: L0.A.apply(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, chan=ch))
+    H.halo = "nccl"
+    res["nccl_eager"] = timed(lambda: H.vcycle(b, x, 1, 1))
+    res["nccl_exchange_L0"] = timed(lambda: L0.A.plan.exchange(L0.x[0], L0.n))
+    H.halo = "peer"
+    tail_ch = cs["tail"]
+    res["tail_only_peer"] = timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1, tail_ch))
+    H.tail.use_graph(True)
+    res["tail_only_peer_tailgraph"] = timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1, tail_ch))
+    H.tail.use_graph(False)
+    if len(H.levels) > 1:
+        L1 = H.levels[1]
+        ch1 = cs[(1, "post", 0)]
+        res["jacobi_L1_all_rows"] = timed(lambda: L1.A.rowop(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw))
+        res["jacobi_L1_peer_apply"] = timed(lambda: L1.A.apply(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw, chan=ch1))
+    H.check_exchange()
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    H.close()
     dist.barrier()
     dist.destroy_process_group()
 
