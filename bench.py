@@ -328,8 +328,8 @@ def run_ours_distributed(args, rank, world, local):
                           "distributed_levels": [int(o[-1]) for o in H.offsets[:-1]],
                           "replicated_levels": [l.A.shape[0] for l in H.tail.levels], "cycle": "V(1,1) zero-guess",
                           "halo_entries_fine": L0.A.plan.n_halo,
-                          "halo_transport": ("peer stores into CUDA-IPC windows over NVLink + device flags, interior rows "
-                                             "between push and wait (no collective in the cycle)" if H.halo == "peer"
+                          "halo_transport": ("tagged peer stores into CUDA-IPC windows over NVLink, boundary rows gather the halo in "
+                                             "place, interior rows in between (no collective in the cycle)" if H.halo == "peer"
                                              else "NCCL all-to-all on a side stream overlapped with the interior rows"),
                           "launch_mode": launch_mode,
                           "l2_policy": "inputs larger than L2 (fine operator 1.4 GB per GPU vs 126 MB L2)",

@@ -238,8 +238,9 @@ int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int
 /* ------------------------------------------------------------------ multi-GPU: peer-memory halo exchange
  * (the reference has no distributed solve).  One process per GPU; each rank exports one
  * window with CUDA IPC, its peers map it and write halo values straight into it over NVLink (no staging
- * buffer, no collective call inside the cycle).  Device-side sequence numbers + flags order the transfer,
- * so a whole cycle is a fixed list of kernel launches that replays from a CUDA graph. */
+ * buffer, no collective call inside the cycle).  Every value travels with the channel's sequence tag in
+ * the same atomic unit (f64: 16-byte slot, f32: 8-byte slot), so the consumer needs no fence and no flag;
+ * sequence numbers live in device memory and a whole cycle replays from a CUDA graph. */
 
 /* cudaMalloc a zeroed window of `bytes` and export it: ipc_handle_host receives 64 bytes to ship to peers */
 int mlamg_peer_alloc(long long bytes, void **ptr, void *ipc_handle_host);
@@ -249,22 +250,29 @@ int mlamg_peer_close(void *ptr);
 int mlamg_peer_free(void *ptr);
 
 typedef struct mlamg_channel *mlamg_channel_t;
-/* One exchange step.  Send side: n_send_peers segments of the send list (counts >= 0), each with the two
+/* bytes one element occupies in a receive region (value + tag) */
+int mlamg_channel_slot_bytes(int dtype);
+/* One exchange step.  Send side: n_send_peers segments of the send list (counts > 0), each with the two
  * remote destination addresses (sequence parity 0/1, already offset to this rank's segment of the peer's
- * region) and the remote flag address.  Receive side: n_recv_peers segments laid out back to back in the
- * local regions recv_region0/1, one local flag per source.  A zero-count segment only carries the flag
- * (keeps two ranks in step).  state: 4 zeroed device u64 words owned by the caller (sequence number, two
- * CTA counters, error word: non-zero after a 20 s spin timeout).  At most 16 peers per side. */
+ * region).  Receive side: n_recv slots in each of the local regions recv_region0/1 (segments of the
+ * sources back to back).  state: 4 zeroed device u64 words owned by the caller (sequence number, CTA
+ * counter, spare, error word: non-zero after a 20 s spin timeout).  At most 16 peers. */
 int mlamg_channel_create(int n_send_peers, const int *send_counts_host, void *const *send_dst0_host,
-                         void *const *send_dst1_host, void *const *send_flag_host, int n_recv_peers,
-                         const int *recv_counts_host, const void *recv_region0, const void *recv_region1,
-                         void *const *recv_flag_host, void *state, mlamg_channel_t *out);
+                         void *const *send_dst1_host, int n_recv, const void *recv_region0,
+                         const void *recv_region1, void *state, mlamg_channel_t *out);
 int mlamg_channel_destroy(mlamg_channel_t ch);
-/* pack src[send_idx[i]] (send_idx == NULL: src[i]) into the peers' regions and publish the flags */
+/* pack src[send_idx[i]] (send_idx == NULL: src[i]; negative index: 0, a padding slot) into the peers'
+ * regions and advance the sequence number.  Launched once per use on every rank of a live channel. */
 int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src,
                        mlamg_stream_t stream);
-/* wait for every source's flag, copy the region to dst[0..n_recv), advance the sequence number */
-int mlamg_channel_wait(mlamg_channel_t ch, int dtype, void *dst, mlamg_stream_t stream);
+/* after this use's push: wait for every slot, dst[dst_idx[i]] = slot i (dst_idx == NULL: dst[i];
+ * negative: waited for, not stored) */
+int mlamg_channel_unpack(mlamg_channel_t ch, int dtype, const int *dst_idx, void *dst, mlamg_stream_t stream);
+/* after this use's push: mlamg_rowop_csr whose gathers of columns >= n_own read slot (col - n_own) of the
+ * channel's receive region in place, waiting only for the values that have not landed yet */
+int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nnz_hint, const int *rowptr,
+                        const int *col, const void *val, const void *x, int n_own, const void *b,
+                        const void *dw, void *y, const int *row_list, int row_begin, mlamg_stream_t stream);
 
 #ifdef __cplusplus
 }

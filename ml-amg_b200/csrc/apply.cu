@@ -4,7 +4,9 @@
 // Roofline: every kernel here is HBM-bound (SpMV intensity ~2 flop / 12 B).  One pass over the
 // operator per kernel; x gathers are served by L1/L2 (banded operators) — algorithmic bytes per
 // SURVEY.md §8(d):  B_spmv = nnz(v+4) + 4(N+1) + 2vN,  B_jacobi = nnz(v+4) + 4(N+1) + 4vN.
+#include <string.h>
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mlamg {
 
@@ -34,16 +36,26 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
 // contiguous in CSR, so a warp always reads one contiguous span of col/val; the inner loop is
 // unrolled 4x so every thread keeps 4 (col,val) pairs and 4 gathers of x in flight (HBM latency is
 // hidden by memory-level parallelism, not by occupancy alone).  Segmented shuffle reduction.
-template <typename T, int LANES, int OP, bool NORM>
+// HALO: columns >= halo.n_own are read in place from a peer channel's receive region (values written by the
+// neighbouring GPUs over NVLink, each carrying a sequence tag; the load spins on the few that have not landed).
+template <typename T, int LANES, int OP, bool NORM, bool HALO>
 __global__ void __launch_bounds__(ROW_THREADS)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
                  const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial,
-                 const int *__restrict__ row_order, int row0) {
+                 const int *__restrict__ row_order, int row0, const HaloLL halo) {
     const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
     long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
     T sum = (T)0;
+    unsigned tag = 0;
+    const T *hreg = nullptr;
+    if (HALO) {
+        const unsigned long long seq = *(volatile unsigned long long *)halo.state;   // advanced by this use's push
+        tag = ll_tag(seq);
+        hreg = reinterpret_cast<const T *>((seq & 1ull) ? halo.region[1] : halo.region[0]);
+    }
+#define XLOAD(c) ((HALO && (c) >= halo.n_own) ? ll_load(hreg, (c) - halo.n_own, tag, halo.state) : x[(c)])
     // row_order: optional list of the n rows to process (a permutation of all rows, or a subset).  Used by
     // the restriction, whose rows (aggregates) are numbered randomly by the reference's seeding — visiting
     // them in spatial order lets neighbouring aggregates share the fine-vector sectors they gather through
@@ -64,16 +76,17 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
             const T v1 = p1 ? val[j + LANES] : (T)0;
             const T v2 = p2 ? val[j + 2 * LANES] : (T)0;
             const T v3 = p3 ? val[j + 3 * LANES] : (T)0;
-            const T x0 = x[c0];
-            const T x1 = p1 ? x[c1] : (T)0;
-            const T x2 = p2 ? x[c2] : (T)0;
-            const T x3 = p3 ? x[c3] : (T)0;
+            const T x0 = XLOAD(c0);
+            const T x1 = p1 ? XLOAD(c1) : (T)0;
+            const T x2 = p2 ? XLOAD(c2) : (T)0;
+            const T x3 = p3 ? XLOAD(c3) : (T)0;
             sum += v0 * x0;
             sum += v1 * x1;
             sum += v2 * x2;
             sum += v3 * x3;
         }
     }
+#undef XLOAD
     if (LANES > 1) sum = group_sum<LANES>(sum);
     double rr = 0.0;
     if (valid && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
@@ -151,7 +164,7 @@ static int pick_lanes(int n, long long nnz) {
 template <typename T, int OP, bool NORM>
 static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *x,
                         const T *b, const T *dw, T *y, double *norm2, cudaStream_t s, const int *row_order = nullptr,
-                        int row0 = 0) {
+                        int row0 = 0, const HaloLL *halo = nullptr) {
     if (n <= 0) {
         if (NORM && norm2) MLAMG_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double), s));
         return MLAMG_OK;
@@ -164,8 +177,19 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
         MLAMG_SCRATCH_OK(part);
         partial = part.as<double>();
     }
-#define LAUNCH(L)                                                                                       \
-    csr_rowop_kernel<T, L, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row_order, row0)
+    HaloLL hl;
+    memset(&hl, 0, sizeof(hl));
+    if (halo) hl = *halo;
+    if (halo && NORM) return set_error(MLAMG_EINVAL, "rowop: no norm on the in-place halo variant");
+#define LAUNCH(L)                                                                                                    \
+    do {                                                                                                             \
+        if (halo)                                                                                                    \
+            csr_rowop_kernel<T, L, OP, false, true><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
+                                                                                  nullptr, row_order, row0, hl);     \
+        else                                                                                                         \
+            csr_rowop_kernel<T, L, OP, NORM, false><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
+                                                                                   partial, row_order, row0, hl);    \
+    } while (0)
     switch (lanes) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -482,6 +506,33 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
             break;
         case OP_JACOBI: ROWOP_CASE(OP_JACOBI, false); break;
         default: return set_error(MLAMG_EINVAL, "rowop: bad op %d", op);
+    }
+#undef ROWOP_CASE
+    return MLAMG_OK;
+}
+
+// row-op whose gathers of columns >= n_own read the channel's receive region in place (csrc/peer.cu)
+int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col,
+                        const void *val, const void *x, int n_own, const void *b, const void *dw, void *y,
+                        const int *row_list, int row_begin, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (!ch) return set_error(MLAMG_EINVAL, "channel_rowop: null channel");
+    if (nrows < 0 || n_own < 0) return set_error(MLAMG_EINVAL, "channel_rowop: bad nrows/n_own");
+    if (x == y) return set_error(MLAMG_EINVAL, "channel_rowop: x aliases y");
+    HaloLL hl;
+    hl.n_own = n_own;
+    hl.region[0] = ch->dev.recv_region[0];
+    hl.region[1] = ch->dev.recv_region[1];
+    hl.state = ch->dev.state;
+#define ROWOP_CASE(OPC) \
+    MLAMG_DISPATCH(dtype, return (launch_rowop<T, OPC, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x, \
+                                                               (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list, row_begin, &hl)))
+    switch (op) {
+        case OP_SPMV: ROWOP_CASE(OP_SPMV); break;
+        case OP_SPMV_ADD: ROWOP_CASE(OP_SPMV_ADD); break;
+        case OP_RESIDUAL: ROWOP_CASE(OP_RESIDUAL); break;
+        case OP_JACOBI: ROWOP_CASE(OP_JACOBI); break;
+        default: return set_error(MLAMG_EINVAL, "channel_rowop: bad op %d", op);
     }
 #undef ROWOP_CASE
     return MLAMG_OK;

@@ -78,10 +78,12 @@ SIGNATURES = {
     "mlamg_peer_open": (I, [P, P]),
     "mlamg_peer_close": (I, [P]),
     "mlamg_peer_free": (I, [P]),
-    "mlamg_channel_create": (I, [I, P, P, P, P, I, P, P, P, P, P, P]),
+    "mlamg_channel_slot_bytes": (I, [I]),
+    "mlamg_channel_create": (I, [I, P, P, P, I, P, P, P, P]),
     "mlamg_channel_destroy": (I, [P]),
     "mlamg_channel_push": (I, [P, I, P, P, P]),
-    "mlamg_channel_wait": (I, [P, I, P, P]),
+    "mlamg_channel_unpack": (I, [P, I, P, P, P]),
+    "mlamg_channel_rowop": (I, [P, I, I, I, I, P, P, P, P, I, P, P, P, P, I, P]),
 }
 
 

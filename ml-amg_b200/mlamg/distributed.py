@@ -27,6 +27,7 @@ import torch.distributed as dist
 
 from . import core
 from . import hierarchy as hmod
+from . import _lib
 from ._lib import lib, check
 
 
@@ -197,7 +198,9 @@ class HaloPlan:
 # =====================================================================================================
 # split a row-op into interior / boundary rows around the wait only when the interior kernel is long
 # compared with the exchange latency (a few microseconds over NVLink)
-PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 4_000_000))
+PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 30_000_000))
+# 1: the consuming row-op reads halo values in place from the receive region; 0: unpack kernel + plain row-op
+PEER_INPLACE = _os.environ.get("MLAMG_PEER_INPLACE", "1") == "1"
 _ALIGN = 256
 
 
@@ -208,33 +211,31 @@ def _align(v):
 def plan_channels(specs, comm):
     """Window layout of a list of channel specs and the remote offsets each rank writes to.
 
-    specs: [(send_counts[world], recv_counts[world], elem_bytes, connect_all)], identical in number and
-    order on every rank.  Pure host logic (one all_gather_object); returns
-      {'nbytes': window size, 'flag_off': lambda c, src -> byte offset of flag [c][src],
-       'region': [(off_parity0, off_parity1)] per channel (local),
+    specs: [(send_counts[world], recv_counts[world], slot_bytes)], identical in number and order on every
+    rank.  Pure host logic (two all_gather_object); returns
+      {'nbytes': window size,
+       'region': [(off_parity0, off_parity1)] per channel (local byte offsets),
        'remote': remote[p][c] = (off_parity0, off_parity1) in rank p's window where MY segment starts}"""
     world, me = comm.world, comm.rank
     nch = len(specs)
-    flags_bytes = _align(nch * world * 8)
-    off = flags_bytes
+    off = 0
     region, table = [], []
-    for send_counts, recv_counts, esz, _ in specs:
+    for send_counts, recv_counts, slot in specs:
         assert len(send_counts) == world and len(recv_counts) == world
-        size = _align(max(int(sum(recv_counts)), 1) * esz)
+        size = _align(max(int(sum(recv_counts)), 1) * slot)
         region.append((off, off + size))
         starts = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
-        table.append([(off + int(st) * esz, off + size + int(st) * esz) for st in starts])   # per source rank
+        table.append([(off + int(st) * slot, off + size + int(st) * slot) for st in starts])   # per source rank
         off += 2 * size
     tables = comm.all_gather_obj(table)           # tables[p][c][source] = offsets in p's window
     counts = comm.all_gather_obj([list(map(int, sp_[1])) for sp_ in specs])     # counts[p][c][source]
-    for c, (send_counts, _, _, _) in enumerate(specs):
+    for c, (send_counts, _, _) in enumerate(specs):
         for p in range(world):
             if int(send_counts[p]) != counts[p][c][me]:
                 raise RuntimeError(f"channel {c}: rank {me} sends {send_counts[p]} entries to {p}, which expects "
                                    f"{counts[p][c][me]}")
     remote = [[tables[p][c][me] for c in range(nch)] for p in range(world)]
-    return {"nbytes": off, "nflagbytes": flags_bytes, "region": region, "remote": remote,
-            "flag_off": (lambda c, src: (c * world + src) * 8)}
+    return {"nbytes": max(off, _ALIGN), "region": region, "remote": remote}
 
 
 class PeerWindow:
@@ -278,46 +279,63 @@ class Channel:
         self._h, self.send_idx, self.state, self.n_recv, self.name = handle, send_idx, state, n_recv, name
 
     def push(self, src):
+        """pack src[send_idx] into the peers' regions (tagged values) and advance the sequence number"""
         check(lib.mlamg_channel_push(self._h, core.dt(src), core.ptr(self.send_idx), core.ptr(src), core.stream()))
 
-    def wait(self, dst):
-        assert dst.numel() == self.n_recv
-        check(lib.mlamg_channel_wait(self._h, core.dt(dst), ctypes.c_void_p(dst.data_ptr()), core.stream()))
+    def unpack(self, dst, dst_idx=None):
+        """after push: wait for every slot and copy it to dst (optionally through an index map)"""
+        assert dst_idx is not None or dst.numel() == self.n_recv
+        check(lib.mlamg_channel_unpack(self._h, core.dt(dst), core.ptr(dst_idx), ctypes.c_void_p(dst.data_ptr()),
+                                       core.stream()))
+
+    def rowop(self, A, op, x_ext, n_own, y, b=None, dw=None, rows=None, row_range=None):
+        """after push: core.rowop whose gathers of halo columns read the receive region in place"""
+        begin = 0
+        if rows is not None:
+            n = rows.numel()
+        elif row_range is not None:
+            begin, n = int(row_range[0]), int(row_range[1] - row_range[0])
+        else:
+            n = A.shape[0]
+        if n <= 0:
+            return y
+        check(lib.mlamg_channel_rowop(self._h, core.dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))),
+                                      core.ptr(A.rowptr), core.ptr(A.col), core.ptr(A.val), core.ptr(x_ext), int(n_own),
+                                      core.ptr(b), core.ptr(dw), core.ptr(y), core.ptr(rows), begin, core.stream()))
+        return y
 
 
 class ChannelSet:
-    """All channels of one cycle shape: one window, one flag row per channel (collective constructor).
+    """All channels of one cycle shape in one window (collective constructor).
 
-    specs: [(name, send_idx int32 cuda tensor | None, send_counts, recv_counts, dtype, connect_all)]"""
+    specs: [(name, send_idx int32 cuda tensor | None, send_counts[world], recv_counts[world], dtype)]"""
 
     def __init__(self, comm, specs):
         self.comm = comm
-        world, me = comm.world, comm.rank
+        world = comm.world
         if world > 16:
             raise ValueError("peer channels support at most 16 ranks per node")
-        esz = {torch.float32: 4, torch.float64: 8}
-        lay = plan_channels([(sc, rc, esz[dt_], ca) for _, _, sc, rc, dt_, ca in specs], comm)
+        slot = {torch.float32: int(lib.mlamg_channel_slot_bytes(_lib.F32)),
+                torch.float64: int(lib.mlamg_channel_slot_bytes(_lib.F64))}
+        lay = plan_channels([(sc, rc, slot[dt_]) for _, _, sc, rc, dt_ in specs], comm)
         self.window = PeerWindow(comm, lay["nbytes"])
         W = self.window
         self.state = torch.zeros(len(specs), 4, dtype=torch.int64, device="cuda")
         self.channels = {}
         VP = ctypes.c_void_p
-        for c, (name, send_idx, sc, rc, dt_, connect_all) in enumerate(specs):
-            sp_ = [p for p in range(world) if connect_all or int(sc[p]) > 0]
-            rp_ = [p for p in range(world) if connect_all or int(rc[p]) > 0]
+        for c, (name, send_idx, sc, rc, dt_) in enumerate(specs):
+            sp_ = [p for p in range(world) if int(sc[p]) > 0]
             s_counts = (ctypes.c_int * max(len(sp_), 1))(*[int(sc[p]) for p in sp_])
             s_dst0 = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["remote"][p][c][0] for p in sp_])
             s_dst1 = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["remote"][p][c][1] for p in sp_])
-            s_flag = (VP * max(len(sp_), 1))(*[W.ptrs[p] + lay["flag_off"](c, me) for p in sp_])
-            r_counts = (ctypes.c_int * max(len(rp_), 1))(*[int(rc[p]) for p in rp_])
-            r_flag = (VP * max(len(rp_), 1))(*[W.base + lay["flag_off"](c, p) for p in rp_])
+            n_recv = int(sum(int(v) for v in rc))
             h = VP()
-            check(lib.mlamg_channel_create(len(sp_), s_counts, s_dst0, s_dst1, s_flag, len(rp_), r_counts,
-                                           VP(W.base + lay["region"][c][0]), VP(W.base + lay["region"][c][1]), r_flag,
-                                           VP(self.state[c].data_ptr()), ctypes.byref(h)))
+            check(lib.mlamg_channel_create(len(sp_), s_counts, s_dst0, s_dst1, n_recv, VP(W.base + lay["region"][c][0]),
+                                           VP(W.base + lay["region"][c][1]), VP(self.state[c].data_ptr()), ctypes.byref(h)))
             n_send = int(sum(int(sc[p]) for p in sp_))
             assert send_idx is None or send_idx.numel() == n_send
-            self.channels[name] = Channel(h, send_idx, self.state[c], int(sum(int(rc[p]) for p in rp_)), name)
+            self.channels[name] = Channel(h, send_idx, self.state[c], n_recv, name)
+        torch.cuda.synchronize()
         comm.barrier()
 
     def __getitem__(self, name):
@@ -329,7 +347,7 @@ class ChannelSet:
         bad = torch.nonzero(err).flatten().tolist()
         if bad:
             names = list(self.channels)
-            raise RuntimeError("peer exchange timed out on channel(s) " + ", ".join(names[i] for i in bad))
+            raise RuntimeError("peer exchange timed out on channel(s) " + ", ".join(str(names[i]) for i in bad))
 
     def close(self):
         for ch in self.channels.values():
@@ -450,30 +468,32 @@ class DistOperator:
         core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)
 
     def channel_spec(self, name, dtype):
-        """(name, send list, per-rank counts, dtype, connect_all) of the halo exchange of this operator's input"""
-        return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype, False)
+        """(name, send list, per-rank counts, dtype) of the halo exchange of this operator's input"""
+        return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype)
 
     def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None):
         """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange.
-        chan: peer-memory channel (push -> interior rows -> wait+unpack -> boundary rows, one stream, no
-        collective); None: NCCL all-to-all on a side stream."""
+        chan: peer-memory channel (push -> interior rows -> boundary rows reading the halo in place from the
+        receive region; one stream, no collective); None: NCCL all-to-all on a side stream."""
         plan = self.plan
         if plan.comm.world == 1:
             self.rowop(op, x_ext, y, b, dw)
             return
         if chan is not None:
+            n_own = self.n_cols_own
             chan.push(x_ext)
-            halo = x_ext[self.n_cols_own:self.n_cols_own + plan.n_halo]
-            if overlap and self.peer_split_ok:
+            split = overlap and self.peer_split_ok
+            if split:
                 if self.interior_range is not None:
                     self.rowop(op, x_ext, y, b, dw, row_range=self.interior_range)
                 else:
                     self.rowop(op, x_ext, y, b, dw, rows=self.interior)
-                chan.wait(halo)
-                self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
+            rows = self.boundary if split else None
+            if PEER_INPLACE:
+                chan.rowop(self.csr, op, x_ext, n_own, y, b=b, dw=dw, rows=rows)
             else:
-                chan.wait(halo)
-                self.rowop(op, x_ext, y, b, dw)
+                chan.unpack(x_ext[n_own:n_own + plan.n_halo])
+                self.rowop(op, x_ext, y, b, dw, rows=rows)
             return
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
@@ -683,12 +703,17 @@ class DistHierarchy:
                 specs.append(L.P.channel_spec((l, "P"), self.dtype))
                 for k in range(nu2):
                     specs.append(L.A.channel_spec((l, "post", k), self.dtype))
-            # coarse-level gather: every rank writes its slice of the restricted residual into every window
-            # (itself included); connect_all keeps every pair of ranks in step once per cycle
+            # coarse-level gather: every rank writes its slice of the restricted residual (+ one padding slot, so
+            # that every pair of ranks is in step once per cycle even with an empty slice) into every window
             sizes = self._tail_sizes
             mine = sizes[self.comm.rank]
-            idx = torch.arange(mine, dtype=torch.int32, device="cuda").repeat(self.comm.world).contiguous()
-            specs.append(("tail", idx, [mine] * self.comm.world, list(sizes), self.dtype, True))
+            one = torch.cat([torch.arange(mine, dtype=torch.int32), torch.tensor([-1], dtype=torch.int32)])
+            idx = one.repeat(self.comm.world).cuda().contiguous()
+            specs.append(("tail", idx, [mine + 1] * self.comm.world, [sz + 1 for sz in sizes], self.dtype))
+            offs = self.tail_offsets
+            self._tail_unpack_idx = torch.cat(
+                [torch.cat([torch.arange(int(offs[r]), int(offs[r + 1]), dtype=torch.int32), torch.tensor([-1], dtype=torch.int32)])
+                 for r in range(self.comm.world)]).cuda().contiguous()
             cs = self._chansets[(nu1, nu2)] = ChannelSet(self.comm, specs)
         return cs
 
@@ -732,20 +757,26 @@ class DistHierarchy:
             rhs = nxt_b
         # replicated tail: gather the restricted residual, every rank solves, keep my slice
         xc = self._tail_solve(rhs, nu1, nu2, chans["tail"] if chans is not None else None)
-        for l in range(len(self.levels) - 1, -1, -1):
+        nl = len(self.levels)
+        for l in range(nl - 1, -1, -1):
             L = self.levels[l]
             xa, xb = L.x
             n = L.n
             c = cur[l]
-            L.e[:L.nc].copy_(xc)
+            if xc is not None:                       # coarse correction not yet in L.e (tail, or a level without post-smoothing)
+                L.e[:L.nc].copy_(xc)
             rhs_l = b if l == 0 else self.levels[l].b
             L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"))            # x += P e
+            # the last sweep writes straight into its consumer: the caller's vector (level 0) or the finer level's
+            # coarse-correction buffer — no copy on the way up
+            target = x_out if l == 0 else self.levels[l - 1].e
             for k in range(nu2):
-                o = xb if c is xa else xa
+                o = target if k == nu2 - 1 else (xb if c is xa else xa)
                 L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "post", k))
                 c = o
-            xc = c[:n]
-        x_out.copy_(xc)
+            xc = None if nu2 > 0 else c[:n]
+        if xc is not None:
+            x_out.copy_(xc)
         return x_out
 
     def capture(self, b, x_out, nu1=1, nu2=1):
@@ -773,7 +804,7 @@ class DistHierarchy:
         hi = int(self.tail_offsets[comm.rank + 1])
         if chan is not None:
             chan.push(b_local)
-            chan.wait(self.tail_b)
+            chan.unpack(self.tail_b, self._tail_unpack_idx)
         elif comm.world > 1:
             self._tail_in[:hi - lo].copy_(b_local)
             dist.all_gather_into_tensor(self._tail_out, self._tail_in, group=comm.group)

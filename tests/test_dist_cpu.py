@@ -98,13 +98,13 @@ def _worker(rank, world, port, q):
         assert abs(comm.allreduce_sum(rank + 1.0) - 3.0) < 1e-15
         # peer-window layout (host logic of csrc/peer.cu's channels): emulate every rank's pushes with the planned
         # remote offsets into byte arrays standing in for the windows, then unpack like the wait kernel
-        specs = [(plan.send_counts, plan.recv_counts, 8, False),
-                 ([3 + rank] * world, [3 + r for r in range(world)], 4, True)]       # halo channel, gather channel
+        specs = [(plan.send_counts, plan.recv_counts, 8),
+                 ([3 + rank] * world, [3 + r for r in range(world)], 4)]       # halo channel, gather channel
         lay = md.plan_channels(specs, comm)
-        assert lay["nbytes"] % 256 == 0 and lay["region"][0][0] >= 2 * world * 8
+        assert lay["nbytes"] % 256 == 0 and lay["region"][0][0] == 0
         srcs = [x_ext[:hi - lo].numpy()[plan.send_idx.numpy()], np.arange(3 + rank, dtype=np.float32).repeat(1) + 10 * rank]
         writes = []                                   # (dest rank, byte offset, payload bytes) for parity 0 and 1
-        for c, (sc, rc, esz, _) in enumerate(specs):
+        for c, (sc, rc, esz) in enumerate(specs):
             start = 0
             for pdst in range(world):
                 cnt = int(sc[pdst])

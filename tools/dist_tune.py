@@ -47,14 +47,23 @@ def main():
     res = {"n": n, "world": world, "dist_levels": len(H.levels), "tail": [l.A.shape[0] for l in H.tail.levels]}
     for _ in range(100):
         H.vcycle(b, x, 1, 1)
+    def graph_timed(fn, reps=10):
+        """GPU-side cost of fn: `reps` back-to-back calls captured in one CUDA graph (no CPU launch overhead)"""
+        fn(); torch.cuda.synchronize(); dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            for _ in range(reps):
+                fn()
+        return round(timed(g.replay, k=10) / reps, 4)
+
     res["peer_eager"] = timed(lambda: H.vcycle(b, x, 1, 1))
+    res["peer_graph"] = timed(H.capture(b, x, 1, 1))
+    md.PEER_INPLACE = False
+    res["peer_graph_unpack"] = timed(H.capture(b, x, 1, 1))
+    md.PEER_INPLACE = True
     H.overlap = False
-    res["peer_eager_nosplit"] = timed(lambda: H.vcycle(b, x, 1, 1))
-    replay = H.capture(b, x, 1, 1)
-    res["peer_graph_nosplit"] = timed(replay)
+    res["peer_graph_nosplit"] = timed(H.capture(b, x, 1, 1))
     H.overlap = True
-    replay = H.capture(b, x, 1, 1)
-    res["peer_graph"] = timed(replay)
     H._graph = None
     L0 = H.levels[0]
     cs = H._channels(1, 1)
@@ -62,24 +71,27 @@ def main():
     halo = L0.x[0][L0.n:]
 
     def exch():
-        ch.push(L0.x[0]); ch.wait(halo)
-    res["peer_exchange_L0"] = timed(exch)
-    res["jacobi_L0_all_rows"] = timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw))
-    res["jacobi_L0_peer_apply"] = timed(lambda: L0.A.apply(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, chan=ch))
-    H.halo = "nccl"
-    res["nccl_eager"] = timed(lambda: H.vcycle(b, x, 1, 1))
-    res["nccl_exchange_L0"] = timed(lambda: L0.A.plan.exchange(L0.x[0], L0.n))
-    H.halo = "peer"
+        ch.push(L0.x[0]); ch.unpack(halo)
+    res["g_peer_exchange_L0"] = graph_timed(exch)
+    res["g_jacobi_L0_all_rows"] = graph_timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw))
+    res["g_jacobi_L0_peer_apply"] = graph_timed(lambda: L0.A.apply(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, chan=ch))
+    res["g_jacobi_L0_interior_only"] = graph_timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, row_range=L0.A.interior_range))
+    res["g_jacobi_L0_boundary_list"] = graph_timed(lambda: L0.A.rowop(3, L0.x[0], L0.x[1], b=b, dw=L0.dw, rows=L0.A.boundary))
     tail_ch = cs["tail"]
-    res["tail_only_peer"] = timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1, tail_ch))
-    H.tail.use_graph(True)
-    res["tail_only_peer_tailgraph"] = timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1, tail_ch))
-    H.tail.use_graph(False)
+    res["g_tail_only_peer"] = graph_timed(lambda: H._tail_solve(H._tail_local_b(), 1, 1, tail_ch))
     if len(H.levels) > 1:
         L1 = H.levels[1]
         ch1 = cs[(1, "post", 0)]
-        res["jacobi_L1_all_rows"] = timed(lambda: L1.A.rowop(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw))
-        res["jacobi_L1_peer_apply"] = timed(lambda: L1.A.apply(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw, chan=ch1))
+        res["g_jacobi_L1_all_rows"] = graph_timed(lambda: L1.A.rowop(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw))
+        res["g_jacobi_L1_peer_apply"] = graph_timed(lambda: L1.A.apply(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw, chan=ch1))
+        H.overlap = False
+        res["g_jacobi_L1_peer_apply_nosplit"] = graph_timed(lambda: L1.A.apply(3, L1.x[0], L1.x[1], b=L1.b, dw=L1.dw, overlap=False, chan=ch1))
+        H.overlap = True
+        res["L1"] = {"rows": L1.n, "nnz": L1.A.csr.nnz, "halo": L1.A.plan.n_halo, "boundary_rows": int(L1.A.boundary.numel()),
+                     "P_nnz": L0.P.csr.nnz, "P_halo": L0.P.plan.n_halo, "R_halo": L0.R.plan.n_halo}
+    H.halo = "nccl"
+    res["nccl_eager"] = timed(lambda: H.vcycle(b, x, 1, 1))
+    H.halo = "peer"
     H.check_exchange()
     if rank == 0:
         print(json.dumps(res), flush=True)
