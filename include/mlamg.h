@@ -66,6 +66,12 @@ int mlamg_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *
 int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                      const void *dw, const void *b, const void *x_in, void *x_out,
                      mlamg_stream_t stream);
+/* x_out = dw .* b ; r = b - A x_out (+ *norm2 = ||r||^2 if norm2 != NULL): the first sweep from a zero guess
+ * fused with the residual that follows it in the cycle — x is never read back from HBM, the gathers evaluate
+ * dw[c]*b[c] on the fly. */
+int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                                   const void *dw, const void *b, void *x_out, void *r, double *norm2,
+                                   mlamg_stream_t stream);
 /* x = dw .* b  (first sweep from a zero guess: no pass over A) */
 int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream);
 /* smoother diagonal: mode 0 -> omega / a_ii, mode 1 -> 1 / sum_j |a_ij| (omega ignored) */
@@ -82,14 +88,16 @@ int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *
                      const void *x, const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream);
 /* generic row-op over the row range [row_begin, row_begin + nrows) (row_list == NULL) or the listed rows
  * row_list[0..nrows):
- * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax).  Used by the row-partitioned multi-GPU levels
- * to run interior rows while the halo exchange of x is in flight, then the boundary rows. */
+ * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax) | 4 x=dw.*b (x is an OUTPUT), y=b-Ax.
+ * Used by the row-partitioned multi-GPU levels to run interior rows while the halo exchange of x is in
+ * flight, then the boundary rows. */
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
                     const void *x, const void *b, const void *dw, void *y, const int *row_list, int row_begin,
                     double *norm2, mlamg_stream_t stream);
 /* halo pack: dst[i] = src[idx[i]] */
 int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, mlamg_stream_t stream);
-/* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32), -1 = heuristic */
+/* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32; 0 = staged shared-memory
+ * thread-per-row kernel), -1 = heuristic; -2 / -3 = heuristic without / with the staged kernel */
 int mlamg_set_csr_lanes(int lanes);
 /* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
 int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *val,
@@ -261,9 +269,10 @@ int mlamg_channel_create(int n_send_peers, const int *send_counts_host, void *co
                          void *const *send_dst1_host, int n_recv, const void *recv_region0,
                          const void *recv_region1, void *state, mlamg_channel_t *out);
 int mlamg_channel_destroy(mlamg_channel_t ch);
-/* pack src[send_idx[i]] (send_idx == NULL: src[i]; negative index: 0, a padding slot) into the peers'
- * regions and advance the sequence number.  Launched once per use on every rank of a live channel. */
-int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src,
+/* pack src[send_idx[i]] (times scale[send_idx[i]] if scale != NULL; send_idx == NULL: src[i]; negative
+ * index: 0, a padding slot) into the peers' regions and advance the sequence number.  Launched once per
+ * use on every rank of a live channel. */
+int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src, const void *scale,
                        mlamg_stream_t stream);
 /* after this use's push: wait for every slot, dst[dst_idx[i]] = slot i (dst_idx == NULL: dst[i];
  * negative: waited for, not stored) */

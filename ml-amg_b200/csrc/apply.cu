@@ -10,13 +10,15 @@
 
 namespace mlamg {
 
-enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3 };
+// OP_RESZERO: first pre-smoothing sweep from a zero guess fused with the residual: x = dw.*b is never read back
+// from HBM — the gathers evaluate dw[c]*b[c] on the fly, the epilogue stores x[row] and r[row] = b[row] - (A x)[row]
+enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4 };
 
 constexpr int ROW_THREADS = 256;
 
 template <typename T, int OP, bool NORM>
 __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__restrict__ x, const T *__restrict__ b,
-                                               const T *__restrict__ dw, T *__restrict__ y) {
+                                               const T *__restrict__ dw, T *__restrict__ y, T *__restrict__ y2) {
     double rr = 0.0;
     if (OP == OP_SPMV) {
         y[row] = sum;
@@ -24,6 +26,12 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
         y[row] += sum;
     } else if (OP == OP_RESIDUAL) {
         const T r = b[row] - sum;
+        y[row] = r;
+        if (NORM) rr = (double)r * (double)r;
+    } else if (OP == OP_RESZERO) {
+        const T br = b[row];
+        y2[row] = dw[row] * br;
+        const T r = br - sum;
         y[row] = r;
         if (NORM) rr = (double)r * (double)r;
     } else {  // OP_JACOBI
@@ -39,11 +47,11 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
 // HALO: columns >= halo.n_own are read in place from a peer channel's receive region (values written by the
 // neighbouring GPUs over NVLink, each carrying a sequence tag; the load spins on the few that have not landed).
 template <typename T, int LANES, int OP, bool NORM, bool HALO>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, (LANES == 1 && !HALO) ? 8 : 6)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
                  const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial,
-                 const int *__restrict__ row_order, int row0, const HaloLL halo) {
+                 const int *__restrict__ row_order, int row0, const HaloLL halo, T *__restrict__ y2) {
     const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
     long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
@@ -55,7 +63,8 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
         tag = ll_tag(seq);
         hreg = reinterpret_cast<const T *>((seq & 1ull) ? halo.region[1] : halo.region[0]);
     }
-#define XLOAD(c) ((HALO && (c) >= halo.n_own) ? ll_load(hreg, (c) - halo.n_own, tag, halo.state) : x[(c)])
+#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : x[(c)])
+#define XLOAD(c) ((HALO && (c) >= halo.n_own) ? ll_load(hreg, (c) - halo.n_own, tag, halo.state) : XOWN(c))
     // row_order: optional list of the n rows to process (a permutation of all rows, or a subset).  Used by
     // the restriction, whose rows (aggregates) are numbered randomly by the reference's seeding — visiting
     // them in spatial order lets neighbouring aggregates share the fine-vector sectors they gather through
@@ -65,31 +74,98 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     if (valid) {
         const int start = rowptr[row];
         const int end = rowptr[row + 1];
-        // batches of 4 predicated entries per lane: all col/val loads, then all x gathers, then the FMAs
-        for (int j = start + lane; j < end; j += 4 * LANES) {
-            const bool p1 = j + LANES < end, p2 = j + 2 * LANES < end, p3 = j + 3 * LANES < end;
-            const int c0 = col[j];
-            const int c1 = p1 ? col[j + LANES] : 0;
-            const int c2 = p2 ? col[j + 2 * LANES] : 0;
-            const int c3 = p3 ? col[j + 3 * LANES] : 0;
-            const T v0 = val[j];
-            const T v1 = p1 ? val[j + LANES] : (T)0;
-            const T v2 = p2 ? val[j + 2 * LANES] : (T)0;
-            const T v3 = p3 ? val[j + 3 * LANES] : (T)0;
-            const T x0 = XLOAD(c0);
-            const T x1 = p1 ? XLOAD(c1) : (T)0;
-            const T x2 = p2 ? XLOAD(c2) : (T)0;
-            const T x3 = p3 ? XLOAD(c3) : (T)0;
-            sum += v0 * x0;
-            sum += v1 * x1;
-            sum += v2 * x2;
-            sum += v3 * x3;
+        // batches of NB predicated entries per lane: all col/val loads, then all x gathers, then the FMAs
+        // (the fused zero-guess op gathers two vectors per entry: 2-entry batches keep it at 32 registers)
+        constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
+        for (int j = start + lane; j < end; j += NB * LANES) {
+            bool p[NB];
+            int c[NB];
+            T v[NB], xv[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) p[k] = (k == 0) || (j + k * LANES < end);
+#pragma unroll
+            for (int k = 0; k < NB; k++) c[k] = p[k] ? col[j + k * LANES] : 0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) v[k] = p[k] ? val[j + k * LANES] : (T)0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) xv[k] = p[k] ? XLOAD(c[k]) : (T)0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) sum += v[k] * xv[k];
         }
     }
 #undef XLOAD
+#undef XOWN
     if (LANES > 1) sum = group_sum<LANES>(sum);
     double rr = 0.0;
-    if (valid && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
+    if (valid && lane == 0) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y, y2);
+    if (NORM) {
+        __shared__ double sm[32];
+        rr = block_sum(rr, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+    }
+}
+
+// Staged thread-per-row kernel for short rows (mean <= 12 entries: the fine-level operator, P).  A CTA owns 256
+// consecutive rows, i.e. ONE contiguous span of col/val: the span is copied to shared memory with fully
+// coalesced loads (8 + 8 independent loads per thread in flight, every sector requested once), then each
+// thread walks its own row out of shared memory (stride = row length: conflict-free for odd lengths).  The
+// plain thread-per-row kernel asks L1 for every 128-byte line of the span once per entry of a row (7x for
+// the 7-point operator, ncu: 4.3x the DRAM bytes through L1); here L1 only serves the gathers of x.
+constexpr int STAGE_CAP = 2048;      // entries per chunk: 24 KB of shared memory per CTA, 8 CTAs per SM
+
+template <typename T, int OP, bool NORM>
+__global__ void __launch_bounds__(ROW_THREADS, 8)
+csr_staged_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ val,
+                  const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *__restrict__ y,
+                  double *__restrict__ partial, int row0, T *__restrict__ y2) {
+    __shared__ int s_col[STAGE_CAP];
+    __shared__ T s_val[STAGE_CAP];
+    __shared__ int s_ptr[ROW_THREADS + 1];
+    const int t = threadIdx.x;
+    const long long first = (long long)blockIdx.x * ROW_THREADS;        // first row of this CTA, relative to row0
+    const int nr = (int)min((long long)ROW_THREADS, (long long)n - first);
+    const long long row = first + t + row0;
+    if (t <= nr) s_ptr[t] = rowptr[first + row0 + t];
+    if (t == 0) s_ptr[nr] = rowptr[first + row0 + nr];
+    __syncthreads();
+    const int beg = s_ptr[0], end = s_ptr[nr];
+    const bool valid = t < nr;
+    const int my_s = valid ? s_ptr[t] : 0, my_e = valid ? s_ptr[t + 1] : 0;
+    T sum = (T)0;
+    for (int base = beg; base < end; base += STAGE_CAP) {
+        const int cnt = min(STAGE_CAP, end - base);
+#pragma unroll
+        for (int k = 0; k < STAGE_CAP / ROW_THREADS; k++) {
+            const int e = t + k * ROW_THREADS;
+            if (e < cnt) s_col[e] = col[base + e];
+        }
+#pragma unroll
+        for (int k = 0; k < STAGE_CAP / ROW_THREADS; k++) {
+            const int e = t + k * ROW_THREADS;
+            if (e < cnt) s_val[e] = val[base + e];
+        }
+        __syncthreads();
+        const int js = max(my_s, base) - base, je = min(my_e, base + cnt) - base;
+        constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
+#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : x[(c)])
+        for (int j = js; j < je; j += NB) {
+            bool p[NB];
+            int c[NB];
+            T xv[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) p[k] = (k == 0) || (j + k < je);
+#pragma unroll
+            for (int k = 0; k < NB; k++) c[k] = p[k] ? s_col[j + k] : 0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) xv[k] = p[k] ? XOWN(c[k]) : (T)0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) sum += (p[k] ? s_val[j + k] : (T)0) * xv[k];
+        }
+#undef XOWN
+        if (base + STAGE_CAP < end) __syncthreads();
+    }
+    double rr = 0.0;
+    if (valid) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y, y2);
     if (NORM) {
         __shared__ double sm[32];
         rr = block_sum(rr, sm);
@@ -136,7 +212,7 @@ sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restric
         }
     }
     double rr = 0.0;
-    if (row < n) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y);
+    if (row < n) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y, (T *)nullptr);
     if (NORM) {
         __shared__ double sm[32];
         rr = block_sum(rr, sm);
@@ -144,33 +220,38 @@ sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restric
     }
 }
 
-static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic
+static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic, 0 = staged kernel
+// the heuristic never picks the staged kernel: measured at 256^3 it is slower than the plain thread-per-row
+// kernel (fine Jacobi sweep 436 vs 290 us, prolongation 252 vs 181 us — the two CTA barriers serialise the load
+// and gather phases and cost more memory-level parallelism than the single-touch loads save); kept as variant 0
+static int g_staged = 0;
 
 static int pick_lanes(int n, long long nnz) {
-    if (g_force_lanes > 0) return g_force_lanes;
+    if (g_force_lanes >= 0) return g_force_lanes;
     // ~8-12 entries per lane: enough independent loads per thread to cover HBM latency
     const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
     int lanes = 32;
-    if (mean <= 12.0) lanes = 1;
+    if (mean <= 12.0) lanes = (g_staged && (long long)n >= 148LL * 1024) ? 0 : 1;
     else if (mean <= 24.0) lanes = 2;
     else if (mean <= 48.0) lanes = 4;
     else if (mean <= 128.0) lanes = 8;
     else if (mean <= 384.0) lanes = 16;
     // small levels: not enough rows to fill 148 SMs -> spend more lanes per row (up to the row length)
-    while (lanes < 32 && (long long)n * lanes < 148LL * 1024 && 2.0 * lanes <= mean) lanes *= 2;
+    while (lanes > 0 && lanes < 32 && (long long)n * lanes < 148LL * 1024 && 2.0 * lanes <= mean) lanes *= 2;
     return lanes;
 }
 
 template <typename T, int OP, bool NORM>
 static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *x,
                         const T *b, const T *dw, T *y, double *norm2, cudaStream_t s, const int *row_order = nullptr,
-                        int row0 = 0, const HaloLL *halo = nullptr) {
+                        int row0 = 0, const HaloLL *halo = nullptr, T *y2 = nullptr) {
     if (n <= 0) {
         if (NORM && norm2) MLAMG_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double), s));
         return MLAMG_OK;
     }
-    const int lanes = pick_lanes(n, nnz_hint);
-    const unsigned blocks = cdiv((long long)n * lanes, ROW_THREADS);
+    int lanes = pick_lanes(n, nnz_hint);
+    if (lanes == 0 && (row_order || halo)) lanes = 1;      // the staged kernel walks a row RANGE without halo columns
+    const unsigned blocks = cdiv((long long)n * (lanes ? lanes : 1), ROW_THREADS);
     double *partial = nullptr;
     Scratch part(NORM ? (size_t)blocks * sizeof(double) : (size_t)-1, s);
     if (NORM) {
@@ -185,12 +266,15 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
     do {                                                                                                             \
         if (halo)                                                                                                    \
             csr_rowop_kernel<T, L, OP, false, true><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
-                                                                                  nullptr, row_order, row0, hl);     \
+                                                                                  nullptr, row_order, row0, hl, y2); \
         else                                                                                                         \
             csr_rowop_kernel<T, L, OP, NORM, false><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
-                                                                                   partial, row_order, row0, hl);    \
+                                                                                   partial, row_order, row0, hl, y2); \
     } while (0)
     switch (lanes) {
+        case 0:
+            csr_staged_kernel<T, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row0, y2);
+            break;
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
         case 4: LAUNCH(4); break;
@@ -300,6 +384,17 @@ int jacobi_t(int n, long long nnz, const int *rowptr, const int *col, const T *v
              const T *x_in, T *x_out, cudaStream_t s) {
     return launch_rowop<T, OP_JACOBI, false>(n, nnz, rowptr, col, val, x_in, b, dw, x_out, nullptr, s);
 }
+
+// x_out = dw .* b ; r = b - A x_out (+ *norm2 = ||r||^2): zero-guess first sweep fused with the residual
+template <typename T>
+int reszero_t(int n, long long nnz, const int *rowptr, const int *col, const T *val, const T *dw, const T *b, T *x_out,
+              T *r, double *norm2, cudaStream_t s) {
+    if (norm2)
+        return launch_rowop<T, OP_RESZERO, true>(n, nnz, rowptr, col, val, nullptr, b, dw, r, norm2, s, nullptr, 0, nullptr, x_out);
+    return launch_rowop<T, OP_RESZERO, false>(n, nnz, rowptr, col, val, nullptr, b, dw, r, nullptr, s, nullptr, 0, nullptr, x_out);
+}
+template int reszero_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, float *, float *, double *, cudaStream_t);
+template int reszero_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, double *, double *, double *, cudaStream_t);
 
 template int spmv_t<float>(int, long long, const int *, const int *, const float *, const float *, float *, cudaStream_t);
 template int spmv_t<double>(int, long long, const int *, const int *, const double *, const double *, double *, cudaStream_t);
@@ -458,6 +553,16 @@ int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *co
     return MLAMG_OK;
 }
 
+int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                                   const void *dw, const void *b, void *x_out, void *r, double *norm2, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "jacobi_zero_residual: n < 0");
+    if (x_out == r || b == x_out || b == r) return set_error(MLAMG_EINVAL, "jacobi_zero_residual: aliased arguments");
+    MLAMG_DISPATCH(dtype, return reszero_t<T>(n, nnz, rowptr, col, (const T *)val, (const T *)dw, (const T *)b, (T *)x_out,
+                                              (T *)r, norm2, s));
+    return MLAMG_OK;
+}
+
 int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream) {
     MLAMG_DISPATCH(dtype, return jacobi_zero_t<T>(n, (const T *)dw, (const T *)b, (T *)x, as_stream(stream)));
     return MLAMG_OK;
@@ -505,6 +610,11 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
             if (norm2) { ROWOP_CASE(OP_RESIDUAL, true); } else { ROWOP_CASE(OP_RESIDUAL, false); }
             break;
         case OP_JACOBI: ROWOP_CASE(OP_JACOBI, false); break;
+        case OP_RESZERO:       // x is the OUTPUT x = dw.*b here
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
+                                                                             (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                             row_begin, nullptr, (T *)const_cast<void *>(x))));
+            break;
         default: return set_error(MLAMG_EINVAL, "rowop: bad op %d", op);
     }
 #undef ROWOP_CASE
@@ -532,6 +642,11 @@ int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nn
         case OP_SPMV_ADD: ROWOP_CASE(OP_SPMV_ADD); break;
         case OP_RESIDUAL: ROWOP_CASE(OP_RESIDUAL); break;
         case OP_JACOBI: ROWOP_CASE(OP_JACOBI); break;
+        case OP_RESZERO:       // x is the OUTPUT x = dw.*b here; halo columns carry the neighbours' dw.*b
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
+                                                                             (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                             row_begin, &hl, (T *)const_cast<void *>(x))));
+            break;
         default: return set_error(MLAMG_EINVAL, "channel_rowop: bad op %d", op);
     }
 #undef ROWOP_CASE
@@ -548,8 +663,13 @@ int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, m
 }
 
 int mlamg_set_csr_lanes(int lanes) {
-    if (lanes != -1 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
-        return set_error(MLAMG_EINVAL, "set_csr_lanes: lanes must be -1 or a power of two <= 32");
+    if (lanes == -2 || lanes == -3) {      // -2 / -3: heuristic without / with the staged short-row kernel
+        g_force_lanes = -1;
+        g_staged = lanes == -3;
+        return MLAMG_OK;
+    }
+    if (lanes != -1 && lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return set_error(MLAMG_EINVAL, "set_csr_lanes: lanes must be -1 (heuristic), 0 (staged) or a power of two <= 32");
     g_force_lanes = lanes;
     return MLAMG_OK;
 }

@@ -24,6 +24,8 @@ template <typename T>
 int jacobi_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
 template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStream_t);
 template <typename T>
+int reszero_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
+template <typename T>
 int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
                  cudaStream_t);
 template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
@@ -113,10 +115,17 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
         const int pre_pp = zero ? (nu1 > 0 ? nu1 - 1 : 0) : nu1;
         const int total_pp = pre_pp + nu2;
         T *c;
+        bool fused = false;
         if (zero) {
             // first write goes where the final result lands in the home buffer after total_pp swaps
             c = (total_pp % 2 == 0) ? xa : xb;
-            if (nu1 > 0) MLAMG_TRY(jacobi_zero_t<T>(A.n, dw, rhs[l], c, s));
+            // V(1,*) from a zero guess: x = dw.*b and r = b - A x in ONE pass (x is never read back from HBM)
+            // only for short rows (thread-per-row kernel): with several lanes per row the doubled gathers make the
+            // kernel L1-bound (measured at 256^3, level 1, 30 entries/row: 70 us fused vs 56 us for the pair)
+            fused = (nu1 == 1) && !lev.sell_ptr && (double)A.nnz <= 12.0 * (double)A.n;
+            if (fused)
+                MLAMG_TRY(reszero_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, (T *)lev.r, nullptr, s));
+            else if (nu1 > 0) MLAMG_TRY(jacobi_zero_t<T>(A.n, dw, rhs[l], c, s));
             else MLAMG_CUDA(cudaMemsetAsync(c, 0, (size_t)A.n * sizeof(T), s));
         } else {
             c = xa;   // caller's iterate
@@ -127,7 +136,7 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             c = o;
         }
         cur[l] = c;
-        MLAMG_TRY(level_residual<T>(lev, rhs[l], c, (T *)lev.r, nullptr, s));
+        if (!fused) MLAMG_TRY(level_residual<T>(lev, rhs[l], c, (T *)lev.r, nullptr, s));
         const Csr &R = lev.R;
         T *bc = (T *)h->lv[l + 1].b;
         MLAMG_TRY(spmv_perm_t<T>(R.n, R.nnz, R.rowptr, R.col, (const T *)R.val, (const T *)lev.r, bc, lev.r_order, s));
@@ -347,8 +356,13 @@ double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int ze
         const double b_prolong = pnnz * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N;
         const bool zero = (l > 0) || zero_guess;
         double pre = nu1 * b_jac;
+        double res = b_res;
         if (zero && nu1 > 0) pre = (nu1 - 1) * b_jac + 3 * v * N;   // x = dw.*b : read dw,b write x
-        total += pre + nu2 * b_jac + b_res + b_restrict + b_prolong;
+        if (zero && nu1 == 1 && !lev.sell_ptr && nnz <= 12.0 * N) {   // fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
+            pre = 0.0;
+            res = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N;
+        }
+        total += pre + nu2 * b_jac + res + b_restrict + b_prolong;
     }
     const double nc = h->lv[L - 1].A.n;
     total += nc * nc * v + 2 * nc * v;   // dense inverse GEMV

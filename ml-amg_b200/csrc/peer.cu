@@ -26,7 +26,8 @@ constexpr int PEER_THREADS = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(PEER_THREADS)
-channel_push_kernel(const ChannelDev ch, const int *__restrict__ send_idx, const T *__restrict__ src) {
+channel_push_kernel(const ChannelDev ch, const int *__restrict__ send_idx, const T *__restrict__ src,
+                    const T *__restrict__ scale) {
     const unsigned long long seq = *(volatile unsigned long long *)ch.state + 1ull;
     const int par = (int)(seq & 1ull);
     const unsigned tag = ll_tag(seq);
@@ -35,7 +36,8 @@ channel_push_kernel(const ChannelDev ch, const int *__restrict__ send_idx, const
         int p = 0;
         while (p + 1 < ch.n_send_peers && i >= ch.send_start[p + 1]) p++;
         const int j = send_idx ? send_idx[i] : (int)i;
-        const T v = j >= 0 ? src[j] : (T)0;             // negative index: padding slot (keeps two ranks in step)
+        T v = j >= 0 ? src[j] : (T)0;                   // negative index: padding slot (keeps two ranks in step)
+        if (scale && j >= 0) v = scale[j] * v;          // x = dw .* b sent without materialising x first
         ll_store(reinterpret_cast<T *>(ch.send_dst[par][p]), i - ch.send_start[p], v, tag);
     }
     __syncthreads();
@@ -145,7 +147,8 @@ int mlamg_channel_destroy(mlamg_channel_t ch) {
     return MLAMG_OK;
 }
 
-int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src, mlamg_stream_t stream) {
+int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const void *src, const void *scale,
+                       mlamg_stream_t stream) {
     if (!ch) return set_error(MLAMG_EINVAL, "channel_push: null channel");
     const ChannelDev &d = ch->dev;
     if (d.n_send == 0 && d.n_recv == 0) return MLAMG_OK;
@@ -153,7 +156,7 @@ int mlamg_channel_push(mlamg_channel_t ch, int dtype, const int *send_idx, const
     // always launched on a live channel: it advances the sequence number even with nothing to send
     unsigned blocks = d.n_send > 0 ? cdiv(d.n_send, 2 * PEER_THREADS) : 1u;
     if (blocks > 148u) blocks = 148u;
-    MLAMG_DISPATCH(dtype, (channel_push_kernel<T><<<blocks, PEER_THREADS, 0, s>>>(d, send_idx, (const T *)src)));
+    MLAMG_DISPATCH(dtype, (channel_push_kernel<T><<<blocks, PEER_THREADS, 0, s>>>(d, send_idx, (const T *)src, (const T *)scale)));
     MLAMG_LAUNCHED();
     return MLAMG_OK;
 }

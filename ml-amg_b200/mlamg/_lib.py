@@ -29,6 +29,7 @@ SIGNATURES = {
     "mlamg_residual_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_csr": (I, [I, I, I, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_zero": (I, [I, I, P, P, P, P]),
+    "mlamg_jacobi_zero_residual_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_smoother_diag": (I, [I, I, D, I, P, P, P, P, P]),
     "mlamg_sell_slice_ptr": (I, [I, P, P, P, P]),
     "mlamg_sell_fill": (I, [I, I, P, P, P, P, P, P, P]),
@@ -81,7 +82,7 @@ SIGNATURES = {
     "mlamg_channel_slot_bytes": (I, [I]),
     "mlamg_channel_create": (I, [I, P, P, P, I, P, P, P, P]),
     "mlamg_channel_destroy": (I, [P]),
-    "mlamg_channel_push": (I, [P, I, P, P, P]),
+    "mlamg_channel_push": (I, [P, I, P, P, P, P]),
     "mlamg_channel_unpack": (I, [P, I, P, P, P]),
     "mlamg_channel_rowop": (I, [P, I, I, I, I, P, P, P, P, I, P, P, P, P, I, P]),
 }

@@ -225,8 +225,8 @@ def spmv_perm(A, x, row_order, out=None):
 
 
 def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None):
-    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax)) over all rows, the int32 list `rows`,
-    or the contiguous range row_range=(begin, end)"""
+    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 x=dw.*b (x is WRITTEN), y=b-Ax) over all
+    rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
     begin = 0
     if rows is not None:
         n = rows.numel()
@@ -270,6 +270,21 @@ def jacobi_sweep(A, dw, b, x_in, x_out=None):
     check(lib.mlamg_jacobi_csr(dt(A.val), n, A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(dw), ptr(b), ptr(x_in),
                                ptr(x_out), stream()))
     return x_out
+
+
+def jacobi_zero_residual(A, dw, b, x_out=None, r_out=None, norm=False):
+    """x = dw .* b and r = b - A x in one pass over A (first zero-guess sweep fused with the residual)."""
+    n = A.shape[0]
+    if x_out is None:
+        x_out = torch.empty_like(b)
+    if r_out is None:
+        r_out = torch.empty_like(b)
+    nrm = torch.zeros(1, dtype=torch.float64, device=b.device) if norm else None
+    check(lib.mlamg_jacobi_zero_residual_csr(dt(A.val), n, A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(dw), ptr(b),
+                                             ptr(x_out), ptr(r_out), ptr(nrm), stream()))
+    if norm:
+        return x_out, r_out, float(nrm.sqrt().item())
+    return x_out, r_out
 
 
 def jacobi_zero(dw, b, out=None):

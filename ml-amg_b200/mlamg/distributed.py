@@ -278,9 +278,10 @@ class Channel:
     def __init__(self, handle, send_idx, state, n_recv, name):
         self._h, self.send_idx, self.state, self.n_recv, self.name = handle, send_idx, state, n_recv, name
 
-    def push(self, src):
-        """pack src[send_idx] into the peers' regions (tagged values) and advance the sequence number"""
-        check(lib.mlamg_channel_push(self._h, core.dt(src), core.ptr(self.send_idx), core.ptr(src), core.stream()))
+    def push(self, src, scale=None):
+        """pack src[send_idx] (.* scale[send_idx]) into the peers' regions (tagged values), advance the sequence number"""
+        check(lib.mlamg_channel_push(self._h, core.dt(src), core.ptr(self.send_idx), core.ptr(src), core.ptr(scale),
+                                     core.stream()))
 
     def unpack(self, dst, dst_idx=None):
         """after push: wait for every slot and copy it to dst (optionally through an index map)"""
@@ -481,7 +482,10 @@ class DistOperator:
             return
         if chan is not None:
             n_own = self.n_cols_own
-            chan.push(x_ext)
+            if op == 4:                # x = dw.*b is produced by this very pass: the neighbours get dw.*b directly
+                chan.push(b, scale=dw)
+            else:
+                chan.push(x_ext)
             split = overlap and self.peer_split_ok
             if split:
                 if self.interior_range is not None:
@@ -489,12 +493,14 @@ class DistOperator:
                 else:
                     self.rowop(op, x_ext, y, b, dw, rows=self.interior)
             rows = self.boundary if split else None
-            if PEER_INPLACE:
+            if PEER_INPLACE or op == 4:
                 chan.rowop(self.csr, op, x_ext, n_own, y, b=b, dw=dw, rows=rows)
             else:
                 chan.unpack(x_ext[n_own:n_own + plan.n_halo])
                 self.rowop(op, x_ext, y, b, dw, rows=rows)
             return
+        if op == 4:
+            raise ValueError("the fused zero-guess sweep + residual needs the peer transport (halo columns of b, dw)")
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
             self.rowop(op, x_ext, y, b, dw)
@@ -740,7 +746,10 @@ class DistHierarchy:
             xa, xb = L.x
             n = L.n
             c = xa
-            if nu1 > 0:
+            fused = nu1 == 1 and (chans is not None or comm.world == 1) and L.A.csr.nnz <= 12 * n    # short rows only
+            if fused:      # x = dw.*b and r = b - A x in one pass over A (x is never read back)
+                L.A.apply(4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
+            elif nu1 > 0:
                 core.jacobi_zero(L.dw, rhs, c[:n])
             else:
                 c[:n].zero_()
@@ -748,7 +757,8 @@ class DistHierarchy:
                 o = xb if c is xa else xa
                 L.A.apply(3, c, o, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "pre", k))
                 c = o
-            L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))   # r[:n] = b - A x
+            if not fused:
+                L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))   # r[:n] = b - A x
             nxt_b = self.levels[l + 1].b if l + 1 < len(self.levels) else None
             if nxt_b is None:
                 nxt_b = self._tail_local_b()

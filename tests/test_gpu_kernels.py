@@ -61,6 +61,14 @@ def test_spmv_residual_jacobi(name, dtype):
         xn = mlamg.jacobi_sweep(Ad, dev(dw, dtype), bd, xd)
         close(xn, x + dw * (b - A @ x), dtype, scale + np.abs(b).max())
         close(mlamg.jacobi_zero(dev(dw, dtype), bd), dw * b, dtype)
+        # first zero-guess sweep fused with the residual: same x bit for bit, r = b - A x, deterministic norm
+        x0 = mlamg.jacobi_zero(dev(dw, dtype), bd)
+        xf, rf, nrm = mlamg.jacobi_zero_residual(Ad, dev(dw, dtype), bd, norm=True)
+        assert torch.equal(xf, x0)
+        assert torch.equal(rf, mlamg.residual(Ad, x0, bd))
+        xr = (dw * b).astype(dtype)
+        close(rf, b - A @ xr, dtype, (abs(A) @ np.abs(xr)).max() + np.abs(b).max())
+        assert abs(nrm - np.linalg.norm((b - A @ xr).astype(np.float64))) <= 10 * TOL[dtype] * max(nrm, 1e-30)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -247,17 +255,43 @@ def test_sell32_rowops(name, dtype):
         close(S.jacobi_sweep(dwd, bd, xd), x + dw * (b - A @ x), dtype, scale)
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, 16, 32])
 def test_csr_lane_variants(lanes):
+    """every threads-per-row variant (0 = staged shared-memory kernel, incl. rows longer than one staging chunk)"""
     import mlamg
+    from mlamg import core
     try:
         mlamg.set_csr_lanes(lanes)
-        for name in ("poisson3d", "random_dense_rows", "single_row"):
-            A = MATS[name]()
+        cases = [MATS[k]() for k in ("poisson3d", "random_dense_rows", "single_row")]
+        cases.append(oml.poisson((40, 30, 3)))                           # 3600 rows: several CTAs, one chunk each
+        cases.append(sp.vstack([random_csr(3, 5000, 0.9, 7), random_csr(600, 5000, 0.002, 8, empty_rows=True),
+                                random_csr(2, 5000, 0.6, 9)]).tocsr())   # rows of ~4500 entries: multi-chunk staging
+        for A in cases:
             rs = np.random.RandomState(1)
-            x = rs.randn(A.shape[1])
-            y = mlamg.spmv(mlamg.DeviceCSR.from_scipy(A), dev(x, np.float64))
-            close(y, A @ x, np.float64, (abs(A) @ np.abs(x)).max())
+            n, m = A.shape
+            x, b, dw, y0 = rs.randn(m), rs.randn(n), rs.rand(n), rs.randn(n)
+            Ad = mlamg.DeviceCSR.from_scipy(A)
+            scale = (abs(A) @ np.abs(x)).max() + np.abs(b).max() + np.abs(y0).max()
+            close(mlamg.spmv(Ad, dev(x, np.float64)), A @ x, np.float64, scale)
+            r, nrm = mlamg.residual(Ad, dev(x, np.float64), dev(b, np.float64), norm=True)
+            close(r, b - A @ x, np.float64, scale)
+            assert abs(nrm - np.linalg.norm(b - A @ x)) <= 1e-12 * nrm
+            yd = dev(y0, np.float64)
+            mlamg.spmv_add(Ad, dev(x, np.float64), yd)
+            close(yd, y0 + A @ x, np.float64, scale)
+            if n == m:
+                close(mlamg.jacobi_sweep(Ad, dev(dw, np.float64), dev(b, np.float64), dev(x, np.float64)),
+                      x + dw * (b - A @ x), np.float64, scale)
+                xf, rf = mlamg.jacobi_zero_residual(Ad, dev(dw, np.float64), dev(b, np.float64))
+                close(xf, dw * b, np.float64)
+                close(rf, b - A @ (dw * b), np.float64, scale)
+                # a row range that starts inside the matrix (multi-GPU interior rows)
+                lo, hi = n // 5, n - n // 7
+                yd = dev(y0, np.float64)
+                core.rowop(Ad, 3, dev(x, np.float64), yd, b=dev(b, np.float64), dw=dev(dw, np.float64), row_range=(lo, hi))
+                ref = y0.copy()
+                ref[lo:hi] = (x + dw * (b - A @ x))[lo:hi]
+                close(yd, ref, np.float64, scale)
     finally:
         mlamg.set_csr_lanes(-1)
 
@@ -273,7 +307,7 @@ def test_spmv_row_order_is_result_invariant():
     assert torch.equal(y0, y1)
 
 
-@pytest.mark.parametrize("op", [0, 1, 2, 3])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4])
 def test_rowop_on_row_subset(op):
     """interior / boundary splits of the multi-GPU levels: only the listed rows are touched"""
     from mlamg import core
@@ -285,8 +319,13 @@ def test_rowop_on_row_subset(op):
     rows = np.sort(rs.permutation(n)[: n // 3]).astype(np.int32)      # includes rows > len(rows)
     Ad = mlamg.DeviceCSR.from_scipy(A)
     yd = dev(y0, np.float64)
-    core.rowop(Ad, op, dev(x, np.float64), yd, b=dev(b, np.float64), dw=dev(dw, np.float64), rows=torch.from_numpy(rows).cuda())
-    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x)}[op]
+    xd = dev(x, np.float64)
+    core.rowop(Ad, op, xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64), rows=torch.from_numpy(rows).cuda())
+    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b)}[op]
+    if op == 4:          # x is an output here: the listed rows receive dw.*b, the others keep their content
+        xr = x.copy()
+        xr[rows] = (dw * b)[rows]
+        assert np.array_equal(xd.cpu().numpy(), xr)
     ref = y0.copy()
     ref[rows] = full[rows]
     got = yd.cpu().numpy()
