@@ -293,12 +293,14 @@ class Hierarchy:
 
 def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
                     P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
-                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never"):
+                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never", fallback=None):
     """Build the multilevel hierarchy on the device.
 
     A           : scipy / torch sparse / DeviceCSR
     aggregates  : 'lloyd' (Lloyd clustering per level, reference seeding) or a list of
                   (labels, ncoarse) per level (learned / external aggregates)
+    fallback    : None -> stop coarsening when the list of external aggregates is exhausted;
+                  'lloyd' -> continue with Lloyd + smoothed aggregation below the learned levels
     P_hat       : optional list of per-level weights on A_l's pattern (learned P = P_hat Agg)
     lam_max     : |lambda_max(D^-1 A)| per level: None -> on-device power iteration; float, list or
                   callable(DeviceCSR) -> supplied (parity runs pass the oracle's value)
@@ -313,8 +315,8 @@ def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxite
         n = A.shape[0]
         if len(levels) >= max_levels or n <= max_coarse:
             break
-        if isinstance(aggregates, str):
-            if aggregates != "lloyd":
+        if isinstance(aggregates, str) or (lvl >= len(aggregates) and fallback == "lloyd"):
+            if isinstance(aggregates, str) and aggregates != "lloyd":
                 raise ValueError(f"unknown aggregation strategy {aggregates!r}")
             labels, nc, roots, seeds = lloyd_labels(A, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand)
             L.roots, L.seeds = roots, seeds

@@ -1,0 +1,150 @@
+"""Synthetic problem generators for the named benchmark shapes (host side, numpy/scipy; NOT on the hot path).
+
+The reference builds its datasets with pygmsh meshes and `pyamg.gallery.fem.gradgradform`
+(ns/model/data.py:349-394, utils/create_data.py:69-78, demos/voronoi_jump_disc.py:10-22); neither pygmsh nor
+pyamg exists here, so the same *shapes* are generated directly:
+
+  * P1 (linear triangle) stiffness matrix  a(u,v) = int kappa grad u . grad v  with one kappa per element
+    (evaluated at the centroid, as gradgradform does), Dirichlet boundary rows/columns removed;
+  * kappa piecewise constant on the Voronoi cells of Ns in {2,3} seeds, 10^U(-4,4) re-drawn until the
+    spread exceeds 1e3 (the reference's 'jump' dataset);
+  * structured-triangle and Delaunay meshes, Morton (Z-curve) ordering so that contiguous row blocks are
+    spatially compact (the row partition of the multi-GPU levels);
+  * stand-ins for the GNN outputs of FullAggNet.forward (agg_interp.py:459-481): centres = top-k of a random
+    score, Bellman-Ford weights and P_hat weights = relu(N(0,1)) in float32 on A's pattern, torch.manual_seed.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+
+# ------------------------------------------------------------------------------------------ meshes
+def structured_triangles(nx, ny):
+    """(nx+1) x (ny+1) points on [0,1]^2, two triangles per cell.  -> (pts float64[n,2], tris int64[m,3], boundary mask)"""
+    xs, ys = np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    pts = np.column_stack([X.ravel(), Y.ravel()])
+    idx = np.arange((nx + 1) * (ny + 1), dtype=np.int64).reshape(ny + 1, nx + 1)
+    a, b_, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    tris = np.concatenate([np.column_stack([a, b_, d]), np.column_stack([a, d, c])])
+    bnd = np.zeros(pts.shape[0], dtype=bool)
+    bnd[idx[0, :]] = bnd[idx[-1, :]] = bnd[idx[:, 0]] = bnd[idx[:, -1]] = True
+    return pts, tris, bnd
+
+
+def delaunay_triangles(npts, seed=0):
+    """Delaunay triangulation of npts uniform random points in [0,1]^2; the convex-hull vertices are the
+    Dirichlet boundary.  -> (pts, tris, boundary mask)"""
+    from scipy.spatial import Delaunay
+    rs = np.random.RandomState(seed)
+    pts = rs.uniform(0.0, 1.0, size=(int(npts), 2))
+    tri = Delaunay(pts)
+    bnd = np.zeros(pts.shape[0], dtype=bool)
+    bnd[np.unique(tri.convex_hull)] = True
+    return pts, tri.simplices.astype(np.int64), bnd
+
+
+def morton_order(pts, bits=16):
+    """permutation sorting 2-D points along the Z-curve"""
+    q = np.clip((pts * (1 << bits)).astype(np.uint64), 0, (1 << bits) - 1)
+
+    def spread(v):
+        v = (v | (v << 16)) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << 8)) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << 2)) & np.uint64(0x3333333333333333)
+        v = (v | (v << 1)) & np.uint64(0x5555555555555555)
+        return v
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return np.argsort(key, kind="stable")
+
+
+# ------------------------------------------------------------------------------------------ coefficients
+def voronoi_jump_kappa(centroids, rng, n_seeds=None):
+    """piecewise-constant diffusion on the Voronoi cells of 2 or 3 random seeds (utils/create_data.py:69-78).
+    -> (kappa per centroid, jumps array [x, y, d])"""
+    ns = int(rng.choice([2, 3])) if n_seeds is None else int(n_seeds)
+    S = rng.uniform(0.0, 1.0, (ns, 2))
+    while True:
+        D = 10.0 ** rng.uniform(-4.0, 4.0, ns)
+        if np.ptp(D) > 1e3:
+            break
+    d2 = ((centroids[:, None, :] - S[None, :, :]) ** 2).sum(axis=2)
+    return D[np.argmin(d2, axis=1)], np.column_stack([S, D])
+
+
+# ------------------------------------------------------------------------------------------ assembly
+def p1_stiffness(pts, tris, kappa=None):
+    """P1 stiffness matrix (all nodes), kappa: None (Laplacian) or one value per triangle."""
+    p0, p1, p2 = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
+    # gradients of the barycentric functions: g_i = rot90(edge opposite to i) / (2 area)
+    e0, e1, e2 = p2 - p1, p0 - p2, p1 - p0
+    area2 = e2[:, 0] * (-e1[:, 1]) - e2[:, 1] * (-e1[:, 0])          # 2 * signed area = cross(p1-p0, p2-p0)
+    scale = (1.0 if kappa is None else np.asarray(kappa, dtype=np.float64)) / (2.0 * np.abs(area2))
+    E = [e0, e1, e2]
+    rows, cols, vals = [], [], []
+    for i in range(3):
+        for j in range(3):
+            rows.append(tris[:, i])
+            cols.append(tris[:, j])
+            vals.append(scale * (E[i][:, 0] * E[j][:, 0] + E[i][:, 1] * E[j][:, 1]))
+    n = pts.shape[0]
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+def remove_dirichlet(A, pts, bnd):
+    """drop boundary rows/columns (R A R^T of data.py:384-390) and exact zeros"""
+    keep = np.nonzero(~bnd)[0]
+    Ad = sp.csr_matrix(A[keep][:, keep])
+    Ad.eliminate_zeros()
+    Ad.sort_indices()
+    return Ad, pts[keep]
+
+
+def voronoi_jump_problem(n_side=64, seed=0, mesh="structured", npts=None, n_seeds=None):
+    """2-D jump-coefficient diffusion (BASELINE config 3 shape).  mesh: 'structured' (n_side x n_side cells) or
+    'delaunay' (npts random points).  Rows in Morton order.  -> (A csr float64, pts, jumps)"""
+    rng = np.random.RandomState(seed)
+    if mesh == "structured":
+        pts, tris, bnd = structured_triangles(n_side, n_side)
+    elif mesh == "delaunay":
+        pts, tris, bnd = delaunay_triangles(npts or n_side * n_side, seed)
+    else:
+        raise ValueError(f"unknown mesh {mesh!r}")
+    cent = (pts[tris[:, 0]] + pts[tris[:, 1]] + pts[tris[:, 2]]) / 3.0
+    kappa, jumps = voronoi_jump_kappa(cent, rng, n_seeds)
+    A, p = remove_dirichlet(p1_stiffness(pts, tris, kappa), pts, bnd)
+    order = morton_order(p)
+    A = sp.csr_matrix(A[order][:, order])
+    A.sort_indices()
+    return A, p[order], jumps
+
+
+def delaunay_laplacian(npts, seed=0):
+    """P1 Laplacian on a Delaunay mesh of npts random points, Dirichlet hull, Morton-ordered rows
+    (BASELINE config 4 shape: ~7 entries per row).  -> (A csr float64, pts)"""
+    pts, tris, bnd = delaunay_triangles(npts, seed)
+    A, p = remove_dirichlet(p1_stiffness(pts, tris, None), pts, bnd)
+    order = morton_order(p)
+    A = sp.csr_matrix(A[order][:, order])
+    A.sort_indices()
+    return A, p[order]
+
+
+# ------------------------------------------------------------------------------------------ GNN stand-ins
+def random_gnn_outputs(A, alpha=0.1, seed=0):
+    """Stand-ins for the three network outputs of FullAggNet.forward with the dtypes and supports the real nets
+    produce (agg_interp.py:459-481): top_k = sorted ids of the k = ceil(alpha m) best random scores (int64),
+    BF edge weights and P_hat edge weights = relu(N(0,1)) float32 on A's stored pattern (CSR order incl. the
+    diagonal, data.py:39-46).  torch.manual_seed(seed) makes them reproducible."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    m = A.shape[0]
+    k = int(np.ceil(alpha * m))
+    scores = torch.rand(m, generator=g)
+    top_k = torch.sort(torch.topk(scores, k).indices).values
+    bf = torch.relu(torch.randn(A.nnz, generator=g)).to(torch.float32)
+    ph = torch.relu(torch.randn(A.nnz, generator=g)).to(torch.float32)
+    return top_k.numpy().astype(np.int64), bf.numpy(), ph.numpy()

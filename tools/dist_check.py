@@ -18,7 +18,8 @@ import torch.distributed as dist
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    delaunay = len(sys.argv) > 1 and sys.argv[1] == "--delaunay"
+    n = int(sys.argv[2 if delaunay else 1]) if len(sys.argv) > (2 if delaunay else 1) else (4000 if delaunay else 12)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -31,14 +32,29 @@ def main():
     md.OVERLAP_MIN_NNZ = 0          # exercise the interior/boundary overlap path even on tiny levels
     md.PEER_SPLIT_MIN_NNZ = 0
     comm = md.Comm()
-    rowptr, col, val = md.poisson_slab(n, world, rank)
-    N_loc = n ** 3
-    offsets = [r * N_loc for r in range(world + 1)]
-    lam = [2.0, 1.9, 1.8, 1.7, 1.6]
-    kw = dict(ratio=0.06, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
-              replicate_below=max(60, N_loc * world // 40))
+    if delaunay:
+        # BASELINE config 4 shape: P1 Laplacian on a Delaunay mesh of n random points (Morton-ordered rows, ~7 entries
+        # per row), contiguous row blocks.  Every rank generates the same global matrix and keeps its rows.
+        from mlamg import problems
+        A, _ = problems.delaunay_laplacian(n, seed=0)
+        N = A.shape[0]
+        offsets = [int(round(r * N / world)) for r in range(world + 1)]
+        Al = A[offsets[rank]:offsets[rank + 1]]
+        rowptr = torch.from_numpy(Al.indptr.astype(np.int32)).cuda()
+        col = torch.from_numpy(Al.indices.astype(np.int32)).cuda()
+        val = torch.from_numpy(Al.data.copy()).cuda()
+        lam = [2.0, 1.9, 1.8, 1.7, 1.6]
+        kw = dict(ratio=0.08, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
+                  replicate_below=max(60, N // 20))
+    else:
+        rowptr, col, val = md.poisson_slab(n, world, rank)
+        N_loc = n ** 3
+        offsets = [r * N_loc for r in range(world + 1)]
+        lam = [2.0, 1.9, 1.8, 1.7, 1.6]
+        kw = dict(ratio=0.06, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
+                  replicate_below=max(60, N_loc * world // 40))
+        A = oml.poisson((n, n, n * world))
     H = md.DistHierarchy(rowptr, col, val, comm, **kw)
-    A = oml.poisson((n, n, n * world))
     ref, offs = oml.build_hierarchy_partitioned(A, offsets, **kw)
     ok = True
 
