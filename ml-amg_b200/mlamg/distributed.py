@@ -877,6 +877,8 @@ class DistHierarchy:
             b_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
             b_res = nnz * (v + 4) + 4 * (N + 1) + 3 * v * N
             pre = (nu1 - 1) * b_jac + 3 * v * N if nu1 > 0 else 0
+            if nu1 == 1 and nnz <= 12 * N and (self.halo == "peer" or self.comm.world == 1):
+                pre, b_res = 0, b_jac          # fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
             tot += pre + nu2 * b_jac + b_res + (pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc) + \
                 (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
         return tot + self.tail.cycle_bytes(nu1, nu2, True)

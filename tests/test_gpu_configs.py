@@ -46,7 +46,7 @@ def test_config2_poisson3d_128_setup_and_pcg_full_size():
                               max_coarse=1000, max_levels=8)
     assert len(H.levels) >= 3 and H.levels[0].A.shape[0] == n ** 3 and H.levels[0].A.nnz == 14581760
     lam_pi = mlamg.lambda_max(A, iters=200)
-    assert abs(lam_pi - exact) < 2e-3                # power iteration vs the analytic value
+    assert exact - 2e-2 < lam_pi <= exact + 1e-12    # power iteration approaches the analytic value from below
     # every aggregate index is used, every node is aggregated, Galerkin operators are symmetric
     lab = H.levels[0].labels
     nc = H.levels[1].A.shape[0]
@@ -142,7 +142,7 @@ def test_config3_voronoi_jump_4m_dof_properties():
     # the label is inherited along a shortest-path edge (a neighbour can be re-labelled later without the fp32 sum
     # changing, so this is required of all but a vanishing fraction of the nodes)
     attains = off & (cand == dist[rows]) & (labels[cols] == labels[rows])
-    has = torch.zeros(n, dtype=torch.bool, device="cuda").scatter_reduce(0, rows, attains, reduce="amax")
+    has = torch.zeros(n, dtype=torch.int32, device="cuda").scatter_reduce(0, rows, attains.to(torch.int32), reduce="amax")
     assert float(has[non_centre].float().mean()) > 0.9999, "labels do not follow shortest-path edges"
     # --- P = P_hat Agg: stored pattern = distinct neighbour labels per row, row sums preserved
     P_T, P = ai.learned_prolongator(Ad, ph, labels, k)
