@@ -72,6 +72,13 @@ int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *co
 int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                                    const void *dw, const void *b, void *x_out, void *r, double *norm2,
                                    mlamg_stream_t stream);
+/* x_out = x_in + dw .* r + Q e  (x_out may alias x_in): prolongation fused with the first post-smoothing sweep.
+ * With r = b - A x_in known (it was computed for the restriction),  (x_in + P e) followed by one sweep
+ * x + dw.*(b - A x)  equals  x_in + dw.*r + Q e  with  Q = (I - D_w A) P  built once at setup — one pass over Q
+ * replaces a pass over P and a pass over A.  (rowptr, col, val) is Q. */
+int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                             const void *e, const void *x_in, const void *r, const void *dw, void *x_out,
+                             mlamg_stream_t stream);
 /* x = dw .* b  (first sweep from a zero guess: no pass over A) */
 int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream);
 /* smoother diagonal: mode 0 -> omega / a_ii, mode 1 -> 1 / sum_j |a_ij| (omega ignored) */
@@ -88,17 +95,20 @@ int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *
                      const void *x, const void *b, const void *dw, void *y, double *norm2, mlamg_stream_t stream);
 /* generic row-op over the row range [row_begin, row_begin + nrows) (row_list == NULL) or the listed rows
  * row_list[0..nrows):
- * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax) | 4 x=dw.*b (x is an OUTPUT), y=b-Ax.
+ * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) (x unused) |
+ * 5 y=aux+dw.*b+Ax (aux may alias y).  aux is NULL for ops 0-3.
  * Used by the row-partitioned multi-GPU levels to run interior rows while the halo exchange of x is in
  * flight, then the boundary rows. */
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
-                    const void *x, const void *b, const void *dw, void *y, const int *row_list, int row_begin,
-                    double *norm2, mlamg_stream_t stream);
+                    const void *x, const void *b, const void *dw, void *y, void *aux, const int *row_list,
+                    int row_begin, double *norm2, mlamg_stream_t stream);
 /* halo pack: dst[i] = src[idx[i]] */
 int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, mlamg_stream_t stream);
 /* tuning hook: force the threads-per-row of the CSR kernels (1,2,4,8,16,32; 0 = staged shared-memory
  * thread-per-row kernel), -1 = heuristic; -2 / -3 = heuristic without / with the staged kernel */
 int mlamg_set_csr_lanes(int lanes);
+/* tuning hook: entries each lane keeps in flight per loop trip of the CSR kernels (2, 4, 8), 0 = default */
+int mlamg_set_csr_batch(int nb);
 /* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
 int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *val,
                    const void *X, void *Y, double alpha, double beta, mlamg_stream_t stream);
@@ -215,6 +225,11 @@ int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int 
 int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, const int *p_rowptr,
                                  const int *p_col, const void *p_val, const int *r_rowptr,
                                  const int *r_col, const void *r_val);
+/* optional Q = (I - D_w A) P of level l (rows n_l, columns n_{l+1}; D_w = diag(dw) of that level): when set, the
+ * prolongation and the first post-smoothing sweep run as one pass over Q (mlamg_prolong_smooth_csr).
+ * q_rowptr == NULL removes it. */
+int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz, const int *q_rowptr,
+                                      const int *q_col, const void *q_val);
 /* dense inverse of the coarsest operator (n x n row-major, in the hierarchy dtype) */
 int mlamg_hierarchy_set_coarse_inverse(mlamg_hierarchy_t h, const void *inv);
 /* allocate per-level work vectors (and the pinned staging buffers of the *_host entry points) */
@@ -281,7 +296,8 @@ int mlamg_channel_unpack(mlamg_channel_t ch, int dtype, const int *dst_idx, void
  * channel's receive region in place, waiting only for the values that have not landed yet */
 int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nnz_hint, const int *rowptr,
                         const int *col, const void *val, const void *x, int n_own, const void *b,
-                        const void *dw, void *y, const int *row_list, int row_begin, mlamg_stream_t stream);
+                        const void *dw, void *y, void *aux, const int *row_list, int row_begin,
+                        mlamg_stream_t stream);
 
 #ifdef __cplusplus
 }

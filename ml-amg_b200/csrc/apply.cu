@@ -12,13 +12,16 @@ namespace mlamg {
 
 // OP_RESZERO: first pre-smoothing sweep from a zero guess fused with the residual: x = dw.*b is never read back
 // from HBM — the gathers evaluate dw[c]*b[c] on the fly, the epilogue stores x[row] and r[row] = b[row] - (A x)[row]
-enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4 };
+// OP_PSMOOTH: prolongation fused with the first post-smoothing sweep.  With r = b - A x already known (it was
+// computed for the restriction), x + P e followed by one sweep equals  x + dw.*r + Q e,  Q = (I - D_w A) P
+// precomputed at setup: one pass over Q instead of a pass over P and a pass over A.
+enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4, OP_PSMOOTH = 5 };
 
 constexpr int ROW_THREADS = 256;
 
 template <typename T, int OP, bool NORM>
 __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__restrict__ x, const T *__restrict__ b,
-                                               const T *__restrict__ dw, T *__restrict__ y, T *__restrict__ y2) {
+                                               const T *__restrict__ dw, T *y, T *y2) {
     double rr = 0.0;
     if (OP == OP_SPMV) {
         y[row] = sum;
@@ -34,6 +37,8 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
         const T r = br - sum;
         y[row] = r;
         if (NORM) rr = (double)r * (double)r;
+    } else if (OP == OP_PSMOOTH) {   // y2 = x before the correction (may alias y), b = residual
+        y[row] = y2[row] + dw[row] * b[row] + sum;
     } else {  // OP_JACOBI
         y[row] = x[row] + dw[row] * (b[row] - sum);
     }
@@ -46,12 +51,12 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
 // hidden by memory-level parallelism, not by occupancy alone).  Segmented shuffle reduction.
 // HALO: columns >= halo.n_own are read in place from a peer channel's receive region (values written by the
 // neighbouring GPUs over NVLink, each carrying a sequence tag; the load spins on the few that have not landed).
-template <typename T, int LANES, int OP, bool NORM, bool HALO>
-__global__ void __launch_bounds__(ROW_THREADS, (LANES == 1 && !HALO) ? 8 : 6)
+template <typename T, int LANES, int OP, bool NORM, bool HALO, int NBT>
+__global__ void __launch_bounds__(ROW_THREADS, (LANES == 1 && !HALO && NBT <= 4) ? 8 : (NBT <= 4 ? 6 : 4))
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
-                 const T *__restrict__ dw, T *__restrict__ y, double *__restrict__ partial,
-                 const int *__restrict__ row_order, int row0, const HaloLL halo, T *__restrict__ y2) {
+                 const T *__restrict__ dw, T *y, double *__restrict__ partial,
+                 const int *__restrict__ row_order, int row0, const HaloLL halo, T *y2) {
     const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
     long long row = gtid / LANES;
     const int lane = threadIdx.x & (LANES - 1);
@@ -76,7 +81,7 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
         const int end = rowptr[row + 1];
         // batches of NB predicated entries per lane: all col/val loads, then all x gathers, then the FMAs
         // (the fused zero-guess op gathers two vectors per entry: 2-entry batches keep it at 32 registers)
-        constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
+        constexpr int NB = NBT;
         for (int j = start + lane; j < end; j += NB * LANES) {
             bool p[NB];
             int c[NB];
@@ -116,8 +121,8 @@ constexpr int STAGE_CAP = 2048;      // entries per chunk: 24 KB of shared memor
 template <typename T, int OP, bool NORM>
 __global__ void __launch_bounds__(ROW_THREADS, 8)
 csr_staged_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ val,
-                  const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *__restrict__ y,
-                  double *__restrict__ partial, int row0, T *__restrict__ y2) {
+                  const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *y,
+                  double *__restrict__ partial, int row0, T *y2) {
     __shared__ int s_col[STAGE_CAP];
     __shared__ T s_val[STAGE_CAP];
     __shared__ int s_ptr[ROW_THREADS + 1];
@@ -221,6 +226,7 @@ sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restric
 }
 
 static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic, 0 = staged kernel
+static int g_force_batch = 0;    // tuning hook (mlamg_set_csr_batch): entries per lane and loop trip (2, 4, 8), 0 = default
 // the heuristic never picks the staged kernel: measured at 256^3 it is slower than the plain thread-per-row
 // kernel (fine Jacobi sweep 436 vs 290 us, prolongation 252 vs 181 us — the two CTA barriers serialise the load
 // and gather phases and cost more memory-level parallelism than the single-touch loads save); kept as variant 0
@@ -262,14 +268,19 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
     memset(&hl, 0, sizeof(hl));
     if (halo) hl = *halo;
     if (halo && NORM) return set_error(MLAMG_EINVAL, "rowop: no norm on the in-place halo variant");
+    constexpr int NB_DEFAULT = (OP == OP_RESZERO) ? 2 : 4;
+    const int nb = (g_force_batch > 0 && !halo) ? g_force_batch : NB_DEFAULT;
+#define LAUNCH_NB(L, B)                                                                                              \
+    csr_rowop_kernel<T, L, OP, NORM, false, B><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y,      \
+                                                                              partial, row_order, row0, hl, y2)
 #define LAUNCH(L)                                                                                                    \
     do {                                                                                                             \
         if (halo)                                                                                                    \
-            csr_rowop_kernel<T, L, OP, false, true><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
-                                                                                  nullptr, row_order, row0, hl, y2); \
-        else                                                                                                         \
-            csr_rowop_kernel<T, L, OP, NORM, false><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, \
-                                                                                   partial, row_order, row0, hl, y2); \
+            csr_rowop_kernel<T, L, OP, false, true, NB_DEFAULT><<<blocks, ROW_THREADS, 0, s>>>(                      \
+                n, rowptr, col, val, x, b, dw, y, nullptr, row_order, row0, hl, y2);                                 \
+        else if (nb == 2) LAUNCH_NB(L, 2);                                                                           \
+        else if (nb == 8) LAUNCH_NB(L, 8);                                                                           \
+        else LAUNCH_NB(L, 4);                                                                                        \
     } while (0)
     switch (lanes) {
         case 0:
@@ -283,6 +294,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
         default: LAUNCH(32); break;
     }
 #undef LAUNCH
+#undef LAUNCH_NB
     MLAMG_LAUNCHED();
     if (NORM) return reduce_partials(partial, (int)blocks, norm2, s);
     return MLAMG_OK;
@@ -393,6 +405,16 @@ int reszero_t(int n, long long nnz, const int *rowptr, const int *col, const T *
         return launch_rowop<T, OP_RESZERO, true>(n, nnz, rowptr, col, val, nullptr, b, dw, r, norm2, s, nullptr, 0, nullptr, x_out);
     return launch_rowop<T, OP_RESZERO, false>(n, nnz, rowptr, col, val, nullptr, b, dw, r, nullptr, s, nullptr, 0, nullptr, x_out);
 }
+// x_out = x_in + dw .* r + Q e   (x_out may alias x_in)
+template <typename T>
+int psmooth_t(int n, long long nnz, const int *rowptr, const int *col, const T *val, const T *e, const T *x_in, const T *r,
+              const T *dw, T *x_out, cudaStream_t s) {
+    return launch_rowop<T, OP_PSMOOTH, false>(n, nnz, rowptr, col, val, e, r, dw, x_out, nullptr, s, nullptr, 0, nullptr,
+                                              const_cast<T *>(x_in));
+}
+template int psmooth_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
+template int psmooth_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
+
 template int reszero_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, float *, float *, double *, cudaStream_t);
 template int reszero_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, double *, double *, double *, cudaStream_t);
 
@@ -563,6 +585,16 @@ int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr,
     return MLAMG_OK;
 }
 
+int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val, const void *e,
+                             const void *x_in, const void *r, const void *dw, void *x_out, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "prolong_smooth: n < 0");
+    if (e == x_out || r == x_out) return set_error(MLAMG_EINVAL, "prolong_smooth: aliased arguments");
+    MLAMG_DISPATCH(dtype, return psmooth_t<T>(n, nnz, rowptr, col, (const T *)val, (const T *)e, (const T *)x_in, (const T *)r,
+                                              (const T *)dw, (T *)x_out, s));
+    return MLAMG_OK;
+}
+
 int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream) {
     MLAMG_DISPATCH(dtype, return jacobi_zero_t<T>(n, (const T *)dw, (const T *)b, (T *)x, as_stream(stream)));
     return MLAMG_OK;
@@ -595,11 +627,11 @@ int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, c
 // (row_list == NULL, nrows = n) or over the subset row_list[0..nrows) (interior / boundary splits of
 // the row-partitioned multi-GPU levels: interior rows run while the halo exchange is in flight).
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
-                    const void *x, const void *b, const void *dw, void *y, const int *row_list, int row_begin,
+                    const void *x, const void *b, const void *dw, void *y, void *aux, const int *row_list, int row_begin,
                     double *norm2, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
     if (nrows < 0) return set_error(MLAMG_EINVAL, "rowop: nrows < 0");
-    if (x == y) return set_error(MLAMG_EINVAL, "rowop: x aliases y");
+    if (x == y && x) return set_error(MLAMG_EINVAL, "rowop: x aliases y");
 #define ROWOP_CASE(OPC, NRM) \
     MLAMG_DISPATCH(dtype, return (launch_rowop<T, OPC, NRM>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x, \
                                                              (const T *)b, (const T *)dw, (T *)y, norm2, s, row_list, row_begin)))
@@ -610,10 +642,17 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
             if (norm2) { ROWOP_CASE(OP_RESIDUAL, true); } else { ROWOP_CASE(OP_RESIDUAL, false); }
             break;
         case OP_JACOBI: ROWOP_CASE(OP_JACOBI, false); break;
-        case OP_RESZERO:       // x is the OUTPUT x = dw.*b here
+        case OP_RESZERO:       // aux = x_out (x = dw.*b is produced, not read)
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "rowop: op 4 needs aux = x_out");
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
-                                                                             row_begin, nullptr, (T *)const_cast<void *>(x))));
+                                                                             row_begin, nullptr, (T *)aux)));
+            break;
+        case OP_PSMOOTH:       // aux = x_in (may alias y); x = coarse correction, b = residual
+            if (!aux) return set_error(MLAMG_EINVAL, "rowop: op 5 needs aux = x_in");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
+                                                                             (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                             row_begin, nullptr, (T *)aux)));
             break;
         default: return set_error(MLAMG_EINVAL, "rowop: bad op %d", op);
     }
@@ -623,7 +662,7 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
 
 // row-op whose gathers of columns >= n_own read the channel's receive region in place (csrc/peer.cu)
 int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col,
-                        const void *val, const void *x, int n_own, const void *b, const void *dw, void *y,
+                        const void *val, const void *x, int n_own, const void *b, const void *dw, void *y, void *aux,
                         const int *row_list, int row_begin, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
     if (!ch) return set_error(MLAMG_EINVAL, "channel_rowop: null channel");
@@ -642,10 +681,17 @@ int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nn
         case OP_SPMV_ADD: ROWOP_CASE(OP_SPMV_ADD); break;
         case OP_RESIDUAL: ROWOP_CASE(OP_RESIDUAL); break;
         case OP_JACOBI: ROWOP_CASE(OP_JACOBI); break;
-        case OP_RESZERO:       // x is the OUTPUT x = dw.*b here; halo columns carry the neighbours' dw.*b
+        case OP_RESZERO:       // aux = x_out; halo columns carry the neighbours' dw.*b
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "channel_rowop: op 4 needs aux = x_out");
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
-                                                                             row_begin, &hl, (T *)const_cast<void *>(x))));
+                                                                             row_begin, &hl, (T *)aux)));
+            break;
+        case OP_PSMOOTH:       // aux = x_in (may alias y)
+            if (!aux) return set_error(MLAMG_EINVAL, "channel_rowop: op 5 needs aux = x_in");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
+                                                                             (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                             row_begin, &hl, (T *)aux)));
             break;
         default: return set_error(MLAMG_EINVAL, "channel_rowop: bad op %d", op);
     }
@@ -659,6 +705,12 @@ int mlamg_gather(int dtype, int n, const int *idx, const void *src, void *dst, m
     unsigned blocks = cdiv(n, 256);
     MLAMG_DISPATCH(dtype, (gather_kernel<T><<<blocks, 256, 0, s>>>(n, idx, (const T *)src, (T *)dst)));
     MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_set_csr_batch(int nb) {
+    if (nb != 0 && nb != 2 && nb != 4 && nb != 8) return set_error(MLAMG_EINVAL, "set_csr_batch: 0, 2, 4 or 8");
+    g_force_batch = nb;
     return MLAMG_OK;
 }
 

@@ -26,6 +26,8 @@ template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStre
 template <typename T>
 int reszero_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
 template <typename T>
+int psmooth_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
+template <typename T>
 int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
                  cudaStream_t);
 template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
@@ -40,6 +42,8 @@ struct Csr {
 
 struct LevelData {
     Csr A, P, R;
+    Csr Q;                                                  // optional (I - D_w A) P: prolongation fused with the first post sweep
+    bool has_Q = false;
     const void *dw = nullptr;
     const int *r_order = nullptr;                           // optional processing order of the rows of R
     const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A
@@ -155,8 +159,20 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
         T *xa = (l == 0) ? x : (T *)lev.x;
         T *xb = (T *)lev.tmp;
         T *c = cur[l];
-        MLAMG_TRY(spmv_add_t<T>(P.n, P.nnz, P.rowptr, P.col, (const T *)P.val, cur[l + 1], c, s));
-        for (int k = 0; k < nu2; k++) {
+        int k0 = 0;
+        if (lev.has_Q && nu2 > 0) {
+            // x + P e followed by one sweep  ==  x + dw.*r + Q e  (r = b - A x is still in lev.r from the way down):
+            // one pass over Q instead of a pass over P and a pass over A
+            const Csr &Q = lev.Q;
+            T *o = (c == xa) ? xb : xa;
+            MLAMG_TRY(psmooth_t<T>(Q.n, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], c, (const T *)lev.r,
+                                   (const T *)lev.dw, o, s));
+            c = o;
+            k0 = 1;
+        } else {
+            MLAMG_TRY(spmv_add_t<T>(P.n, P.nnz, P.rowptr, P.col, (const T *)P.val, cur[l + 1], c, s));
+        }
+        for (int k = k0; k < nu2; k++) {
             T *o = (c == xa) ? xb : xa;
             MLAMG_TRY(level_jacobi<T>(lev, rhs[l], c, o, s));
             c = o;
@@ -281,6 +297,18 @@ int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, cons
     return MLAMG_OK;
 }
 
+int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz, const int *q_rowptr, const int *q_col,
+                                      const void *q_val) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level + 1 >= (int)h->lv.size()) return set_error(MLAMG_EINVAL, "set_post_operator: bad level");
+    LevelData &lev = h->lv[level];
+    if (!lev.has_A) return set_error(MLAMG_EINVAL, "set_post_operator: set the level operator first");
+    lev.Q.n = lev.A.n; lev.Q.nnz = q_nnz; lev.Q.rowptr = q_rowptr; lev.Q.col = q_col; lev.Q.val = q_val;
+    lev.has_Q = q_rowptr != nullptr;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return MLAMG_OK;
+}
+
 int mlamg_hierarchy_set_coarse_inverse(mlamg_hierarchy_t h, const void *inv) {
     MLAMG_TRY(check_handle(h));
     h->coarse_inv = inv;
@@ -362,7 +390,10 @@ double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int ze
             pre = 0.0;
             res = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N;
         }
-        total += pre + nu2 * b_jac + res + b_restrict + b_prolong;
+        double post = nu2 * b_jac + b_prolong;
+        if (lev.has_Q && nu2 > 0)     // fused prolongation + first post sweep: read Q, e, x, r, dw; write x
+            post = (nu2 - 1) * b_jac + (double)lev.Q.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N;
+        total += pre + post + res + b_restrict;
     }
     const double nc = h->lv[L - 1].A.n;
     total += nc * nc * v + 2 * nc * v;   // dense inverse GEMV

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mlamg_sell_fill": (I, [I, I, P, P, P, P, P, P, P]),
     "mlamg_sell_rowop": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_set_csr_lanes": (I, [I]),
+    "mlamg_set_csr_batch": (I, [I]),
     "mlamg_hierarchy_set_operator_sell": (I, [P, I, P, P, P]),
     "mlamg_spmm_csr": (I, [I, I, I, P, P, P, P, P, D, D, P]),
     "mlamg_axpby": (I, [I, I, D, P, D, P, P]),
@@ -58,7 +59,8 @@ SIGNATURES = {
     "mlamg_poisson_nnz": (LL, [I, I, I]),
     "mlamg_poisson_csr": (I, [I, I, I, I, P, P, P, P]),
     "mlamg_poisson_csr_slab": (I, [I, I, I, I, I, I, P, P, P, P, P]),
-    "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, I, P, P]),
+    "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P]),
+    "mlamg_prolong_smooth_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_gather": (I, [I, I, P, P, P, P]),
     "mlamg_bellman_ford": (I, [I, I, P, P, P, I, P, P, P, P, P]),
     "mlamg_lloyd_cluster": (I, [I, I, P, P, P, I, P, I, P, P, P, P]),
@@ -66,6 +68,7 @@ SIGNATURES = {
     "mlamg_hierarchy_create": (I, [I, I, P]),
     "mlamg_hierarchy_set_operator": (I, [P, I, I, I, P, P, P, P]),
     "mlamg_hierarchy_set_transfer": (I, [P, I, I, P, P, P, P, P, P]),
+    "mlamg_hierarchy_set_post_operator": (I, [P, I, I, P, P, P]),
     "mlamg_hierarchy_set_coarse_inverse": (I, [P, P]),
     "mlamg_hierarchy_finalize": (I, [P, P]),
     "mlamg_hierarchy_destroy": (I, [P]),
@@ -84,7 +87,7 @@ SIGNATURES = {
     "mlamg_channel_destroy": (I, [P]),
     "mlamg_channel_push": (I, [P, I, P, P, P, P]),
     "mlamg_channel_unpack": (I, [P, I, P, P, P]),
-    "mlamg_channel_rowop": (I, [P, I, I, I, I, P, P, P, P, I, P, P, P, P, I, P]),
+    "mlamg_channel_rowop": (I, [P, I, I, I, I, P, P, P, P, I, P, P, P, P, P, I, P]),
 }
 
 

@@ -203,6 +203,10 @@ def set_csr_lanes(lanes=-1):
     check(lib.mlamg_set_csr_lanes(int(lanes)))
 
 
+def set_csr_batch(nb=0):
+    check(lib.mlamg_set_csr_batch(int(nb)))
+
+
 # ------------------------------------------------------------------ V-cycle apply kernels
 def spmv(A, x, out=None):
     n, m = A.shape
@@ -224,9 +228,9 @@ def spmv_perm(A, x, row_order, out=None):
     return out
 
 
-def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None):
-    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 x=dw.*b (x is WRITTEN), y=b-Ax) over all
-    rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
+def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None, aux=None):
+    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) | 5 y=aux+dw.*b+Ax)
+    over all rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
     begin = 0
     if rows is not None:
         n = rows.numel()
@@ -237,8 +241,18 @@ def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None):
     if n <= 0:
         return y
     check(lib.mlamg_rowop_csr(dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))), ptr(A.rowptr), ptr(A.col),
-                              ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(rows), begin, None, stream()))
+                              ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(aux), ptr(rows), begin, None, stream()))
     return y
+
+
+def prolong_smooth(Q, e, x_in, r, dw, x_out=None):
+    """x_out = x_in + dw .* r + Q e (prolongation fused with the first post-smoothing sweep; x_out may be x_in)."""
+    n = Q.shape[0]
+    if x_out is None:
+        x_out = torch.empty_like(x_in)
+    check(lib.mlamg_prolong_smooth_csr(dt(Q.val), n, Q.nnz, ptr(Q.rowptr), ptr(Q.col), ptr(Q.val), ptr(e), ptr(x_in), ptr(r),
+                                       ptr(dw), ptr(x_out), stream()))
+    return x_out
 
 
 def spmv_add(A, x, y):

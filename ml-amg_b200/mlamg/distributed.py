@@ -289,7 +289,7 @@ class Channel:
         check(lib.mlamg_channel_unpack(self._h, core.dt(dst), core.ptr(dst_idx), ctypes.c_void_p(dst.data_ptr()),
                                        core.stream()))
 
-    def rowop(self, A, op, x_ext, n_own, y, b=None, dw=None, rows=None, row_range=None):
+    def rowop(self, A, op, x_ext, n_own, y, b=None, dw=None, rows=None, row_range=None, aux=None):
         """after push: core.rowop whose gathers of halo columns read the receive region in place"""
         begin = 0
         if rows is not None:
@@ -302,7 +302,8 @@ class Channel:
             return y
         check(lib.mlamg_channel_rowop(self._h, core.dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))),
                                       core.ptr(A.rowptr), core.ptr(A.col), core.ptr(A.val), core.ptr(x_ext), int(n_own),
-                                      core.ptr(b), core.ptr(dw), core.ptr(y), core.ptr(rows), begin, core.stream()))
+                                      core.ptr(b), core.ptr(dw), core.ptr(y), core.ptr(aux), core.ptr(rows), begin,
+                                      core.stream()))
         return y
 
 
@@ -465,45 +466,50 @@ class DistOperator:
         self.csr = hmod._permuted(self.csr, row_new2old, cmap)
         self._split_rows()
 
-    def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None):
-        core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range)
+    def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None, aux=None):
+        core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range, aux=aux)
 
     def channel_spec(self, name, dtype):
         """(name, send list, per-rank counts, dtype) of the halo exchange of this operator's input"""
         return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype)
 
-    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None):
+    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None, aux=None):
         """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange.
         chan: peer-memory channel (push -> interior rows -> boundary rows reading the halo in place from the
-        receive region; one stream, no collective); None: NCCL all-to-all on a side stream."""
+        receive region; one stream, no collective); None: NCCL all-to-all on a side stream.
+        op 4 (x = dw.*b, y = b - A x): x_ext is the OUTPUT x, the neighbours receive dw.*b directly.
+        op 5 (y = aux + dw.*b + A x_ext): aux = iterate before the correction, b = residual, x_ext = coarse correction."""
         plan = self.plan
+        xin = None if op == 4 else x_ext           # gather vector (op 4 evaluates dw[c]*b[c] instead)
+        if op == 4:
+            aux = x_ext
         if plan.comm.world == 1:
-            self.rowop(op, x_ext, y, b, dw)
+            self.rowop(op, xin, y, b, dw, aux=aux)
             return
         if chan is not None:
             n_own = self.n_cols_own
-            if op == 4:                # x = dw.*b is produced by this very pass: the neighbours get dw.*b directly
+            if op == 4:
                 chan.push(b, scale=dw)
             else:
                 chan.push(x_ext)
             split = overlap and self.peer_split_ok
             if split:
                 if self.interior_range is not None:
-                    self.rowop(op, x_ext, y, b, dw, row_range=self.interior_range)
+                    self.rowop(op, xin, y, b, dw, row_range=self.interior_range, aux=aux)
                 else:
-                    self.rowop(op, x_ext, y, b, dw, rows=self.interior)
+                    self.rowop(op, xin, y, b, dw, rows=self.interior, aux=aux)
             rows = self.boundary if split else None
             if PEER_INPLACE or op == 4:
-                chan.rowop(self.csr, op, x_ext, n_own, y, b=b, dw=dw, rows=rows)
+                chan.rowop(self.csr, op, xin, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             else:
                 chan.unpack(x_ext[n_own:n_own + plan.n_halo])
-                self.rowop(op, x_ext, y, b, dw, rows=rows)
+                self.rowop(op, xin, y, b, dw, rows=rows, aux=aux)
             return
         if op == 4:
             raise ValueError("the fused zero-guess sweep + residual needs the peer transport (halo columns of b, dw)")
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
-            self.rowop(op, x_ext, y, b, dw)
+            self.rowop(op, x_ext, y, b, dw, aux=aux)
             return
         main = torch.cuda.current_stream()
         comm_stream.wait_stream(main)
@@ -511,14 +517,14 @@ class DistOperator:
             plan.exchange(x_ext, self.n_cols_own)
         if self.interior_range is not None:
             i0, i1 = self.interior_range
-            self.rowop(op, x_ext, y, b, dw, row_range=(i0, i1))
+            self.rowop(op, x_ext, y, b, dw, row_range=(i0, i1), aux=aux)
             main.wait_stream(comm_stream)
-            self.rowop(op, x_ext, y, b, dw, row_range=(0, i0))
-            self.rowop(op, x_ext, y, b, dw, row_range=(i1, self.n_rows))
+            self.rowop(op, x_ext, y, b, dw, row_range=(0, i0), aux=aux)
+            self.rowop(op, x_ext, y, b, dw, row_range=(i1, self.n_rows), aux=aux)
         else:
-            self.rowop(op, x_ext, y, b, dw, rows=self.interior)
+            self.rowop(op, x_ext, y, b, dw, rows=self.interior, aux=aux)
             main.wait_stream(comm_stream)
-            self.rowop(op, x_ext, y, b, dw, rows=self.boundary)
+            self.rowop(op, x_ext, y, b, dw, rows=self.boundary, aux=aux)
 
 
 class DistLevel:
@@ -530,7 +536,7 @@ class DistHierarchy:
 
     def __init__(self, rowptr, col_global, val, comm=None, *, ratio=0.1, distance="unit", maxiter=10, rand=0,
                  lam_max=None, max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
-                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True, halo=None):
+                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True, halo=None, fuse_post=True):
         core.require_cuda()
         self.comm = comm or Comm()
         comm = self.comm
@@ -541,6 +547,8 @@ class DistHierarchy:
         if self.halo not in ("peer", "nccl"):
             raise ValueError("halo must be 'peer' or 'nccl'")
         self._chansets = {}
+        # Q = (I - D_w A) P per level: prolongation + first post-smoothing sweep as one pass (see Hierarchy)
+        self.fuse_post = bool(fuse_post)
         self.comm_stream = torch.cuda.Stream() if comm.world > 1 else None
         self.levels = []
         self.offsets = []
@@ -626,6 +634,13 @@ class DistHierarchy:
         L.P_global = Pg
         L.dw = core.smoother_diag(L.A.csr, smoother, jacobi_weight)
         L.nc = nc_local
+        L.Q = None
+        if self.fuse_post:
+            # rows of P for every column of my rows of A (owned + halo fine nodes), then Q = (I - D_w A) P
+            f_rp, f_col, f_val = fetch_rows(Pg.rowptr, Pg.col, Pg.val, offs, L.A.plan.halo_ids, comm)
+            e_rp, e_col, e_val = csr_vstack([(Pg.rowptr, Pg.col, Pg.val), (f_rp, f_col, f_val)])
+            Qg = hmod.post_operator(L.A.csr, core.DeviceCSR(e_rp, e_col, e_val, (L.A.n_ext, nc_glob)), L.dw)
+            L.Q = DistOperator(Qg.rowptr, Qg.col, Qg.val, nc_local, clo, coffs, comm)
         return L, (AH.rowptr, AH.col, AH.val), coffs
 
     def _renumber(self):
@@ -645,9 +660,13 @@ class DistHierarchy:
             inv = torch.empty_like(order)
             inv[order] = torch.arange(order.numel(), device=dev)
             Lf.P.renumber(None, inv)
+            if Lf.Q is not None:
+                Lf.Q.renumber(None, inv)
             Lf.R.renumber(order, None)
             Lc.A.renumber(order, inv)
             Lc.P.renumber(order, None)
+            if Lc.Q is not None:
+                Lc.Q.renumber(order, None)
             Lc.R.renumber(None, inv)
             Lc.dw = Lc.dw[order].contiguous()
             Lc.perm_new2old = order
@@ -677,7 +696,7 @@ class DistHierarchy:
             L.x = [torch.zeros(L.A.n_ext, dtype=dt_, device=dev) for _ in range(2)]
             L.b = torch.zeros(L.n, dtype=dt_, device=dev)
             L.r = torch.zeros(L.R.n_ext, dtype=dt_, device=dev)
-            L.e = torch.zeros(L.P.n_ext, dtype=dt_, device=dev)
+            L.e = torch.zeros(max(L.P.n_ext, L.Q.n_ext if L.Q is not None else 0), dtype=dt_, device=dev)
         n_tail = int(self.tail_offsets[-1])
         self.tail_b = torch.zeros(n_tail, dtype=dt_, device=dev)
         self.tail_x = torch.zeros(n_tail, dtype=dt_, device=dev)
@@ -706,7 +725,7 @@ class DistHierarchy:
                     specs.append(L.A.channel_spec((l, "pre", k), self.dtype))
                 specs.append(L.A.channel_spec((l, "res"), self.dtype))
                 specs.append(L.R.channel_spec((l, "R"), self.dtype))
-                specs.append(L.P.channel_spec((l, "P"), self.dtype))
+                specs.append((L.Q if (L.Q is not None and nu2 > 0) else L.P).channel_spec((l, "P"), self.dtype))
                 for k in range(nu2):
                     specs.append(L.A.channel_spec((l, "post", k), self.dtype))
             # coarse-level gather: every rank writes its slice of the restricted residual (+ one padding slot, so
@@ -776,11 +795,19 @@ class DistHierarchy:
             if xc is not None:                       # coarse correction not yet in L.e (tail, or a level without post-smoothing)
                 L.e[:L.nc].copy_(xc)
             rhs_l = b if l == 0 else self.levels[l].b
-            L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"))            # x += P e
             # the last sweep writes straight into its consumer: the caller's vector (level 0) or the finer level's
             # coarse-correction buffer — no copy on the way up
             target = x_out if l == 0 else self.levels[l - 1].e
-            for k in range(nu2):
+            k0 = 0
+            if L.Q is not None and nu2 > 0:
+                # x + P e followed by one sweep == x + dw.*r + Q e (r is still in L.r): one pass over Q
+                o = target if nu2 == 1 else (xb if c is xa else xa)
+                L.Q.apply(5, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=c)
+                c = o
+                k0 = 1
+            else:
+                L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"))        # x += P e
+            for k in range(k0, nu2):
                 o = target if k == nu2 - 1 else (xb if c is xa else xa)
                 L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "post", k))
                 c = o
@@ -879,8 +906,10 @@ class DistHierarchy:
             pre = (nu1 - 1) * b_jac + 3 * v * N if nu1 > 0 else 0
             if nu1 == 1 and nnz <= 12 * N and (self.halo == "peer" or self.comm.world == 1):
                 pre, b_res = 0, b_jac          # fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
-            tot += pre + nu2 * b_jac + b_res + (pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc) + \
-                (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
+            post = nu2 * b_jac + (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
+            if L.Q is not None and nu2 > 0:   # fused prolongation + first post sweep: read Q, e, x, r, dw; write x
+                post = (nu2 - 1) * b_jac + L.Q.csr.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N
+            tot += pre + post + b_res + (pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc)
         return tot + self.tail.cycle_bytes(nu1, nu2, True)
 
 

@@ -87,6 +87,16 @@ def galerkin(A, P, R=None, drop=True, symmetric=False):
     return core.drop_zeros(AH) if drop else AH
 
 
+def post_operator(A, P, dw):
+    """Q = (I - diag(dw) A) P — the prolongator seen through one smoothing sweep (A must store its diagonal)."""
+    n = A.shape[0]
+    rows = torch.repeat_interleave(torch.arange(n, device=A.col.device), (A.rowptr[1:] - A.rowptr[:-1]).long())
+    sval = -dw[rows] * A.val
+    sval += (A.col.long() == rows).to(sval.dtype)
+    del rows
+    return core.spgemm(A.with_values(sval), P)
+
+
 def _permuted(M, row_new2old, col_old2new):
     """rows gathered by row_new2old (None = keep), column ids mapped by col_old2new (None = keep), rows re-sorted"""
     if row_new2old is None and col_old2new is None:
@@ -118,7 +128,7 @@ class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
     def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
-                 sell_max_padding=1.5, restrict_order=True, renumber=True):
+                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True):
         """levels: list[Level] in the REFERENCE numbering (what setup produced and what parity is checked on).
 
         renumber (default on): the cycle runs on apply copies whose coarse levels are renumbered spatially
@@ -127,6 +137,10 @@ class Hierarchy:
         hits a different 32-byte L2 sector: measured at 256^3 the prolongation was L2-transaction bound
         (211 us for 0.88 GB).  Coarse vectors are internal to the cycle, so the renumbering is invisible outside;
         results change only by the re-ordered floating-point sums (within the 1e-12 parity bar).
+        fuse_post (default on): per level Q = (I - D_w A) P is built once, so that the prolongation and the first
+        post-smoothing sweep run as ONE pass over Q:  x + P e followed by x + dw.*(b - A x) equals
+        x + dw.*r + Q e  with the residual r the cycle already computed for the restriction.  Same arithmetic up
+        to rounding (well inside the 1e-12 bar), one pass over A less per level and cycle.
         sell: 'never' (default) -> CSR kernels only: measured on B200 at 256^3 the thread-per-row CSR kernel
         with predicated 4-entry batches (0.322 ms/sweep) is as fast as SELL-32 (0.337 ms), so the second copy
         of A is not worth its HBM; 'auto' / 'always' build SELL-32 copies for the smoother/residual kernels."""
@@ -154,6 +168,12 @@ class Hierarchy:
         for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
             check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
                                                    ptr(R.rowptr), ptr(R.col), ptr(R.val)))
+        self._Q = []
+        if fuse_post:
+            for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
+                Q = post_operator(A, P, dw)
+                self._Q.append(Q)
+                check(lib.mlamg_hierarchy_set_post_operator(self._h, l, Q.nnz, ptr(Q.rowptr), ptr(Q.col), ptr(Q.val)))
         # Without renumbering the restriction rows keep the reference's random seed numbering; then at least
         # VISIT them in the order of their first fine node so neighbouring aggregates share sectors of r.
         self._r_order = []
@@ -293,7 +313,8 @@ class Hierarchy:
 
 def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
                     P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
-                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never", fallback=None):
+                    dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never", fallback=None,
+                    fuse_post=True):
     """Build the multilevel hierarchy on the device.
 
     A           : scipy / torch sparse / DeviceCSR
@@ -350,4 +371,5 @@ def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxite
     if levels[-1].A.shape[0] > max_dense:
         raise _lib.MlamgError(_lib.ELIMIT, f"coarsest level has {levels[-1].A.shape[0]} rows; raise max_levels or "
                                            f"lower max_coarse (dense coarse solve limit {max_dense})")
-    return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph, sell=sell)
+    return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph, sell=sell,
+                     fuse_post=fuse_post)

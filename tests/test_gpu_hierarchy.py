@@ -132,6 +132,27 @@ def test_multilevel_setup_and_cycles_fp64(shape, ratio, smoother):
     assert H.cycle_bytes() > 0 and "levels" in repr(H)
 
 
+def test_fused_post_operator_cycle_matches_plain_cycle():
+    """Hierarchy(fuse_post=True) (default: one pass over Q = (I - D_w A) P on the way up) against the plain
+    prolongation + sweep, for several sweep counts, zero and non-zero guesses"""
+    import mlamg
+    A = oml.poisson((20, 18, 11))
+    lam = [2.0, 1.9, 1.8, 1.7]
+    kw = dict(aggregates="lloyd", ratio=0.05, distance="unit", rand=0, lam_max=lam, max_coarse=30)
+    Hf = mlamg.build_hierarchy(A, fuse_post=True, **kw)
+    Hp = mlamg.build_hierarchy(A, fuse_post=False, **kw)
+    assert len(Hf._Q) == len(Hf.levels) - 1 and not Hp._Q
+    assert Hf.cycle_bytes(1, 1) < Hp.cycle_bytes(1, 1)
+    n = A.shape[0]
+    b = torch.from_numpy(np.random.RandomState(0).randn(n)).cuda()
+    x0 = torch.from_numpy(np.random.RandomState(1).randn(n)).cuda()
+    for nu1, nu2 in ((1, 1), (2, 2), (0, 1), (1, 0), (3, 1)):
+        for guess in (None, x0):
+            xf = Hf.vcycle(b, None if guess is None else guess.clone(), nu1, nu2)
+            xp = Hp.vcycle(b, None if guess is None else guess.clone(), nu1, nu2)
+            assert float((xf - xp).abs().max()) <= 1e-13 * float(xp.abs().max()), (nu1, nu2)
+
+
 def test_multilevel_fp32():
     import mlamg
     A = oml.poisson((40, 36))

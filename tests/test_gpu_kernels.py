@@ -307,7 +307,7 @@ def test_spmv_row_order_is_result_invariant():
     assert torch.equal(y0, y1)
 
 
-@pytest.mark.parametrize("op", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5])
 def test_rowop_on_row_subset(op):
     """interior / boundary splits of the multi-GPU levels: only the listed rows are touched"""
     from mlamg import core
@@ -315,13 +315,16 @@ def test_rowop_on_row_subset(op):
     A = oml.poisson((12, 11, 10))
     n = A.shape[0]
     rs = np.random.RandomState(op)
-    x, b, dw, y0 = rs.randn(n), rs.randn(n), rs.rand(n), rs.randn(n)
+    x, b, dw, y0, z0 = rs.randn(n), rs.randn(n), rs.rand(n), rs.randn(n), rs.randn(n)
     rows = np.sort(rs.permutation(n)[: n // 3]).astype(np.int32)      # includes rows > len(rows)
     Ad = mlamg.DeviceCSR.from_scipy(A)
     yd = dev(y0, np.float64)
     xd = dev(x, np.float64)
-    core.rowop(Ad, op, xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64), rows=torch.from_numpy(rows).cuda())
-    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b)}[op]
+    zd = dev(z0, np.float64)
+    aux = {4: xd, 5: zd}.get(op)            # op 4: aux = x_out; op 5: aux = iterate before the correction
+    core.rowop(Ad, op, None if op == 4 else xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64),
+               rows=torch.from_numpy(rows).cuda(), aux=aux)
+    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b), 5: z0 + dw * b + A @ x}[op]
     if op == 4:          # x is an output here: the listed rows receive dw.*b, the others keep their content
         xr = x.copy()
         xr[rows] = (dw * b)[rows]
@@ -333,3 +336,32 @@ def test_rowop_on_row_subset(op):
     mask[rows] = False
     assert np.array_equal(got[mask], y0[mask]), "rows outside the list were modified"
     assert np.abs(got[rows] - ref[rows]).max() <= 1e-13 * np.abs(full).max()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prolong_smooth_equals_prolong_then_sweep(dtype):
+    """x + P e followed by one smoothing sweep == x + dw.*r + Q e with Q = (I - D_w A) P, r = b - A x"""
+    import mlamg
+    A = oml.poisson((16, 12, 9)).astype(dtype)
+    n = A.shape[0]
+    rs = np.random.RandomState(2)
+    lab = rs.randint(0, 60, n)
+    P = sp.csr_matrix((rs.rand(n) + 0.5, (np.arange(n), lab)), shape=(n, 60))
+    P = sp.csr_matrix((sp.eye(n) - 0.6 * sp.diags(1.0 / A.diagonal()) @ A) @ P).astype(dtype)      # smoothed: 1-ring pattern
+    P.sort_indices()
+    x, b, e = rs.randn(n).astype(dtype), rs.randn(n).astype(dtype), rs.randn(60).astype(dtype)
+    dw = (0.66 / A.diagonal()).astype(dtype)
+    Ad, Pd = mlamg.DeviceCSR.from_scipy(A), mlamg.DeviceCSR.from_scipy(P)
+    Q = mlamg.post_operator(Ad, Pd, dev(dw, dtype))
+    Qref = (sp.eye(n) - sp.diags(dw.astype(np.float64)) @ A.astype(np.float64)) @ P.astype(np.float64)
+    assert_csr_close(Q.to_scipy().astype(np.float64), sp.csr_matrix(Qref), TOL[dtype] * 10)
+    xd, bd, ed = dev(x, dtype), dev(b, dtype), dev(e, dtype)
+    r = mlamg.residual(Ad, xd, bd)
+    fused = mlamg.prolong_smooth(Q, ed, xd, r, dev(dw, dtype))
+    x64, b64, A64, P64 = x.astype(np.float64), b.astype(np.float64), A.astype(np.float64), P.astype(np.float64)
+    xp = x64 + P64 @ e.astype(np.float64)
+    ref = xp + dw.astype(np.float64) * (b64 - A64 @ xp)
+    close(fused, ref, dtype, np.abs(ref).max() * 10)
+    inplace = xd.clone()
+    mlamg.prolong_smooth(Q, ed, inplace, r, dev(dw, dtype), x_out=inplace)
+    assert torch.equal(inplace, fused)

@@ -67,17 +67,24 @@ def main():
             out = {"level": l, "op": name, "rows": N if "restrict" not in name else Nc,
                    "mean_row": round((pn / Nc) if "restrict" in name else (pn / N if name == "prolong_add" else nnz / N), 2),
                    "MB": round(nbytes / 1e6, 1), "us": {}, "GBs": {}}
-            for lanes in (-2, 0, 1, 2, 4, 8, 16, 32):
-                if lanes == 0 and name == "restrict_ordered":
-                    continue
-                mlamg.set_csr_lanes(lanes)
-                try:
-                    t = gtime(fn)
-                finally:
-                    mlamg.set_csr_lanes(-1)
-                key = {-2: "heur", 0: "staged"}.get(lanes, str(lanes))
-                out["us"][key] = round(t, 1)
-                out["GBs"][key] = round(nbytes / t / 1e3)
+            mean = out["mean_row"]
+            cand = [l for l in (1, 2, 4, 8, 16, 32) if l <= max(1, 2 * mean) and l * 16 >= mean]
+            if os.environ.get("TUNE_ALL") == "1":
+                cand = [0, 1, 2, 4, 8, 16, 32]
+            for lanes in [-2] + cand:
+                for nb in ((0,) if lanes == -2 else (2, 4, 8)):
+                    if lanes == 0 and (name == "restrict_ordered" or nb != 4):
+                        continue
+                    mlamg.set_csr_lanes(lanes)
+                    core.set_csr_batch(nb)
+                    try:
+                        t = gtime(fn)
+                    finally:
+                        mlamg.set_csr_lanes(-1)
+                        core.set_csr_batch(0)
+                    key = "heur" if lanes == -2 else ("staged" if lanes == 0 else f"{lanes}x{nb}")
+                    out["us"][key] = round(t, 1)
+                    out["GBs"][key] = round(nbytes / t / 1e3)
             print(json.dumps(out), flush=True)
 
 
