@@ -72,6 +72,11 @@ int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *co
 int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                                    const void *dw, const void *b, void *x_out, void *r, double *norm2,
                                    mlamg_stream_t stream);
+/* the same on column-scaled values val_scaled[j] = a_ij * dw_j (A D_w on A's pattern, built once at setup): the
+ * gathers read b alone, so the pass runs at the speed of a plain residual */
+int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *rowptr, const int *col,
+                                          const void *val_scaled, const void *dw, const void *b, void *x_out,
+                                          void *r, double *norm2, mlamg_stream_t stream);
 /* x_out = x_in + dw .* r + Q e  (x_out may alias x_in): prolongation fused with the first post-smoothing sweep.
  * With r = b - A x_in known (it was computed for the restriction),  (x_in + P e) followed by one sweep
  * x + dw.*(b - A x)  equals  x_in + dw.*r + Q e  with  Q = (I - D_w A) P  built once at setup — one pass over Q
@@ -96,7 +101,8 @@ int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *
 /* generic row-op over the row range [row_begin, row_begin + nrows) (row_list == NULL) or the listed rows
  * row_list[0..nrows):
  * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) (x unused) |
- * 5 y=aux+dw.*b+Ax (aux may alias y).  aux is NULL for ops 0-3.
+ * 5 y=aux+dw.*b+Ax (aux may alias y) | 6 = op 4 with val holding a_ij*dw_j (gathers b alone).  aux is NULL
+ * for ops 0-3.
  * Used by the row-partitioned multi-GPU levels to run interior rows while the halo exchange of x is in
  * flight, then the boundary rows. */
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,
@@ -225,6 +231,9 @@ int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int 
 int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, const int *p_rowptr,
                                  const int *p_col, const void *p_val, const int *r_rowptr,
                                  const int *r_col, const void *r_val);
+/* optional values of A D_w (a_ij * dw_j) on level l's pattern: the zero-guess sweep + residual pass of a V(1,*)
+ * cycle then gathers b alone (mlamg_jacobi_zero_residual_scaled_csr).  NULL removes it. */
+int mlamg_hierarchy_set_operator_scaled(mlamg_hierarchy_t h, int level, const void *val_scaled);
 /* optional Q = (I - D_w A) P of level l (rows n_l, columns n_{l+1}; D_w = diag(dw) of that level): when set, the
  * prolongation and the first post-smoothing sweep run as one pass over Q (mlamg_prolong_smooth_csr).
  * q_rowptr == NULL removes it. */

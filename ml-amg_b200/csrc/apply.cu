@@ -15,7 +15,9 @@ namespace mlamg {
 // OP_PSMOOTH: prolongation fused with the first post-smoothing sweep.  With r = b - A x already known (it was
 // computed for the restriction), x + P e followed by one sweep equals  x + dw.*r + Q e,  Q = (I - D_w A) P
 // precomputed at setup: one pass over Q instead of a pass over P and a pass over A.
-enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4, OP_PSMOOTH = 5 };
+// OP_RESZERO_S: OP_RESZERO on the column-scaled operator A D_w (values a_ij * dw_j, built once at setup): the
+// gathers read b[c] alone — r = b - (A D_w) b — so the pass runs at the speed of a plain residual.
+enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4, OP_PSMOOTH = 5, OP_RESZERO_S = 6 };
 
 constexpr int ROW_THREADS = 256;
 
@@ -31,7 +33,7 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
         const T r = b[row] - sum;
         y[row] = r;
         if (NORM) rr = (double)r * (double)r;
-    } else if (OP == OP_RESZERO) {
+    } else if (OP == OP_RESZERO || OP == OP_RESZERO_S) {
         const T br = b[row];
         y2[row] = dw[row] * br;
         const T r = br - sum;
@@ -68,7 +70,7 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
         tag = ll_tag(seq);
         hreg = reinterpret_cast<const T *>((seq & 1ull) ? halo.region[1] : halo.region[0]);
     }
-#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : x[(c)])
+#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : (OP == OP_RESZERO_S ? b[(c)] : x[(c)]))
 #define XLOAD(c) ((HALO && (c) >= halo.n_own) ? ll_load(hreg, (c) - halo.n_own, tag, halo.state) : XOWN(c))
     // row_order: optional list of the n rows to process (a permutation of all rows, or a subset).  Used by
     // the restriction, whose rows (aggregates) are numbered randomly by the reference's seeding — visiting
@@ -152,7 +154,7 @@ csr_staged_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__
         __syncthreads();
         const int js = max(my_s, base) - base, je = min(my_e, base + cnt) - base;
         constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
-#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : x[(c)])
+#define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : (OP == OP_RESZERO_S ? b[(c)] : x[(c)]))
         for (int j = js; j < je; j += NB) {
             bool p[NB];
             int c[NB];
@@ -415,6 +417,19 @@ int psmooth_t(int n, long long nnz, const int *rowptr, const int *col, const T *
 template int psmooth_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
 template int psmooth_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
 
+// the same on the column-scaled values a_ij * dw_j (single gather of b)
+template <typename T>
+int reszero_scaled_t(int n, long long nnz, const int *rowptr, const int *col, const T *val_scaled, const T *dw, const T *b,
+                     T *x_out, T *r, double *norm2, cudaStream_t s) {
+    if (norm2)
+        return launch_rowop<T, OP_RESZERO_S, true>(n, nnz, rowptr, col, val_scaled, nullptr, b, dw, r, norm2, s, nullptr, 0,
+                                                   nullptr, x_out);
+    return launch_rowop<T, OP_RESZERO_S, false>(n, nnz, rowptr, col, val_scaled, nullptr, b, dw, r, nullptr, s, nullptr, 0,
+                                                nullptr, x_out);
+}
+template int reszero_scaled_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, float *, float *, double *, cudaStream_t);
+template int reszero_scaled_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, double *, double *, double *, cudaStream_t);
+
 template int reszero_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, float *, float *, double *, cudaStream_t);
 template int reszero_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, double *, double *, double *, cudaStream_t);
 
@@ -585,6 +600,17 @@ int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr,
     return MLAMG_OK;
 }
 
+int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *rowptr, const int *col,
+                                          const void *val_scaled, const void *dw, const void *b, void *x_out, void *r,
+                                          double *norm2, mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "jacobi_zero_residual_scaled: n < 0");
+    if (x_out == r || b == x_out || b == r) return set_error(MLAMG_EINVAL, "jacobi_zero_residual_scaled: aliased arguments");
+    MLAMG_DISPATCH(dtype, return reszero_scaled_t<T>(n, nnz, rowptr, col, (const T *)val_scaled, (const T *)dw, (const T *)b,
+                                                     (T *)x_out, (T *)r, norm2, s));
+    return MLAMG_OK;
+}
+
 int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val, const void *e,
                              const void *x_in, const void *r, const void *dw, void *x_out, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
@@ -648,6 +674,12 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
                                                                              row_begin, nullptr, (T *)aux)));
             break;
+        case OP_RESZERO_S:     // op 4 on column-scaled values a_ij*dw_j: gathers b alone
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "rowop: op 6 needs aux = x_out");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO_S, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
+                                                                               (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                               row_begin, nullptr, (T *)aux)));
+            break;
         case OP_PSMOOTH:       // aux = x_in (may alias y); x = coarse correction, b = residual
             if (!aux) return set_error(MLAMG_EINVAL, "rowop: op 5 needs aux = x_in");
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
@@ -686,6 +718,12 @@ int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nn
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
                                                                              row_begin, &hl, (T *)aux)));
+            break;
+        case OP_RESZERO_S:     // halo columns carry the neighbours' b
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "channel_rowop: op 6 needs aux = x_out");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO_S, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
+                                                                               (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                               row_begin, &hl, (T *)aux)));
             break;
         case OP_PSMOOTH:       // aux = x_in (may alias y)
             if (!aux) return set_error(MLAMG_EINVAL, "channel_rowop: op 5 needs aux = x_in");

@@ -26,6 +26,8 @@ template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStre
 template <typename T>
 int reszero_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
 template <typename T>
+int reszero_scaled_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
+template <typename T>
 int psmooth_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
 template <typename T>
 int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
@@ -44,6 +46,7 @@ struct LevelData {
     Csr A, P, R;
     Csr Q;                                                  // optional (I - D_w A) P: prolongation fused with the first post sweep
     bool has_Q = false;
+    const void *val_scaled = nullptr;                       // optional values of A D_w (a_ij * dw_j) on A's pattern
     const void *dw = nullptr;
     const int *r_order = nullptr;                           // optional processing order of the rows of R
     const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A
@@ -126,8 +129,11 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             // V(1,*) from a zero guess: x = dw.*b and r = b - A x in ONE pass (x is never read back from HBM)
             // only for short rows (thread-per-row kernel): with several lanes per row the doubled gathers make the
             // kernel L1-bound (measured at 256^3, level 1, 30 entries/row: 70 us fused vs 56 us for the pair)
-            fused = (nu1 == 1) && !lev.sell_ptr && (double)A.nnz <= 12.0 * (double)A.n;
-            if (fused)
+            fused = (nu1 == 1) && !lev.sell_ptr && (lev.val_scaled || (double)A.nnz <= 12.0 * (double)A.n);
+            if (fused && lev.val_scaled)      // on the column-scaled copy A D_w the gathers read b alone (any row length)
+                MLAMG_TRY(reszero_scaled_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)lev.val_scaled, dw, rhs[l], c, (T *)lev.r,
+                                              nullptr, s));
+            else if (fused)
                 MLAMG_TRY(reszero_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, dw, rhs[l], c, (T *)lev.r, nullptr, s));
             else if (nu1 > 0) MLAMG_TRY(jacobi_zero_t<T>(A.n, dw, rhs[l], c, s));
             else MLAMG_CUDA(cudaMemsetAsync(c, 0, (size_t)A.n * sizeof(T), s));
@@ -297,6 +303,15 @@ int mlamg_hierarchy_set_transfer(mlamg_hierarchy_t h, int level, int p_nnz, cons
     return MLAMG_OK;
 }
 
+int mlamg_hierarchy_set_operator_scaled(mlamg_hierarchy_t h, int level, const void *val_scaled) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level >= (int)h->lv.size() || !h->lv[level].has_A)
+        return set_error(MLAMG_EINVAL, "set_operator_scaled: set the CSR operator of the level first");
+    h->lv[level].val_scaled = val_scaled;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return MLAMG_OK;
+}
+
 int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz, const int *q_rowptr, const int *q_col,
                                       const void *q_val) {
     MLAMG_TRY(check_handle(h));
@@ -386,7 +401,7 @@ double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int ze
         double pre = nu1 * b_jac;
         double res = b_res;
         if (zero && nu1 > 0) pre = (nu1 - 1) * b_jac + 3 * v * N;   // x = dw.*b : read dw,b write x
-        if (zero && nu1 == 1 && !lev.sell_ptr && nnz <= 12.0 * N) {   // fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
+        if (zero && nu1 == 1 && !lev.sell_ptr && (lev.val_scaled || nnz <= 12.0 * N)) {   // fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
             pre = 0.0;
             res = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N;
         }

@@ -229,8 +229,8 @@ def spmv_perm(A, x, row_order, out=None):
 
 
 def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None, aux=None):
-    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) | 5 y=aux+dw.*b+Ax)
-    over all rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
+    """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) | 5 y=aux+dw.*b+Ax |
+    6 = op 4 with A holding the column-scaled values a_ij*dw_j) over all rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
     begin = 0
     if rows is not None:
         n = rows.numel()
@@ -298,6 +298,24 @@ def jacobi_zero_residual(A, dw, b, x_out=None, r_out=None, norm=False):
                                              ptr(x_out), ptr(r_out), ptr(nrm), stream()))
     if norm:
         return x_out, r_out, float(nrm.sqrt().item())
+    return x_out, r_out
+
+
+def scaled_values(A, dw_cols):
+    """values of A D_w on A's pattern: a_ij * dw_cols[j] (dw_cols indexed by COLUMN; pass the ext vector for the
+    row-partitioned levels)"""
+    return (A.val * dw_cols[A.col.long()]).contiguous()
+
+
+def jacobi_zero_residual_scaled(A, val_scaled, dw, b, x_out=None, r_out=None):
+    """jacobi_zero_residual on the column-scaled values (gathers b alone)"""
+    n = A.shape[0]
+    if x_out is None:
+        x_out = torch.empty_like(b)
+    if r_out is None:
+        r_out = torch.empty_like(b)
+    check(lib.mlamg_jacobi_zero_residual_scaled_csr(dt(A.val), n, A.nnz, ptr(A.rowptr), ptr(A.col), ptr(val_scaled), ptr(dw),
+                                                    ptr(b), ptr(x_out), ptr(r_out), None, stream()))
     return x_out, r_out
 
 

@@ -467,7 +467,17 @@ class DistOperator:
         self._split_rows()
 
     def rowop(self, op, x_ext, y, b=None, dw=None, rows=None, row_range=None, aux=None):
-        core.rowop(self.csr, op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range, aux=aux)
+        core.rowop(self._csr_for(op), op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range, aux=aux)
+
+    def _csr_for(self, op):
+        return self.csr_scaled if op == 6 else self.csr
+
+    def build_scaled(self, dw):
+        """column-scaled copy A D_w (op 6): dw of the halo columns comes from their owners (one exchange at setup)"""
+        dw_ext = torch.zeros(self.n_ext, dtype=dw.dtype, device=dw.device)
+        dw_ext[:self.n_cols_own] = dw
+        self.plan.exchange(dw_ext, self.n_cols_own)
+        self.csr_scaled = self.csr.with_values(core.scaled_values(self.csr, dw_ext))
 
     def channel_spec(self, name, dtype):
         """(name, send list, per-rank counts, dtype) of the halo exchange of this operator's input"""
@@ -480,8 +490,8 @@ class DistOperator:
         op 4 (x = dw.*b, y = b - A x): x_ext is the OUTPUT x, the neighbours receive dw.*b directly.
         op 5 (y = aux + dw.*b + A x_ext): aux = iterate before the correction, b = residual, x_ext = coarse correction."""
         plan = self.plan
-        xin = None if op == 4 else x_ext           # gather vector (op 4 evaluates dw[c]*b[c] instead)
-        if op == 4:
+        xin = None if op in (4, 6) else x_ext      # gather vector (ops 4/6 gather b instead)
+        if op in (4, 6):
             aux = x_ext
         if plan.comm.world == 1:
             self.rowop(op, xin, y, b, dw, aux=aux)
@@ -490,6 +500,8 @@ class DistOperator:
             n_own = self.n_cols_own
             if op == 4:
                 chan.push(b, scale=dw)
+            elif op == 6:
+                chan.push(b)
             else:
                 chan.push(x_ext)
             split = overlap and self.peer_split_ok
@@ -499,13 +511,13 @@ class DistOperator:
                 else:
                     self.rowop(op, xin, y, b, dw, rows=self.interior, aux=aux)
             rows = self.boundary if split else None
-            if PEER_INPLACE or op == 4:
-                chan.rowop(self.csr, op, xin, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
+            if PEER_INPLACE or op in (4, 6):
+                chan.rowop(self._csr_for(op), op, xin, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             else:
                 chan.unpack(x_ext[n_own:n_own + plan.n_halo])
                 self.rowop(op, xin, y, b, dw, rows=rows, aux=aux)
             return
-        if op == 4:
+        if op in (4, 6):
             raise ValueError("the fused zero-guess sweep + residual needs the peer transport (halo columns of b, dw)")
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
@@ -536,7 +548,7 @@ class DistHierarchy:
 
     def __init__(self, rowptr, col_global, val, comm=None, *, ratio=0.1, distance="unit", maxiter=10, rand=0,
                  lam_max=None, max_levels=10, max_coarse=500, replicate_below=200000, smoother="jacobi",
-                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True, halo=None, fuse_post=True):
+                 jacobi_weight=2.0 / 3.0, overlap=True, renumber=True, halo=None, fuse_post=True, fuse_pre=True):
         core.require_cuda()
         self.comm = comm or Comm()
         comm = self.comm
@@ -549,6 +561,7 @@ class DistHierarchy:
         self._chansets = {}
         # Q = (I - D_w A) P per level: prolongation + first post-smoothing sweep as one pass (see Hierarchy)
         self.fuse_post = bool(fuse_post)
+        self.fuse_pre = bool(fuse_pre)
         self.comm_stream = torch.cuda.Stream() if comm.world > 1 else None
         self.levels = []
         self.offsets = []
@@ -581,6 +594,9 @@ class DistHierarchy:
         self.tail_offsets = offs
         if renumber:
             self._renumber()
+        if self.fuse_pre:
+            for L in self.levels:
+                L.A.build_scaled(L.dw)
         self._alloc()
 
     # ---------------------------------------------------------------------------------------------
@@ -765,9 +781,10 @@ class DistHierarchy:
             xa, xb = L.x
             n = L.n
             c = xa
-            fused = nu1 == 1 and (chans is not None or comm.world == 1) and L.A.csr.nnz <= 12 * n    # short rows only
+            scaled = self.fuse_pre and hasattr(L.A, "csr_scaled")
+            fused = nu1 == 1 and (chans is not None or comm.world == 1) and (scaled or L.A.csr.nnz <= 12 * n)
             if fused:      # x = dw.*b and r = b - A x in one pass over A (x is never read back)
-                L.A.apply(4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
+                L.A.apply(6 if scaled else 4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
             elif nu1 > 0:
                 core.jacobi_zero(L.dw, rhs, c[:n])
             else:
@@ -904,7 +921,7 @@ class DistHierarchy:
             b_jac = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N
             b_res = nnz * (v + 4) + 4 * (N + 1) + 3 * v * N
             pre = (nu1 - 1) * b_jac + 3 * v * N if nu1 > 0 else 0
-            if nu1 == 1 and nnz <= 12 * N and (self.halo == "peer" or self.comm.world == 1):
+            if nu1 == 1 and (self.fuse_pre or nnz <= 12 * N) and (self.halo == "peer" or self.comm.world == 1):
                 pre, b_res = 0, b_jac          # fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
             post = nu2 * b_jac + (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
             if L.Q is not None and nu2 > 0:   # fused prolongation + first post sweep: read Q, e, x, r, dw; write x

@@ -128,7 +128,7 @@ class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
     def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
-                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True):
+                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True, fuse_pre=True):
         """levels: list[Level] in the REFERENCE numbering (what setup produced and what parity is checked on).
 
         renumber (default on): the cycle runs on apply copies whose coarse levels are renumbered spatially
@@ -141,6 +141,8 @@ class Hierarchy:
         post-smoothing sweep run as ONE pass over Q:  x + P e followed by x + dw.*(b - A x) equals
         x + dw.*r + Q e  with the residual r the cycle already computed for the restriction.  Same arithmetic up
         to rounding (well inside the 1e-12 bar), one pass over A less per level and cycle.
+        fuse_pre (default on): a copy of every level's values scaled by columns (A D_w) lets the first pass of a
+        V(1,*) cycle from a zero guess — x = dw.*b, r = b - A x — gather b alone: r = b - (A D_w) b.
         sell: 'never' (default) -> CSR kernels only: measured on B200 at 256^3 the thread-per-row CSR kernel
         with predicated 4-entry batches (0.322 ms/sweep) is as fast as SELL-32 (0.337 ms), so the second copy
         of A is not worth its HBM; 'auto' / 'always' build SELL-32 copies for the smoother/residual kernels."""
@@ -168,6 +170,12 @@ class Hierarchy:
         for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
             check(lib.mlamg_hierarchy_set_transfer(self._h, l, P.nnz, ptr(P.rowptr), ptr(P.col), ptr(P.val),
                                                    ptr(R.rowptr), ptr(R.col), ptr(R.val)))
+        self._scaled = []
+        if fuse_pre:
+            for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
+                vs = core.scaled_values(A, dw)
+                self._scaled.append(vs)
+                check(lib.mlamg_hierarchy_set_operator_scaled(self._h, l, ptr(vs)))
         self._Q = []
         if fuse_post:
             for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
@@ -314,7 +322,7 @@ class Hierarchy:
 def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxiter=10, rand=0, lam_max=None,
                     P_hat=None, max_levels=10, max_coarse=500, smoother="jacobi", jacobi_weight=2.0 / 3.0,
                     dtype=None, use_graph=False, keep_labels=True, max_dense=20000, sell="never", fallback=None,
-                    fuse_post=True):
+                    fuse_post=True, fuse_pre=True):
     """Build the multilevel hierarchy on the device.
 
     A           : scipy / torch sparse / DeviceCSR
@@ -372,4 +380,4 @@ def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxite
         raise _lib.MlamgError(_lib.ELIMIT, f"coarsest level has {levels[-1].A.shape[0]} rows; raise max_levels or "
                                            f"lower max_coarse (dense coarse solve limit {max_dense})")
     return Hierarchy(levels, smoother=smoother, jacobi_weight=jacobi_weight, use_graph=use_graph, sell=sell,
-                     fuse_post=fuse_post)
+                     fuse_post=fuse_post, fuse_pre=fuse_pre)

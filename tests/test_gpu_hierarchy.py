@@ -139,9 +139,9 @@ def test_fused_post_operator_cycle_matches_plain_cycle():
     A = oml.poisson((20, 18, 11))
     lam = [2.0, 1.9, 1.8, 1.7]
     kw = dict(aggregates="lloyd", ratio=0.05, distance="unit", rand=0, lam_max=lam, max_coarse=30)
-    Hf = mlamg.build_hierarchy(A, fuse_post=True, **kw)
-    Hp = mlamg.build_hierarchy(A, fuse_post=False, **kw)
-    assert len(Hf._Q) == len(Hf.levels) - 1 and not Hp._Q
+    Hf = mlamg.build_hierarchy(A, fuse_post=True, fuse_pre=True, **kw)
+    Hp = mlamg.build_hierarchy(A, fuse_post=False, fuse_pre=False, **kw)
+    assert len(Hf._Q) == len(Hf.levels) - 1 and not Hp._Q and len(Hf._scaled) == len(Hf.levels) - 1 and not Hp._scaled
     assert Hf.cycle_bytes(1, 1) < Hp.cycle_bytes(1, 1)
     n = A.shape[0]
     b = torch.from_numpy(np.random.RandomState(0).randn(n)).cuda()

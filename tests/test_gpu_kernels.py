@@ -68,6 +68,11 @@ def test_spmv_residual_jacobi(name, dtype):
         assert torch.equal(rf, mlamg.residual(Ad, x0, bd))
         xr = (dw * b).astype(dtype)
         close(rf, b - A @ xr, dtype, (abs(A) @ np.abs(xr)).max() + np.abs(b).max())
+        # ... and on the column-scaled copy A D_w (single gather of b)
+        vs = mlamg.scaled_values(Ad, dev(dw, dtype))
+        xs, rs_ = mlamg.jacobi_zero_residual_scaled(Ad, vs, dev(dw, dtype), bd)
+        assert torch.equal(xs, x0)
+        close(rs_, b - A @ xr, dtype, (abs(A) @ np.abs(xr)).max() + np.abs(b).max())
         assert abs(nrm - np.linalg.norm((b - A @ xr).astype(np.float64))) <= 10 * TOL[dtype] * max(nrm, 1e-30)
 
 
@@ -307,7 +312,7 @@ def test_spmv_row_order_is_result_invariant():
     assert torch.equal(y0, y1)
 
 
-@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6])
 def test_rowop_on_row_subset(op):
     """interior / boundary splits of the multi-GPU levels: only the listed rows are touched"""
     from mlamg import core
@@ -321,11 +326,13 @@ def test_rowop_on_row_subset(op):
     yd = dev(y0, np.float64)
     xd = dev(x, np.float64)
     zd = dev(z0, np.float64)
-    aux = {4: xd, 5: zd}.get(op)            # op 4: aux = x_out; op 5: aux = iterate before the correction
-    core.rowop(Ad, op, None if op == 4 else xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64),
+    aux = {4: xd, 6: xd, 5: zd}.get(op)     # ops 4/6: aux = x_out; op 5: aux = iterate before the correction
+    Aop = Ad.with_values(mlamg.scaled_values(Ad, dev(dw, np.float64))) if op == 6 else Ad
+    core.rowop(Aop, op, None if op in (4, 6) else xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64),
                rows=torch.from_numpy(rows).cuda(), aux=aux)
-    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b), 5: z0 + dw * b + A @ x}[op]
-    if op == 4:          # x is an output here: the listed rows receive dw.*b, the others keep their content
+    full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b), 5: z0 + dw * b + A @ x,
+            6: b - A @ (dw * b)}[op]
+    if op in (4, 6):     # x is an output here: the listed rows receive dw.*b, the others keep their content
         xr = x.copy()
         xr[rows] = (dw * b)[rows]
         assert np.array_equal(xd.cpu().numpy(), xr)
