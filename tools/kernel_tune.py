@@ -53,7 +53,11 @@ def main():
         bc = torch.empty_like(e)
         first = R.col[R.rowptr[:-1].long().clamp(max=max(R.nnz - 1, 0))]
         order = torch.argsort(first, stable=True).to(torch.int32).contiguous()
+        vs = core.scaled_values(Al, dw)
+        Q = H._Q[l]
         ops = {
+            "reszero_scaled": (lambda: core.jacobi_zero_residual_scaled(Al, vs, dw, b, y, r), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
+            "psmooth": (lambda: core.prolong_smooth(Q, e, x, r, dw, y), Q.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N),
             "jacobi": (lambda: core.jacobi_sweep(Al, dw, b, x, y), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
             "residual": (lambda: core.residual(Al, x, b, r), nnz * (v + 4) + 4 * (N + 1) + 3 * v * N),
             "reszero_fused": (lambda: core.jacobi_zero_residual(Al, dw, b, y, r), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
@@ -65,7 +69,8 @@ def main():
         }
         for name, (fn, nbytes) in ops.items():
             out = {"level": l, "op": name, "rows": N if "restrict" not in name else Nc,
-                   "mean_row": round((pn / Nc) if "restrict" in name else (pn / N if name == "prolong_add" else nnz / N), 2),
+                   "mean_row": round((pn / Nc) if "restrict" in name else (pn / N if name == "prolong_add" else
+                                                                           (Q.nnz / N if name == "psmooth" else nnz / N)), 2),
                    "MB": round(nbytes / 1e6, 1), "us": {}, "GBs": {}}
             mean = out["mean_row"]
             cand = [l for l in (1, 2, 4, 8, 16, 32) if l <= max(1, 2 * mean) and l * 16 >= mean]
