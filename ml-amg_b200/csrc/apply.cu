@@ -414,6 +414,25 @@ int psmooth_t(int n, long long nnz, const int *rowptr, const int *col, const T *
     return launch_rowop<T, OP_PSMOOTH, false>(n, nnz, rowptr, col, val, e, r, dw, x_out, nullptr, s, nullptr, 0, nullptr,
                                               const_cast<T *>(x_in));
 }
+// row-range forms (rows [row0, row0 + nrows)) used by the host-buffer entry point to pipeline the first and the last
+// fine-level pass with the PCIe copies
+template <typename T>
+int psmooth_range_t(int nrows, int row0, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *e,
+                    const T *x_in, const T *r, const T *dw, T *x_out, cudaStream_t s) {
+    return launch_rowop<T, OP_PSMOOTH, false>(nrows, nnz_hint, rowptr, col, val, e, r, dw, x_out, nullptr, s, nullptr, row0,
+                                              nullptr, const_cast<T *>(x_in));
+}
+template <typename T>
+int reszero_scaled_range_t(int nrows, int row0, long long nnz_hint, const int *rowptr, const int *col, const T *val_scaled,
+                           const T *dw, const T *b, T *x_out, T *r, cudaStream_t s) {
+    return launch_rowop<T, OP_RESZERO_S, false>(nrows, nnz_hint, rowptr, col, val_scaled, nullptr, b, dw, r, nullptr, s, nullptr,
+                                                row0, nullptr, x_out);
+}
+template int psmooth_range_t<float>(int, int, long long, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
+template int psmooth_range_t<double>(int, int, long long, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
+template int reszero_scaled_range_t<float>(int, int, long long, const int *, const int *, const float *, const float *, const float *, float *, float *, cudaStream_t);
+template int reszero_scaled_range_t<double>(int, int, long long, const int *, const int *, const double *, const double *, const double *, double *, double *, cudaStream_t);
+
 template int psmooth_t<float>(int, long long, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
 template int psmooth_t<double>(int, long long, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
 

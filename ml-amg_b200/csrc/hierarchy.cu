@@ -28,6 +28,11 @@ int reszero_t(int, long long, const int *, const int *, const T *, const T *, co
 template <typename T>
 int reszero_scaled_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
 template <typename T>
+int psmooth_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *,
+                    cudaStream_t);
+template <typename T>
+int reszero_scaled_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, cudaStream_t);
+template <typename T>
 int psmooth_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
 template <typename T>
 int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
@@ -57,6 +62,21 @@ struct LevelData {
 
 }  // namespace mlamg
 
+namespace mlamg {
+// Host-buffer apply (mlamg_vcycle_host): the right-hand side arrives and the result leaves in row chunks on a copy
+// stream; the first fine-level pass runs chunk by chunk as soon as the columns it gathers have arrived, the last one
+// hands every finished chunk to the D2H copy — the two PCIe transfers overlap the two largest kernels.
+constexpr int PIPE_CHUNKS = 8;
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t cs = nullptr;
+    cudaEvent_t in_ev[PIPE_CHUNKS] = {}, out_ev[PIPE_CHUNKS] = {}, fork = nullptr;
+    int row_lo[PIPE_CHUNKS + 1] = {};
+    int need[PIPE_CHUNKS] = {};          // chunk whose arrival completes the columns gathered by the rows of chunk k
+    int nchunks = 0;
+};
+}  // namespace mlamg
+
 struct mlamg_hierarchy {
     int dtype = MLAMG_F64;
     size_t esz = 8;
@@ -69,6 +89,7 @@ struct mlamg_hierarchy {
     double *dscal = nullptr;     // device scalars
     double *hscal = nullptr;     // pinned host mirror
     void *host_b = nullptr, *host_x = nullptr;   // device staging of the *_host entry points
+    mlamg::HostPipe pipe;
     // CUDA graph cache of one V-cycle
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -101,8 +122,10 @@ static int level_residual(const LevelData &lev, const T *b, const T *x, T *r, do
     return residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)A.val, x, b, r, norm2, s);
 }
 
+// pipe != nullptr (host-buffer apply): b arrives / x leaves in row chunks, see HostPipe
 template <typename T>
-static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
+static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2, int zero_guess, cudaStream_t s,
+                          const HostPipe *pipe = nullptr, char *x_host = nullptr) {
     const int L = (int)h->lv.size();
     if (L == 1) {   // single level: exact solve
         return gemv_t<T>(h->lv[0].A.n, (const T *)h->coarse_inv, b, x, s);
@@ -130,7 +153,14 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             // only for short rows (thread-per-row kernel): with several lanes per row the doubled gathers make the
             // kernel L1-bound (measured at 256^3, level 1, 30 entries/row: 70 us fused vs 56 us for the pair)
             fused = (nu1 == 1) && !lev.sell_ptr && (lev.val_scaled || (double)A.nnz <= 12.0 * (double)A.n);
-            if (fused && lev.val_scaled)      // on the column-scaled copy A D_w the gathers read b alone (any row length)
+            if (fused && lev.val_scaled && l == 0 && pipe) {
+                for (int k = 0; k < pipe->nchunks; k++) {      // rows of chunk k as soon as their columns have arrived
+                    const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
+                    MLAMG_CUDA(cudaStreamWaitEvent(s, pipe->in_ev[pipe->need[k]], 0));
+                    MLAMG_TRY(reszero_scaled_range_t<T>(cnt, lo, (long long)((double)A.nnz * cnt / A.n) + 1, A.rowptr, A.col,
+                                                        (const T *)lev.val_scaled, dw, rhs[l], c, (T *)lev.r, s));
+                }
+            } else if (fused && lev.val_scaled)      // on the column-scaled copy A D_w the gathers read b alone (any row length)
                 MLAMG_TRY(reszero_scaled_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)lev.val_scaled, dw, rhs[l], c, (T *)lev.r,
                                               nullptr, s));
             else if (fused)
@@ -171,6 +201,18 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             // one pass over Q instead of a pass over P and a pass over A
             const Csr &Q = lev.Q;
             T *o = (c == xa) ? xb : xa;
+            if (l == 0 && pipe && nu2 == 1 && o == x && x_host) {
+                for (int k = 0; k < pipe->nchunks; k++) {      // every finished chunk of the result goes to the D2H copy
+                    const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
+                    MLAMG_TRY(psmooth_range_t<T>(cnt, lo, (long long)((double)Q.nnz * cnt / Q.n) + 1, Q.rowptr, Q.col,
+                                                 (const T *)Q.val, cur[l + 1], c, (const T *)lev.r, (const T *)lev.dw, o, s));
+                    MLAMG_CUDA(cudaEventRecord(pipe->out_ev[k], s));
+                    MLAMG_CUDA(cudaStreamWaitEvent(pipe->cs, pipe->out_ev[k], 0));
+                    MLAMG_CUDA(cudaMemcpyAsync(x_host + (size_t)lo * sizeof(T), o + lo, (size_t)cnt * sizeof(T),
+                                               cudaMemcpyDeviceToHost, pipe->cs));
+                }
+                x_host = nullptr;      // delivered
+            } else
             MLAMG_TRY(psmooth_t<T>(Q.n, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], c, (const T *)lev.r,
                                    (const T *)lev.dw, o, s));
             c = o;
@@ -188,6 +230,11 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             c = x;
         }
         cur[l] = c;
+    }
+    if (pipe && x_host) {      // result not delivered chunk by chunk (other sweep counts): one copy behind the cycle
+        MLAMG_CUDA(cudaEventRecord(pipe->out_ev[0], s));
+        MLAMG_CUDA(cudaStreamWaitEvent(pipe->cs, pipe->out_ev[0], 0));
+        MLAMG_CUDA(cudaMemcpyAsync(x_host, x, (size_t)h->lv[0].A.n * sizeof(T), cudaMemcpyDeviceToHost, pipe->cs));
     }
     return MLAMG_OK;
 }
@@ -230,6 +277,57 @@ static int ensure_pcg(mlamg_hierarchy *h) {
     MLAMG_CUDA(cudaMalloc(&h->pcg_z, bytes));
     MLAMG_CUDA(cudaMalloc(&h->pcg_p, bytes));
     MLAMG_CUDA(cudaMalloc(&h->pcg_ap, bytes));
+    return MLAMG_OK;
+}
+
+__global__ void __launch_bounds__(256) range_max_kernel(const int *__restrict__ col, int begin, int end, int *out) {
+    int m = -1;
+    for (long long j = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < end; j += (long long)gridDim.x * blockDim.x)
+        m = max(m, col[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(out, m);
+}
+
+// chunk boundaries of the host pipeline and, per chunk, the last chunk of b its rows gather from
+static int ensure_pipe(mlamg_hierarchy *h, cudaStream_t s) {
+    HostPipe &P = h->pipe;
+    if (P.ready) return MLAMG_OK;
+    const Csr &A = h->lv[0].A;
+    const int n = A.n;
+    int rows = (n + PIPE_CHUNKS - 1) / PIPE_CHUNKS;
+    rows = (rows + 255) / 256 * 256;
+    P.nchunks = 0;
+    for (int lo = 0; lo < n; lo += rows) P.row_lo[P.nchunks++] = lo;
+    P.row_lo[P.nchunks] = n;
+    MLAMG_CUDA(cudaStreamCreateWithFlags(&P.cs, cudaStreamNonBlocking));
+    MLAMG_CUDA(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
+    for (int k = 0; k < PIPE_CHUNKS; k++) {
+        MLAMG_CUDA(cudaEventCreateWithFlags(&P.in_ev[k], cudaEventDisableTiming));
+        MLAMG_CUDA(cudaEventCreateWithFlags(&P.out_ev[k], cudaEventDisableTiming));
+    }
+    int ptr_host[PIPE_CHUNKS + 1], maxcol[PIPE_CHUNKS];
+    for (int k = 0; k <= P.nchunks; k++)
+        MLAMG_CUDA(cudaMemcpyAsync(&ptr_host[k], A.rowptr + P.row_lo[k], sizeof(int), cudaMemcpyDeviceToHost, s));
+    Scratch d(PIPE_CHUNKS * sizeof(int), s);
+    MLAMG_SCRATCH_OK(d);
+    MLAMG_CUDA(cudaMemsetAsync(d.p, 0xff, PIPE_CHUNKS * sizeof(int), s));      // -1
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < P.nchunks; k++) {
+        if (ptr_host[k + 1] > ptr_host[k]) {
+            range_max_kernel<<<148 * 4, 256, 0, s>>>(A.col, ptr_host[k], ptr_host[k + 1], d.as<int>() + k);
+            MLAMG_LAUNCHED();
+        }
+    }
+    MLAMG_CUDA(cudaMemcpyAsync(maxcol, d.p, PIPE_CHUNKS * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < P.nchunks; k++) {
+        int need = k;                                   // own rows of b (epilogue) at least
+        for (int j = 0; j < P.nchunks; j++)
+            if (maxcol[k] >= P.row_lo[j]) need = j > need ? j : need;
+        P.need[k] = need;
+    }
+    P.ready = true;
     return MLAMG_OK;
 }
 
@@ -374,6 +472,11 @@ int mlamg_hierarchy_destroy(mlamg_hierarchy_t h) {
     if (h->host_x) cudaFree(h->host_x);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->pipe.cs) {
+        cudaStreamDestroy(h->pipe.cs);
+        cudaEventDestroy(h->pipe.fork);
+        for (int k = 0; k < PIPE_CHUNKS; k++) { cudaEventDestroy(h->pipe.in_ev[k]); cudaEventDestroy(h->pipe.out_ev[k]); }
+    }
     delete h;
     return MLAMG_OK;
 }
@@ -499,16 +602,49 @@ int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int
     cudaStream_t s = as_stream(stream);
     if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
     if (cycles < 1) return set_error(MLAMG_EINVAL, "vcycle_host: cycles < 1");
+    if (nu1 < 0 || nu2 < 0) return set_error(MLAMG_EINVAL, "negative sweep count");
     const size_t bytes = (size_t)h->lv[0].A.n * h->esz;
     if (!h->host_b) {
         MLAMG_CUDA(cudaMalloc(&h->host_b, bytes));
         MLAMG_CUDA(cudaMalloc(&h->host_x, bytes));
     }
-    MLAMG_CUDA(cudaMemcpyAsync(h->host_b, b_host, bytes, cudaMemcpyHostToDevice, s));
-    MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 1, s));
-    for (int c = 1; c < cycles; c++) MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 0, s));
-    MLAMG_CUDA(cudaMemcpyAsync(x_host, h->host_x, bytes, cudaMemcpyDeviceToHost, s));
-    MLAMG_CUDA(cudaStreamSynchronize(s));
+    if (cycles > 1 || h->lv.size() < 2) {      // several cycles: the copies are a small share, keep the graph replay
+        MLAMG_CUDA(cudaMemcpyAsync(h->host_b, b_host, bytes, cudaMemcpyHostToDevice, s));
+        MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 1, s));
+        for (int c = 1; c < cycles; c++) MLAMG_TRY(vcycle_run(h, h->host_b, h->host_x, nu1, nu2, 0, s));
+        MLAMG_CUDA(cudaMemcpyAsync(x_host, h->host_x, bytes, cudaMemcpyDeviceToHost, s));
+        MLAMG_CUDA(cudaStreamSynchronize(s));
+        return MLAMG_OK;
+    }
+    // one preconditioner apply (PETSc PCApply shape): chunked H2D -> first pass per chunk ... last pass per chunk -> chunked D2H
+    MLAMG_TRY(ensure_pipe(h, s));
+    HostPipe &P = h->pipe;
+    MLAMG_CUDA(cudaEventRecord(P.fork, s));
+    MLAMG_CUDA(cudaStreamWaitEvent(P.cs, P.fork, 0));
+    for (int k = 0; k < P.nchunks; k++) {
+        const size_t off = (size_t)P.row_lo[k] * h->esz, len = (size_t)(P.row_lo[k + 1] - P.row_lo[k]) * h->esz;
+        MLAMG_CUDA(cudaMemcpyAsync((char *)h->host_b + off, (const char *)b_host + off, len, cudaMemcpyHostToDevice, P.cs));
+        MLAMG_CUDA(cudaEventRecord(P.in_ev[k], P.cs));
+    }
+    const LevelData &l0 = h->lv[0];
+    const bool chunk_in = nu1 == 1 && l0.val_scaled && !l0.sell_ptr;      // = the fused first pass of vcycle_enqueue
+    if (!chunk_in) MLAMG_CUDA(cudaStreamWaitEvent(s, P.in_ev[P.nchunks - 1], 0));
+    int rc = MLAMG_OK;
+    if (chunk_in) {
+        MLAMG_DISPATCH(h->dtype, rc = vcycle_enqueue<T>(h, (const T *)h->host_b, (T *)h->host_x, nu1, nu2, 1, s, &P, (char *)x_host));
+    } else {
+        MLAMG_DISPATCH(h->dtype, rc = vcycle_enqueue<T>(h, (const T *)h->host_b, (T *)h->host_x, nu1, nu2, 1, s, nullptr, nullptr));
+        if (rc == MLAMG_OK) {
+            MLAMG_CUDA(cudaEventRecord(P.out_ev[0], s));
+            MLAMG_CUDA(cudaStreamWaitEvent(P.cs, P.out_ev[0], 0));
+            MLAMG_CUDA(cudaMemcpyAsync(x_host, h->host_x, bytes, cudaMemcpyDeviceToHost, P.cs));
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s);
+    cudaError_t e2 = cudaStreamSynchronize(P.cs);
+    if (rc != MLAMG_OK) return rc;
+    if (e1 != cudaSuccess) return set_cuda_error(e1, __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return set_cuda_error(e2, __FILE__, __LINE__);
     return MLAMG_OK;
 }
 
