@@ -175,8 +175,14 @@ def run_ours(args):
     v = 8
     r_ = torch.empty_like(b); t_ = torch.empty_like(b)
     ec = torch.randn(Nc, dtype=torch.float64, device="cuda"); bc = torch.empty_like(ec)
-    ops = [("csr_rowop_kernel<double,LANES=1,OP_RESZERO> (fine level: x=dw.*b, r=b-Ax fused, one pass over A)",
-            lambda: core.jacobi_zero_residual(A0, dw0, b, t_, r_), A0.nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
+    if H._scaled:
+        vs0 = H._scaled[0]
+        first = ("csr_rowop_kernel<double,LANES=1,OP_RESZERO_S> (fine level: x=dw.*b, r=b-(A D_w)b fused, one pass over A)",
+                 lambda: core.jacobi_zero_residual_scaled(A0, vs0, dw0, b, t_, r_), A0.nnz * (v + 4) + 4 * (N + 1) + 4 * v * N)
+    else:
+        first = ("csr_rowop_kernel<double,LANES=1,OP_RESZERO> (fine level: x=dw.*b, r=b-Ax fused, one pass over A)",
+                 lambda: core.jacobi_zero_residual(A0, dw0, b, t_, r_), A0.nnz * (v + 4) + 4 * (N + 1) + 4 * v * N)
+    ops = [first,
            ("csr_rowop_kernel<double,LANES=8,OP_SPMV> (fine level: restriction b_c = R r)",
             lambda: core.spmv(R0, r_, bc), P0.nnz * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc)]
     if H._Q:
@@ -210,7 +216,8 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
         try:
-            key = "reszero_fine_bytes_per_launch" if "OP_RESZERO" in dom["kernel"] else "jacobi_fine_bytes_per_launch"
+            key = ("reszero_scaled_fine_bytes_per_launch" if "OP_RESZERO_S" in dom["kernel"] else
+                   "reszero_fine_bytes_per_launch" if "OP_RESZERO" in dom["kernel"] else "jacobi_fine_bytes_per_launch")
             roofline["traffic"] = json.load(open(tr)).get(key)
         except Exception:
             pass
@@ -313,7 +320,8 @@ def run_ours_distributed(args, rank, world, local):
     for k in range(args.steps):
         cycle()
         ev[k][0].record()
-        L0.A.rowop(4, None, L0.r, b=b, dw=L0.dw, aux=L0.x[1], row_range=interior)    # interior rows: no halo column
+        L0.A.rowop(6 if hasattr(L0.A, "csr_scaled") else 4, None, L0.r, b=b, dw=L0.dw, aux=L0.x[1],
+                   row_range=interior)                                                # interior rows: no halo column
         ev[k][1].record()
     torch.cuda.synchronize()
     jac_ms = float(np.mean([a.elapsed_time(c) for a, c in ev]))
@@ -360,7 +368,7 @@ def run_ours_distributed(args, rank, world, local):
                "e2e": {"value": round(N_loc * world / e2e_s / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": N_loc * 8 * world,
                        "d2h_bytes_per_step": N_loc * 8 * world, "ms_per_step": round(e2e_s * 1e3, 3)},
                "gpu_launches": kernels_per_cycle * args.steps * world, "kernels_per_cycle_per_rank": kernels_per_cycle,
-               "roofline": {"bound": "hbm", "kernel": "csr_rowop_kernel<double,LANES=1,OP_RESZERO> (fine level: x=dw.*b, r=b-Ax fused, one pass over A; rank 0)",
+               "roofline": {"bound": "hbm", "kernel": "csr_rowop_kernel<double,LANES=1,OP_RESZERO_S> (fine level: x=dw.*b, r=b-(A D_w)b fused, one pass over A; interior rows of rank 0)",
                             "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": None, "ms_per_launch": round(jac_ms, 4),
                             "algorithmic_bytes_per_launch": B_jac, "cycle_bytes_per_gpu": cyc_bytes,

@@ -84,6 +84,12 @@ int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *
 int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                              const void *e, const void *x_in, const void *r, const void *dw, void *x_out,
                              mlamg_stream_t stream);
+/* x_out = dw .* (rhs + r) + Q e: mlamg_prolong_smooth_csr when x_in is the zero-guess sweep dw.*rhs itself and
+ * r = rhs - A x_in (e.g. from mlamg_residual_csr on the column-scaled values with x = b = rhs): x_in is never
+ * materialised. */
+int mlamg_prolong_smooth_zero_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                                  const void *e, const void *rhs, const void *r, const void *dw, void *x_out,
+                                  mlamg_stream_t stream);
 /* x = dw .* b  (first sweep from a zero guess: no pass over A) */
 int mlamg_jacobi_zero(int dtype, int n, const void *dw, const void *b, void *x, mlamg_stream_t stream);
 /* smoother diagonal: mode 0 -> omega / a_ii, mode 1 -> 1 / sum_j |a_ij| (omega ignored) */
@@ -101,8 +107,8 @@ int mlamg_sell_rowop(int dtype, int op, int n, const int *slice_ptr, const int *
 /* generic row-op over the row range [row_begin, row_begin + nrows) (row_list == NULL) or the listed rows
  * row_list[0..nrows):
  * op 0 y=Ax | 1 y+=Ax | 2 y=b-Ax (+*norm2) | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) (x unused) |
- * 5 y=aux+dw.*b+Ax (aux may alias y) | 6 = op 4 with val holding a_ij*dw_j (gathers b alone).  aux is NULL
- * for ops 0-3.
+ * 5 y=aux+dw.*b+Ax (aux may alias y) | 6 = op 4 with val holding a_ij*dw_j (gathers b alone) |
+ * 7 y=dw.*(aux+b)+Ax.  aux is NULL for ops 0-3.
  * Used by the row-partitioned multi-GPU levels to run interior rows while the halo exchange of x is in
  * flight, then the boundary rows. */
 int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowptr, const int *col, const void *val,

@@ -17,7 +17,11 @@ namespace mlamg {
 // precomputed at setup: one pass over Q instead of a pass over P and a pass over A.
 // OP_RESZERO_S: OP_RESZERO on the column-scaled operator A D_w (values a_ij * dw_j, built once at setup): the
 // gathers read b[c] alone — r = b - (A D_w) b — so the pass runs at the speed of a plain residual.
-enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4, OP_PSMOOTH = 5, OP_RESZERO_S = 6 };
+// OP_PSMOOTH0: OP_PSMOOTH when the iterate before the correction is the zero-guess sweep x = dw.*b itself:
+// y = dw.*(b + r) + Q e.  The pass on the way down then is a plain residual on the scaled copy, r = b - (A D_w) b,
+// that neither stores x nor reads dw (two vectors less traffic per level).
+enum { OP_SPMV = 0, OP_SPMV_ADD = 1, OP_RESIDUAL = 2, OP_JACOBI = 3, OP_RESZERO = 4, OP_PSMOOTH = 5, OP_RESZERO_S = 6,
+       OP_PSMOOTH0 = 7 };
 
 constexpr int ROW_THREADS = 256;
 
@@ -41,6 +45,8 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
         if (NORM) rr = (double)r * (double)r;
     } else if (OP == OP_PSMOOTH) {   // y2 = x before the correction (may alias y), b = residual
         y[row] = y2[row] + dw[row] * b[row] + sum;
+    } else if (OP == OP_PSMOOTH0) {  // y2 = right-hand side, b = residual of x = dw.*rhs
+        y[row] = dw[row] * (y2[row] + b[row]) + sum;
     } else {  // OP_JACOBI
         y[row] = x[row] + dw[row] * (b[row] - sum);
     }
@@ -414,6 +420,24 @@ int psmooth_t(int n, long long nnz, const int *rowptr, const int *col, const T *
     return launch_rowop<T, OP_PSMOOTH, false>(n, nnz, rowptr, col, val, e, r, dw, x_out, nullptr, s, nullptr, 0, nullptr,
                                               const_cast<T *>(x_in));
 }
+// x_out = dw .* (rhs + r) + Q e
+template <typename T>
+int psmooth0_range_t(int nrows, int row0, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *e,
+                     const T *rhs, const T *r, const T *dw, T *x_out, cudaStream_t s) {
+    return launch_rowop<T, OP_PSMOOTH0, false>(nrows, nnz_hint, rowptr, col, val, e, r, dw, x_out, nullptr, s, nullptr, row0,
+                                               nullptr, const_cast<T *>(rhs));
+}
+template int psmooth0_range_t<float>(int, int, long long, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
+template int psmooth0_range_t<double>(int, int, long long, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
+// r = b - A x over the row range (the scaled-copy residual of the chunked host pipeline)
+template <typename T>
+int residual_range_t(int nrows, int row0, long long nnz_hint, const int *rowptr, const int *col, const T *val, const T *x,
+                     const T *b, T *r, cudaStream_t s) {
+    return launch_rowop<T, OP_RESIDUAL, false>(nrows, nnz_hint, rowptr, col, val, x, b, nullptr, r, nullptr, s, nullptr, row0);
+}
+template int residual_range_t<float>(int, int, long long, const int *, const int *, const float *, const float *, const float *, float *, cudaStream_t);
+template int residual_range_t<double>(int, int, long long, const int *, const int *, const double *, const double *, const double *, double *, cudaStream_t);
+
 // row-range forms (rows [row0, row0 + nrows)) used by the host-buffer entry point to pipeline the first and the last
 // fine-level pass with the PCIe copies
 template <typename T>
@@ -630,6 +654,17 @@ int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *
     return MLAMG_OK;
 }
 
+int mlamg_prolong_smooth_zero_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
+                                  const void *e, const void *rhs, const void *r, const void *dw, void *x_out,
+                                  mlamg_stream_t stream) {
+    cudaStream_t s = as_stream(stream);
+    if (n < 0) return set_error(MLAMG_EINVAL, "prolong_smooth_zero: n < 0");
+    if (e == x_out || r == x_out || rhs == x_out) return set_error(MLAMG_EINVAL, "prolong_smooth_zero: aliased arguments");
+    MLAMG_DISPATCH(dtype, return psmooth0_range_t<T>(n, 0, nnz, rowptr, col, (const T *)val, (const T *)e, (const T *)rhs,
+                                                     (const T *)r, (const T *)dw, (T *)x_out, s));
+    return MLAMG_OK;
+}
+
 int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val, const void *e,
                              const void *x_in, const void *r, const void *dw, void *x_out, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
@@ -699,6 +734,12 @@ int mlamg_rowop_csr(int dtype, int op, int nrows, int nnz_hint, const int *rowpt
                                                                                (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
                                                                                row_begin, nullptr, (T *)aux)));
             break;
+        case OP_PSMOOTH0:      // aux = right-hand side; x = coarse correction, b = residual of dw.*rhs
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "rowop: op 7 needs aux = rhs");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH0, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
+                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                              row_begin, nullptr, (T *)aux)));
+            break;
         case OP_PSMOOTH:       // aux = x_in (may alias y); x = coarse correction, b = residual
             if (!aux) return set_error(MLAMG_EINVAL, "rowop: op 5 needs aux = x_in");
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
@@ -743,6 +784,12 @@ int mlamg_channel_rowop(mlamg_channel_t ch, int dtype, int op, int nrows, int nn
             MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_RESZERO_S, false>(nrows, nnz_hint, rowptr, col, (const T *)val, nullptr,
                                                                                (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
                                                                                row_begin, &hl, (T *)aux)));
+            break;
+        case OP_PSMOOTH0:      // aux = right-hand side
+            if (!aux || aux == y) return set_error(MLAMG_EINVAL, "channel_rowop: op 7 needs aux = rhs");
+            MLAMG_DISPATCH(dtype, return (launch_rowop<T, OP_PSMOOTH0, false>(nrows, nnz_hint, rowptr, col, (const T *)val, (const T *)x,
+                                                                              (const T *)b, (const T *)dw, (T *)y, nullptr, s, row_list,
+                                                                              row_begin, &hl, (T *)aux)));
             break;
         case OP_PSMOOTH:       // aux = x_in (may alias y)
             if (!aux) return set_error(MLAMG_EINVAL, "channel_rowop: op 5 needs aux = x_in");

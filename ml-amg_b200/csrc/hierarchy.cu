@@ -28,6 +28,11 @@ int reszero_t(int, long long, const int *, const int *, const T *, const T *, co
 template <typename T>
 int reszero_scaled_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
 template <typename T>
+int psmooth0_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *,
+                     cudaStream_t);
+template <typename T>
+int residual_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, T *, cudaStream_t);
+template <typename T>
 int psmooth_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *,
                     cudaStream_t);
 template <typename T>
@@ -132,6 +137,7 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
     }
     std::vector<T *> cur(L, nullptr);      // where level l's iterate currently lives
     std::vector<const T *> rhs(L, nullptr);
+    std::vector<char> lazy(L, 0);          // x = dw.*b of that level is never materialised (see below)
     rhs[0] = b;
     // ---- downward leg
     for (int l = 0; l < L - 1; l++) {
@@ -153,8 +159,21 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             // only for short rows (thread-per-row kernel): with several lanes per row the doubled gathers make the
             // kernel L1-bound (measured at 256^3, level 1, 30 entries/row: 70 us fused vs 56 us for the pair)
             fused = (nu1 == 1) && !lev.sell_ptr && (lev.val_scaled || (double)A.nnz <= 12.0 * (double)A.n);
-            if (fused && lev.val_scaled && l == 0 && pipe) {
+            // with Q on the way up, x = dw.*b is only an operand of  dw.*(b + r) + Q e : the pass on the way down is a plain
+            // residual on the scaled copy, r = b - (A D_w) b, that neither stores x nor reads dw
+            lazy[l] = fused && lev.val_scaled && lev.has_Q && nu2 > 0;
+            if (lazy[l] && l == 0 && pipe) {
                 for (int k = 0; k < pipe->nchunks; k++) {      // rows of chunk k as soon as their columns have arrived
+                    const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
+                    MLAMG_CUDA(cudaStreamWaitEvent(s, pipe->in_ev[pipe->need[k]], 0));
+                    MLAMG_TRY(residual_range_t<T>(cnt, lo, (long long)((double)A.nnz * cnt / A.n) + 1, A.rowptr, A.col,
+                                                  (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r, s));
+                }
+            } else if (lazy[l]) {
+                MLAMG_TRY(residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r,
+                                        nullptr, s));
+            } else if (fused && lev.val_scaled && l == 0 && pipe) {
+                for (int k = 0; k < pipe->nchunks; k++) {
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
                     MLAMG_CUDA(cudaStreamWaitEvent(s, pipe->in_ev[pipe->need[k]], 0));
                     MLAMG_TRY(reszero_scaled_range_t<T>(cnt, lo, (long long)((double)A.nnz * cnt / A.n) + 1, A.rowptr, A.col,
@@ -204,7 +223,12 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
             if (l == 0 && pipe && nu2 == 1 && o == x && x_host) {
                 for (int k = 0; k < pipe->nchunks; k++) {      // every finished chunk of the result goes to the D2H copy
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
-                    MLAMG_TRY(psmooth_range_t<T>(cnt, lo, (long long)((double)Q.nnz * cnt / Q.n) + 1, Q.rowptr, Q.col,
+                    const long long hint = (long long)((double)Q.nnz * cnt / Q.n) + 1;
+                    if (lazy[l])
+                        MLAMG_TRY(psmooth0_range_t<T>(cnt, lo, hint, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l],
+                                                      (const T *)lev.r, (const T *)lev.dw, o, s));
+                    else
+                    MLAMG_TRY(psmooth_range_t<T>(cnt, lo, hint, Q.rowptr, Q.col,
                                                  (const T *)Q.val, cur[l + 1], c, (const T *)lev.r, (const T *)lev.dw, o, s));
                     MLAMG_CUDA(cudaEventRecord(pipe->out_ev[k], s));
                     MLAMG_CUDA(cudaStreamWaitEvent(pipe->cs, pipe->out_ev[k], 0));
@@ -212,7 +236,10 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                                                cudaMemcpyDeviceToHost, pipe->cs));
                 }
                 x_host = nullptr;      // delivered
-            } else
+            } else if (lazy[l])
+                MLAMG_TRY(psmooth0_range_t<T>(Q.n, 0, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l], (const T *)lev.r,
+                                              (const T *)lev.dw, o, s));
+            else
             MLAMG_TRY(psmooth_t<T>(Q.n, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], c, (const T *)lev.r,
                                    (const T *)lev.dw, o, s));
             c = o;
@@ -509,8 +536,10 @@ double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int ze
             res = nnz * (v + 4) + 4 * (N + 1) + 4 * v * N;
         }
         double post = nu2 * b_jac + b_prolong;
-        if (lev.has_Q && nu2 > 0)     // fused prolongation + first post sweep: read Q, e, x, r, dw; write x
+        if (lev.has_Q && nu2 > 0)     // fused prolongation + first post sweep: read Q, e, x (or rhs), r, dw; write x
             post = (nu2 - 1) * b_jac + (double)lev.Q.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N;
+        if (zero && nu1 == 1 && !lev.sell_ptr && lev.val_scaled && lev.has_Q && nu2 > 0)
+            res = nnz * (v + 4) + 4 * (N + 1) + 2 * v * N;   // lazy x: r = b - (A D_w) b reads A', b and writes r
         total += pre + post + res + b_restrict;
     }
     const double nc = h->lv[L - 1].A.n;

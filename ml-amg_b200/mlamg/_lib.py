@@ -61,6 +61,7 @@ SIGNATURES = {
     "mlamg_poisson_csr_slab": (I, [I, I, I, I, I, I, P, P, P, P, P]),
     "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P]),
     "mlamg_prolong_smooth_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
+    "mlamg_prolong_smooth_zero_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_zero_residual_scaled_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_hierarchy_set_operator_scaled": (I, [P, I, P]),
     "mlamg_gather": (I, [I, I, P, P, P, P]),

@@ -230,7 +230,7 @@ def spmv_perm(A, x, row_order, out=None):
 
 def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None, aux=None):
     """generic row-op (0 y=Ax | 1 y+=Ax | 2 y=b-Ax | 3 y=x+dw.*(b-Ax) | 4 aux=dw.*b, y=b-A(dw.*b) | 5 y=aux+dw.*b+Ax |
-    6 = op 4 with A holding the column-scaled values a_ij*dw_j) over all rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
+    6 = op 4 with A holding the column-scaled values a_ij*dw_j | 7 y=dw.*(aux+b)+Ax) over all rows, the int32 list `rows`, or the contiguous range row_range=(begin, end)"""
     begin = 0
     if rows is not None:
         n = rows.numel()
@@ -243,6 +243,16 @@ def rowop(A, op, x, y, b=None, dw=None, rows=None, row_range=None, aux=None):
     check(lib.mlamg_rowop_csr(dt(A.val), op, n, max(1, int(A.nnz * n / max(A.shape[0], 1))), ptr(A.rowptr), ptr(A.col),
                               ptr(A.val), ptr(x), ptr(b), ptr(dw), ptr(y), ptr(aux), ptr(rows), begin, None, stream()))
     return y
+
+
+def prolong_smooth_zero(Q, e, rhs, r, dw, x_out=None):
+    """x_out = dw .* (rhs + r) + Q e — prolong_smooth when x_in is the zero-guess sweep dw.*rhs (never materialised)."""
+    n = Q.shape[0]
+    if x_out is None:
+        x_out = torch.empty_like(rhs)
+    check(lib.mlamg_prolong_smooth_zero_csr(dt(Q.val), n, Q.nnz, ptr(Q.rowptr), ptr(Q.col), ptr(Q.val), ptr(e), ptr(rhs), ptr(r),
+                                            ptr(dw), ptr(x_out), stream()))
+    return x_out
 
 
 def prolong_smooth(Q, e, x_in, r, dw, x_out=None):

@@ -470,7 +470,7 @@ class DistOperator:
         core.rowop(self._csr_for(op), op, x_ext, y, b=b, dw=dw, rows=rows, row_range=row_range, aux=aux)
 
     def _csr_for(self, op):
-        return self.csr_scaled if op == 6 else self.csr
+        return self.csr_scaled if op in (6, 8) else self.csr
 
     def build_scaled(self, dw):
         """column-scaled copy A D_w (op 6): dw of the halo columns comes from their owners (one exchange at setup)"""
@@ -487,14 +487,29 @@ class DistOperator:
         """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange.
         chan: peer-memory channel (push -> interior rows -> boundary rows reading the halo in place from the
         receive region; one stream, no collective); None: NCCL all-to-all on a side stream.
-        op 4 (x = dw.*b, y = b - A x): x_ext is the OUTPUT x, the neighbours receive dw.*b directly.
-        op 5 (y = aux + dw.*b + A x_ext): aux = iterate before the correction, b = residual, x_ext = coarse correction."""
+        op 4 / 6 (x = dw.*b, y = b - A x; 6 on the column-scaled copy): x_ext is the OUTPUT x, the neighbours receive
+        dw.*b (4) or b (6) directly.
+        op 8 (y = b - (A D_w) b on the scaled copy, x never materialised): x_ext is ignored.
+        op 5 (y = aux + dw.*b + A x_ext): aux = iterate before the correction, b = residual, x_ext = coarse correction.
+        op 7 (y = dw.*(aux + b) + A x_ext): aux = right-hand side, b = residual of dw.*rhs."""
         plan = self.plan
         xin = None if op in (4, 6) else x_ext      # gather vector (ops 4/6 gather b instead)
         if op in (4, 6):
             aux = x_ext
+        kop = op
+        if op == 8:                                # plain residual kernel on the scaled values, gathering b
+            kop, xin = 2, b
         if plan.comm.world == 1:
-            self.rowop(op, xin, y, b, dw, aux=aux)
+            core.rowop(self._csr_for(op), kop, xin, y, b=b, dw=dw, aux=aux)
+            return
+        if chan is not None and op == 8:
+            chan.push(b)
+            split = overlap and self.peer_split_ok
+            A = self.csr_scaled
+            if split:
+                core.rowop(A, 2, b, y, b=b, row_range=self.interior_range, rows=None if self.interior_range is not None
+                           else self.interior)
+            chan.rowop(A, 2, b, self.n_cols_own, y, b=b, rows=self.boundary if split else None)
             return
         if chan is not None:
             n_own = self.n_cols_own
@@ -517,7 +532,7 @@ class DistOperator:
                 chan.unpack(x_ext[n_own:n_own + plan.n_halo])
                 self.rowop(op, xin, y, b, dw, rows=rows, aux=aux)
             return
-        if op in (4, 6):
+        if op in (4, 6, 8):
             raise ValueError("the fused zero-guess sweep + residual needs the peer transport (halo columns of b, dw)")
         if not overlap or comm_stream is None or not self.overlap_ok:
             plan.exchange(x_ext, self.n_cols_own)
@@ -783,7 +798,11 @@ class DistHierarchy:
             c = xa
             scaled = self.fuse_pre and hasattr(L.A, "csr_scaled")
             fused = nu1 == 1 and (chans is not None or comm.world == 1) and (scaled or L.A.csr.nnz <= 12 * n)
-            if fused:      # x = dw.*b and r = b - A x in one pass over A (x is never read back)
+            # with Q on the way up x = dw.*b is never materialised: r = b - (A D_w) b, then x1 = dw.*(b + r) + Q e
+            L.lazy = fused and scaled and L.Q is not None and nu2 > 0
+            if L.lazy:
+                L.A.apply(8, None, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
+            elif fused:    # x = dw.*b and r = b - A x in one pass over A (x is never read back)
                 L.A.apply(6 if scaled else 4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
             elif nu1 > 0:
                 core.jacobi_zero(L.dw, rhs, c[:n])
@@ -819,7 +838,10 @@ class DistHierarchy:
             if L.Q is not None and nu2 > 0:
                 # x + P e followed by one sweep == x + dw.*r + Q e (r is still in L.r): one pass over Q
                 o = target if nu2 == 1 else (xb if c is xa else xa)
-                L.Q.apply(5, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=c)
+                if L.lazy:
+                    L.Q.apply(7, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=rhs_l)
+                else:
+                    L.Q.apply(5, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=c)
                 c = o
                 k0 = 1
             else:
@@ -923,6 +945,8 @@ class DistHierarchy:
             pre = (nu1 - 1) * b_jac + 3 * v * N if nu1 > 0 else 0
             if nu1 == 1 and (self.fuse_pre or nnz <= 12 * N) and (self.halo == "peer" or self.comm.world == 1):
                 pre, b_res = 0, b_jac          # fused x = dw.*b, r = b - A x: read A, b, dw; write x, r
+                if self.fuse_pre and L.Q is not None and nu2 > 0:
+                    b_res = nnz * (v + 4) + 4 * (N + 1) + 2 * v * N      # lazy x: read A D_w, b; write r
             post = nu2 * b_jac + (pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)
             if L.Q is not None and nu2 > 0:   # fused prolongation + first post sweep: read Q, e, x, r, dw; write x
                 post = (nu2 - 1) * b_jac + L.Q.csr.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N

@@ -312,7 +312,7 @@ def test_spmv_row_order_is_result_invariant():
     assert torch.equal(y0, y1)
 
 
-@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_rowop_on_row_subset(op):
     """interior / boundary splits of the multi-GPU levels: only the listed rows are touched"""
     from mlamg import core
@@ -326,12 +326,12 @@ def test_rowop_on_row_subset(op):
     yd = dev(y0, np.float64)
     xd = dev(x, np.float64)
     zd = dev(z0, np.float64)
-    aux = {4: xd, 6: xd, 5: zd}.get(op)     # ops 4/6: aux = x_out; op 5: aux = iterate before the correction
+    aux = {4: xd, 6: xd, 5: zd, 7: zd}.get(op)     # ops 4/6: aux = x_out; op 5: aux = iterate before the correction; 7: rhs
     Aop = Ad.with_values(mlamg.scaled_values(Ad, dev(dw, np.float64))) if op == 6 else Ad
     core.rowop(Aop, op, None if op in (4, 6) else xd, yd, b=dev(b, np.float64), dw=dev(dw, np.float64),
                rows=torch.from_numpy(rows).cuda(), aux=aux)
     full = {0: A @ x, 1: y0 + A @ x, 2: b - A @ x, 3: x + dw * (b - A @ x), 4: b - A @ (dw * b), 5: z0 + dw * b + A @ x,
-            6: b - A @ (dw * b)}[op]
+            6: b - A @ (dw * b), 7: dw * (z0 + b) + A @ x}[op]
     if op in (4, 6):     # x is an output here: the listed rows receive dw.*b, the others keep their content
         xr = x.copy()
         xr[rows] = (dw * b)[rows]
@@ -372,3 +372,12 @@ def test_prolong_smooth_equals_prolong_then_sweep(dtype):
     inplace = xd.clone()
     mlamg.prolong_smooth(Q, ed, inplace, r, dev(dw, dtype), x_out=inplace)
     assert torch.equal(inplace, fused)
+    # zero-guess form: x_in = dw.*b is never materialised; r comes from a plain residual on the scaled copy
+    Ads = Ad.with_values(mlamg.scaled_values(Ad, dev(dw, dtype)))
+    r0 = mlamg.residual(Ads, bd, bd)
+    x0 = (dw * b).astype(dtype)
+    close(r0, b64 - A64 @ x0.astype(np.float64), dtype, np.abs(b64).max() + (abs(A64) @ np.abs(x0.astype(np.float64))).max())
+    z = mlamg.prolong_smooth_zero(Q, ed, bd, r0, dev(dw, dtype))
+    xp = x0.astype(np.float64) + P64 @ e.astype(np.float64)
+    ref0 = xp + dw.astype(np.float64) * (b64 - A64 @ xp)
+    close(z, ref0, dtype, np.abs(ref0).max() * 10)
