@@ -42,6 +42,11 @@ void count_launch(int n = 1);
 static inline cudaStream_t as_stream(mlamg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+// The default memory pool returns everything to the driver at every synchronisation point unless its release
+// threshold is raised: a PCG iteration (three host syncs for its dot products) then re-maps its scratch buffers from
+// scratch each time (measured: 68 ms per iteration at 128^3 instead of well under 1 ms).  Called once per device.
+void keep_pool_memory();
+
 // Stream-ordered scratch allocation (cudaMallocAsync pool: no device sync after warm-up).
 struct Scratch {
     void *p = nullptr;
@@ -51,6 +56,7 @@ struct Scratch {
     // otherwise become two extra nodes per kernel inside a captured CUDA graph)
     Scratch(size_t bytes, cudaStream_t stream) : s(stream) {
         if (bytes == (size_t)-1) return;
+        keep_pool_memory();
         err = cudaMallocAsync(&p, bytes ? bytes : 16, s);
         if (err != cudaSuccess) p = nullptr;
     }

@@ -26,6 +26,20 @@ int set_cuda_error(cudaError_t e, const char *file, int line) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+void keep_pool_memory() {
+    static std::atomic<unsigned long long> done{0};      // bit per device ordinal (< 64)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (done.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done.fetch_or(bit, std::memory_order_relaxed);
+}
+
 // ------------------------------------------------------------------ exclusive scan (int32)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
