@@ -238,26 +238,57 @@ def plan_channels(specs, comm):
     return {"nbytes": max(off, _ALIGN), "region": region, "remote": remote}
 
 
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC windows could not be set up on every rank (raised on ALL ranks together)"""
+
+
 class PeerWindow:
-    """One cudaMalloc block per rank, exported with CUDA IPC and mapped by every peer (collective)."""
+    """One cudaMalloc block per rank, exported with CUDA IPC and mapped by every peer (collective).
+    Failures are detected collectively: either every rank gets a usable window or every rank raises PeerUnavailable."""
 
     def __init__(self, comm, nbytes):
         self.comm = comm
         self.nbytes = int(nbytes)
+        self.base, self.ptrs = None, []
         p = ctypes.c_void_p()
         h = ctypes.create_string_buffer(64)
-        check(lib.mlamg_peer_alloc(self.nbytes, ctypes.byref(p), h))
-        self.base = p.value
-        handles = comm.all_gather_obj(h.raw)       # every window is allocated and zeroed before anyone maps it
-        self.ptrs = []
-        for r, raw in enumerate(handles):
-            if r == comm.rank:
-                self.ptrs.append(self.base)
-            else:
-                q = ctypes.c_void_p()
-                check(lib.mlamg_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)))
-                self.ptrs.append(q.value)
+        err = None
+        try:
+            if _os.environ.get("MLAMG_TEST_PEER_FAIL") == str(comm.rank):      # failure injection for the fallback test
+                raise RuntimeError("injected failure (MLAMG_TEST_PEER_FAIL)")
+            check(lib.mlamg_peer_alloc(self.nbytes, ctypes.byref(p), h))
+            self.base = p.value
+        except Exception as exc:                                   # noqa: BLE001
+            err = f"rank {comm.rank}: {exc}"
+        handles = comm.all_gather_obj(None if err else h.raw)      # every window is allocated and zeroed before anyone maps it
+        if any(x is None for x in handles):
+            self._release_local()
+            raise PeerUnavailable(err or "a peer could not allocate its window")
+        opened = []
+        try:
+            for r, raw in enumerate(handles):
+                if r == comm.rank:
+                    self.ptrs.append(self.base)
+                else:
+                    q = ctypes.c_void_p()
+                    check(lib.mlamg_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)))
+                    self.ptrs.append(q.value)
+                    opened.append(q.value)
+        except Exception as exc:                                   # noqa: BLE001
+            err = f"rank {comm.rank}: {exc}"
+        oks = comm.all_gather_obj(err is None)
+        if not all(oks):
+            for q in opened:
+                lib.mlamg_peer_close(ctypes.c_void_p(q))
+            comm.barrier()
+            self._release_local()
+            raise PeerUnavailable(err or "a peer could not map the windows")
         comm.barrier()
+
+    def _release_local(self):
+        if self.base is not None:
+            lib.mlamg_peer_free(ctypes.c_void_p(self.base))
+        self.base, self.ptrs = None, []
 
     def close(self):
         """collective: unmap the peers' windows, then free the local one"""
@@ -770,7 +801,13 @@ class DistHierarchy:
             self._tail_unpack_idx = torch.cat(
                 [torch.cat([torch.arange(int(offs[r]), int(offs[r + 1]), dtype=torch.int32), torch.tensor([-1], dtype=torch.int32)])
                  for r in range(self.comm.world)]).cuda().contiguous()
-            cs = self._chansets[(nu1, nu2)] = ChannelSet(self.comm, specs)
+            try:
+                cs = self._chansets[(nu1, nu2)] = ChannelSet(self.comm, specs)
+            except PeerUnavailable as exc:        # raised on every rank together: use the NCCL transport instead
+                if self.comm.rank == 0:
+                    print(f"mlamg: peer-memory halo transport unavailable ({exc}); using the NCCL all-to-all", flush=True)
+                self.halo = "nccl"
+                return None
         return cs
 
     def check_exchange(self):

@@ -12,10 +12,10 @@ from helpers import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(nproc, n):
+def _run(nproc, n, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "dist_check.py"), str(n)]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
 
 
 def test_dist_hierarchy_world1_matches_partitioned_oracle():
@@ -28,3 +28,12 @@ def test_dist_hierarchy_world1_matches_partitioned_oracle():
 def test_dist_hierarchy_world2_matches_partitioned_oracle():
     out = _run(2, 12)
     assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_transport_failure_on_one_rank_falls_back_to_nccl_everywhere():
+    """a rank that cannot export its window makes EVERY rank switch to the NCCL transport (collective detection);
+    results still match the partitioned oracle"""
+    out = _run(2, 10, env={"MLAMG_TEST_PEER_FAIL": "1"})
+    assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "peer transport unavailable" in out.stdout
