@@ -67,7 +67,8 @@ int mlamg_jacobi_csr(int dtype, int n, int nnz, const int *rowptr, const int *co
                      const void *dw, const void *b, const void *x_in, void *x_out,
                      mlamg_stream_t stream);
 /* x_out = dw .* b ; r = b - A x_out (+ *norm2 = ||r||^2 if norm2 != NULL): the first sweep from a zero guess
- * fused with the residual that follows it in the cycle — x is never read back from HBM, the gathers evaluate
+ * (MLAMG.py:143-146 with x = 0; loss.py:72) fused with the residual that follows it in the cycle (MLAMG.py:190-191,
+ * multigrid.py:181) — x is never read back from HBM, the gathers evaluate
  * dw[c]*b[c] on the fly. */
 int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                                    const void *dw, const void *b, void *x_out, void *r, double *norm2,
@@ -77,7 +78,8 @@ int mlamg_jacobi_zero_residual_csr(int dtype, int n, int nnz, const int *rowptr,
 int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *rowptr, const int *col,
                                           const void *val_scaled, const void *dw, const void *b, void *x_out,
                                           void *r, double *norm2, mlamg_stream_t stream);
-/* x_out = x_in + dw .* r + Q e  (x_out may alias x_in): prolongation fused with the first post-smoothing sweep.
+/* x_out = x_in + dw .* r + Q e  (x_out may alias x_in): prolongation (x += P e, MLAMG.py:191, multigrid.py:181)
+ * fused with the first post-smoothing sweep (MLAMG.py:192, :143-146).
  * With r = b - A x_in known (it was computed for the restriction),  (x_in + P e) followed by one sweep
  * x + dw.*(b - A x)  equals  x_in + dw.*r + Q e  with  Q = (I - D_w A) P  built once at setup — one pass over Q
  * replaces a pass over P and a pass over A.  (rowptr, col, val) is Q. */
