@@ -111,13 +111,14 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
+    import mlamg
+    from mlamg import core, distributed as md_
+    cpus = md_.bind_cpu_affinity(local)            # host buffers of this rank on the NUMA node of its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import mlamg
-    from mlamg import core
     n = args.n
     if world > 1:
-        return run_ours_distributed(args, rank, world, local)
+        return run_ours_distributed(args, rank, world, local, cpus)
     t_setup0 = time.time()
     A = mlamg.poisson((n, n, n), torch.float64)
     H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=RATIO, distance="unit", maxiter=10, rand=0,
@@ -261,7 +262,7 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-def run_ours_distributed(args, rank, world, local):
+def run_ours_distributed(args, rank, world, local, cpus=None):
     """Weak scaling: n^3 DOF per GPU, global grid n x n x (n*world) in z-slabs, row-partitioned levels with
     NCCL halo exchange overlapped with the interior rows, coarse levels replicated below 500k rows.
     value = global DOFs x cycles / max-over-ranks device time."""
@@ -379,7 +380,8 @@ def run_ours_distributed(args, rank, world, local):
                           "setup_s": round(setup_s, 2)},
                "vcycles_per_s": round(1e3 / ms, 2), "clocks": clk,
                "e2e": {"value": round(N_loc * world / e2e_s / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": N_loc * 8 * world,
-                       "d2h_bytes_per_step": N_loc * 8 * world, "ms_per_step": round(e2e_s * 1e3, 3)},
+                       "d2h_bytes_per_step": N_loc * 8 * world, "ms_per_step": round(e2e_s * 1e3, 3),
+                       "cpu_affinity_rank0": (f"{len(cpus)} cores local to the GPU" if cpus else "not set")},
                "gpu_launches": kernels_per_cycle * args.steps * world, "kernels_per_cycle_per_rank": kernels_per_cycle,
                "roofline": {"bound": "hbm", "kernel": "csr_rowop_kernel<double,LANES=1,OP_RESIDUAL> on the column-scaled copy (fine level: r = b - (A D_w) b, one pass over A; interior rows of rank 0)",
                             "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",

@@ -110,6 +110,29 @@ class Comm:
             dist.barrier(group=self.group)
 
 
+def bind_cpu_affinity(device_index):
+    """Pin this process to the CPU cores NVML reports as local to its GPU (one process per GPU): pinned host
+    buffers allocated afterwards land on the GPU's NUMA node, so the host<->device copies of several ranks do
+    not cross the socket interconnect.  Returns the core list, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:                                           # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (_os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = _os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            _os.sched_setaffinity(0, cpus)
+        return cpus or None
+    except Exception:                                               # noqa: BLE001
+        return None
+
+
 def partition_offsets(n_local, comm):
     counts = comm.all_gather_int(n_local)
     return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
