@@ -297,6 +297,15 @@ static int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int n
     return MLAMG_OK;
 }
 
+// turns CUDA-graph replay of the cycle on for the lifetime of a solver call (the host syncs of the dot products
+// would otherwise expose the launch time of every kernel of the cycle), restoring the caller's setting afterwards
+struct GraphScope {
+    mlamg_hierarchy *h;
+    bool saved;
+    explicit GraphScope(mlamg_hierarchy *hh) : h(hh), saved(hh->use_graph) { h->use_graph = true; }
+    ~GraphScope() { h->use_graph = saved; }
+};
+
 static int ensure_pcg(mlamg_hierarchy *h) {
     if (h->pcg_r) return MLAMG_OK;
     const size_t bytes = (size_t)h->lv[0].A.n * h->esz;
@@ -559,6 +568,7 @@ int mlamg_solve(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, d
     if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
     if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "solve: bad maxiter/res_host");
     MLAMG_TRY(ensure_pcg(h));
+    GraphScope graph_on(h);      // b and x are fixed across the iterations: every cycle after the first is one graph launch
     const Csr &A = h->lv[0].A;
     int it = 0;
     double nrm2 = 0.0;
@@ -583,6 +593,7 @@ int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, dou
     if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
     if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "pcg: bad maxiter/res_host");
     MLAMG_TRY(ensure_pcg(h));
+    GraphScope graph_on(h);      // the preconditioner is always applied to (r, z): one graph launch per iteration
     const Csr &A = h->lv[0].A;
     const int n = A.n, dt = h->dtype;
     void *r = h->pcg_r, *z = h->pcg_z, *p = h->pcg_p, *ap = h->pcg_ap;
