@@ -274,7 +274,7 @@ def run_ours(args):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(n, 1), "dof": N, "nnz": A0.nnz, "levels": [l.A.shape[0] for l in H.levels],
                       "operator_complexity": round(H.operator_complexity(), 4), "cycle": "V(1,1) zero-guess",
-                      "l2_policy": "inputs larger than L2 (fine operator 1.4 GB vs 126 MB L2)", "setup_s": round(setup_s, 2)},
+                      "l2_policy": f"inputs larger than L2 (fine operator {A0.nnz * 12 / 1e9:.1f} GB vs 126 MB L2)", "setup_s": round(setup_s, 2)},
            "vcycles_per_s": round(1e3 / ms, 2), "clocks": clk, "e2e": e2e, "gpu_launches": kernels_per_cycle * args.steps,
            "kernels_per_cycle": kernels_per_cycle, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(out))
