@@ -1,6 +1,5 @@
 """Mirror of the reference's `ns.lib.sparse_tensor` (/root/reference/ns/lib/sparse_tensor.py) without
 torch_sparse: spspmm -> hash SpGEMM kernel, spmm -> SpMM kernel, spT -> transpose kernel."""
-import numpy as np
 import scipy.sparse as sp
 import torch
 

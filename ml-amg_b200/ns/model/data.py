@@ -7,7 +7,6 @@ plotting helpers are out of scope — `mlamg.proble
 import bz2
 import pickle
 
-import numpy as np
 import scipy.sparse as sp
 import torch
 

@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, assert_csr_bitwise, rel_hist_err, hist_err0, canonical
+from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, assert_csr_bitwise, rel_hist_err, hist_err0
 from oracle import reference_path as rp, multilevel as oml, pyamg_restated as pr
 
 pytestmark = pytest.mark.gpu
