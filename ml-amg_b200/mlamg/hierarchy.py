@@ -266,9 +266,11 @@ class Hierarchy:
         return x
 
     def solve(self, b, x0=None, tol=1e-8, maxiter=100, nu1=1, nu2=1, cycle="V", accel=None, residuals=None,
-              return_residuals=False):
+              return_residuals=False, restart=30):
         """pyamg-style solve.  accel=None: stationary V-cycles until ||b-Ax|| <= tol*||b|| ;
-        accel='cg': V-cycle preconditioned CG.  Accepts numpy or CUDA tensors, returns the same kind."""
+        accel='cg': V-cycle preconditioned CG; accel='gmres': left-preconditioned restarted GMRES (the call of
+        ns/preconditioner/PyAMG.py:119; history = preconditioned residual norms, stop at tol*||M b||).
+        Accepts numpy or CUDA tensors, returns the same kind."""
         if cycle != "V":
             raise NotImplementedError("only V cycles are built on this path")
         is_np = isinstance(b, np.ndarray)
@@ -282,14 +284,78 @@ class Hierarchy:
                                   ctypes.byref(nit), stream()))
         elif accel == "cg":
             check(lib.mlamg_pcg(self._h, ptr(bd), ptr(xd), nu1, nu2, tol, maxiter, res, ctypes.byref(nit), stream()))
+        elif accel == "gmres":
+            hist = self._gmres(bd, xd, tol, maxiter, nu1, nu2, restart)
+            if residuals is not None:
+                residuals[:] = list(hist)
+            out = xd.cpu().numpy() if is_np else xd
+            return (out, hist) if return_residuals else out
         else:
-            raise NotImplementedError(f"accel={accel!r}: only None and 'cg' are built (the reference's gmres "
-                                      "acceleration lives in pyamg, PyAMG.py:119)")
+            raise NotImplementedError(f"accel={accel!r}: None, 'cg' and 'gmres' are built")
         hist = np.array(res[:nit.value + 1])
         if residuals is not None:
             residuals[:] = list(hist)
         out = xd.cpu().numpy() if is_np else xd
         return (out, hist) if return_residuals else out
+
+    def _gmres(self, b, x, tol, maxiter, nu1, nu2, restart):
+        """Left-preconditioned GMRES(restart), modified Gram-Schmidt + Givens; x updated in place.  The operator
+        applications (A v, one V-cycle per Krylov vector) and the dot products / updates run in libmlamg_b200.so;
+        the (restart+1) x restart Hessenberg lives on the host.  Same algorithm as oracle.multilevel.gmres."""
+        A = self.levels[0].A
+        n = A.shape[0]
+        t = torch.empty(n, dtype=self.dtype, device=b.device)
+
+        def precond_residual():
+            core.residual(A, x, b, out=t)
+            return self.vcycle(t, None, nu1, nu2)
+
+        nmb = float(torch.linalg.vector_norm(self.vcycle(b, None, nu1, nu2)).item())
+        stop = tol * (nmb if nmb != 0 else 1.0)
+        res, it = [], 0
+        while True:
+            r = precond_residual()
+            beta = float(np.sqrt(core.dot(r, r)))
+            if not res:
+                res.append(beta)
+            if beta <= stop or it >= maxiter:
+                break
+            m = min(int(restart), maxiter - it)
+            V = [r.mul_(1.0 / beta)]
+            Hm = np.zeros((m + 1, m))
+            cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+            g[0] = beta
+            k = 0
+            for j in range(m):
+                core.spmv(A, V[j], out=t)
+                w = self.vcycle(t, None, nu1, nu2)
+                for i in range(j + 1):
+                    Hm[i, j] = core.dot(w, V[i])
+                    core.axpby(-Hm[i, j], V[i], 1.0, w)
+                Hm[j + 1, j] = float(np.sqrt(core.dot(w, w)))
+                if Hm[j + 1, j] != 0.0:
+                    V.append(w.mul_(1.0 / Hm[j + 1, j]))
+                for i in range(j):
+                    tmp = cs[i] * Hm[i, j] + sn[i] * Hm[i + 1, j]
+                    Hm[i + 1, j] = -sn[i] * Hm[i, j] + cs[i] * Hm[i + 1, j]
+                    Hm[i, j] = tmp
+                d = np.hypot(Hm[j, j], Hm[j + 1, j])
+                cs[j], sn[j] = (1.0, 0.0) if d == 0.0 else (Hm[j, j] / d, Hm[j + 1, j] / d)
+                Hm[j, j] = cs[j] * Hm[j, j] + sn[j] * Hm[j + 1, j]
+                Hm[j + 1, j] = 0.0
+                g[j + 1] = -sn[j] * g[j]
+                g[j] = cs[j] * g[j]
+                it += 1
+                k = j + 1
+                res.append(abs(g[j + 1]))
+                if res[-1] <= stop or len(V) <= j + 1:
+                    break
+            y = np.linalg.solve(np.triu(Hm[:k, :k]), g[:k]) if k else np.zeros(0)
+            for i in range(k):
+                core.axpby(float(y[i]), V[i], 1.0, x)
+            if res[-1] <= stop:
+                break
+        return np.array(res)
 
     def solve_abs(self, b, x, tol_abs, maxiter, nu1=1, nu2=1):
         """Stationary iteration with an ABSOLUTE residual tolerance (MLAMG.py:189-195), device tensors."""

@@ -3,8 +3,9 @@
 Mirrors /root/reference/ns/preconditioner/PyAMG.py: _createAmgSolver :79-96
 (`pyamg.aggregation.smoothed_aggregation_solver(A, max_levels)`), _apply :118-120
 (`Amg.solve(b, tol=amg_rtol, accel='gmres')`).  Options: `pyamg_amg_rtol` 1e-8,
-`pyamg_amg_max_levels` 10, `pyamg_amg_precondition_with_gmres` (:52-54) — Krylov acceleration here
-is CG (`accel='cg'`); GMRES lives inside pyamg and is not part of the hot path.
+`pyamg_amg_max_levels` 10, `pyamg_amg_precondition_with_gmres` (:52-54).  The Krylov acceleration is the
+left-preconditioned restarted GMRES of `mlamg.Hierarchy.solve(accel='gmres')` (pyamg's own gmres is not
+available to pin it against; the algorithm is the one restated in oracle/multilevel.py).
 """
 import traceback
 
@@ -54,7 +55,7 @@ class PyAMG(PCBase):
 
     def _apply(self, pc, X, Y):
         y = self.Amg.solve(np.asarray(X.array_r), tol=self.amg_rtol, maxiter=200,
-                           accel=('cg' if self.amg_precon_krylov else None))
+                           accel=('gmres' if self.amg_precon_krylov else None))
         Y.setArray(y)
 
     def applyTranspose(self, pc, X, Y):

@@ -162,6 +162,64 @@ def pcg(levels, b, x0=None, tol=1e-8, maxiter=200, nu1=1, nu2=1):
     return x, np.array(res), it
 
 
+def gmres(levels, b, x0=None, tol=1e-8, maxiter=100, restart=30, nu1=1, nu2=1):
+    """Left-preconditioned restarted GMRES (modified Gram-Schmidt, Givens rotations), M^-1 = one V-cycle from a zero
+    guess — the shape of `Amg.solve(b, tol, accel='gmres')` at ns/preconditioner/PyAMG.py:119.  PARITY UNPINNED: pyamg's
+    own gmres (Householder by default) is not available; this restatement defines the algorithm the GPU path is held to.
+    History = norms of the PRECONDITIONED residual (entry 0 = initial); stops when it drops below tol*||M b||_2.
+    Returns (x, history, iterations)."""
+    A = levels[0].A
+    M = lambda v: vcycle(levels, v.copy(), None, nu1, nu2)
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    nmb = la.norm(M(b))
+    stop = tol * (nmb if nmb != 0 else 1.0)
+    res = []
+    it = 0
+    while True:
+        r = M(b - A @ x)
+        beta = la.norm(r)
+        if not res:
+            res.append(beta)
+        if beta <= stop or it >= maxiter:
+            break
+        m = min(restart, maxiter - it)
+        V = [r / beta]
+        H = np.zeros((m + 1, m))
+        cs, sn = np.zeros(m), np.zeros(m)
+        g = np.zeros(m + 1)
+        g[0] = beta
+        k = 0
+        for j in range(m):
+            w = M(A @ V[j])
+            for i in range(j + 1):
+                H[i, j] = w @ V[i]
+                w = w - H[i, j] * V[i]
+            H[j + 1, j] = la.norm(w)
+            if H[j + 1, j] != 0.0:
+                V.append(w / H[j + 1, j])
+            for i in range(j):
+                t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+                H[i, j] = t
+            d = np.hypot(H[j, j], H[j + 1, j])
+            cs[j], sn[j] = (1.0, 0.0) if d == 0.0 else (H[j, j] / d, H[j + 1, j] / d)
+            H[j, j] = cs[j] * H[j, j] + sn[j] * H[j + 1, j]
+            H[j + 1, j] = 0.0
+            g[j + 1] = -sn[j] * g[j]
+            g[j] = cs[j] * g[j]
+            it += 1
+            k = j + 1
+            res.append(abs(g[j + 1]))
+            if res[-1] <= stop or len(V) <= j + 1:
+                break
+        y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
+        for i in range(k):
+            x = x + y[i] * V[i]
+        if res[-1] <= stop:
+            break
+    return x, np.array(res), it
+
+
 # ------------------------------------------------------------------ problem generators
 def poisson(shape, dtype=np.float64):
     """Dirichlet (2*dim+1)-point Laplacian, lexicographic order with shape[0] (x) fastest,
