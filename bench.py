@@ -445,7 +445,29 @@ def cpu_baseline_same_hierarchy(H, b, x_gpu, cycles):
         oml.vcycle(levels, b.copy(), None, 1, 1)
         ts.append(time.perf_counter() - t0)
     N = levels[0].A.shape[0]
+    # the reference's own expressions on the fine level, best of 2: A@x (multigrid.py:181), the MLAMG.jacobi
+    # form x + Dinv*(b - A@x) (MLAMG.py:143-146), P.T@r and P@e (multigrid.py:181)
+    L0 = levels[0]
+    xv = np.random.RandomState(2).randn(N)
+    ec = np.random.RandomState(3).randn(L0.P.shape[1])
+
+    def best(fn, k=2):
+        out = []
+        for _ in range(k):
+            t0 = time.perf_counter(); fn(); out.append(time.perf_counter() - t0)
+        return min(out)
+    v = 8
+    nnz, pn, Nc = L0.A.nnz, L0.P.nnz, L0.P.shape[1]
+    ops = {"spmv": (lambda: L0.A @ xv, nnz * (v + 4) + 4 * (N + 1) + 2 * v * N),
+           "jacobi_sweep": (lambda: xv + L0.dw * (b - L0.A @ xv), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
+           "restrict": (lambda: L0.R @ xv, pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc),
+           "prolong_add": (lambda: xv + L0.P @ ec, pn * (v + 4) + 4 * (N + 1) + v * Nc + 2 * v * N)}
+    cpu_ops = {}
+    for name, (fn, nbytes) in ops.items():
+        t = best(fn)
+        cpu_ops[name] = {"ms": round(t * 1e3, 1), "GBs": round(nbytes / t / 1e9, 2)}
     return {"value": round(N / min(ts) / 1e9, 5), "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(),
+            "fine_level_ops_scipy": cpu_ops,
             "kind": "port", "sample": f"{len(ts)} full-size V(1,1) cycles of the oracle (scipy, single-threaded) on the "
             f"same hierarchy, best of {len(ts)}; {min(ts):.2f} s per cycle", "parity_rel_err_vs_gpu_cycle": rel}
 
