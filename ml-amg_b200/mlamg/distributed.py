@@ -221,7 +221,9 @@ class HaloPlan:
 # =====================================================================================================
 # split a row-op into interior / boundary rows around the wait only when the interior kernel is long
 # compared with the exchange latency (a few microseconds over NVLink)
-PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 30_000_000))
+PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 2_000_000))
+# 1: the push kernel runs on a side stream next to the interior rows (forked/joined inside the captured graph)
+PEER_FORK_PUSH = _os.environ.get("MLAMG_PEER_FORK_PUSH", "1") == "1"
 # 1: the consuming row-op reads halo values in place from the receive region; 0: unpack kernel + plain row-op
 PEER_INPLACE = _os.environ.get("MLAMG_PEER_INPLACE", "1") == "1"
 _ALIGN = 256
@@ -556,35 +558,33 @@ class DistOperator:
         if plan.comm.world == 1:
             core.rowop(self._csr_for(op), kop, xin, y, b=b, dw=dw, aux=aux)
             return
-        if chan is not None and op == 8:
-            chan.push(b)
-            split = overlap and self.peer_split_ok
-            A = self.csr_scaled
-            if split:
-                core.rowop(A, 2, b, y, b=b, row_range=self.interior_range, rows=None if self.interior_range is not None
-                           else self.interior)
-            chan.rowop(A, 2, b, self.n_cols_own, y, b=b, rows=self.boundary if split else None)
-            return
         if chan is not None:
             n_own = self.n_cols_own
-            if op == 4:
-                chan.push(b, scale=dw)
-            elif op == 6:
-                chan.push(b)
-            else:
-                chan.push(x_ext)
             split = overlap and self.peer_split_ok
-            if split:
-                if self.interior_range is not None:
-                    self.rowop(op, xin, y, b, dw, row_range=self.interior_range, aux=aux)
+            fork = split and PEER_FORK_PUSH and comm_stream is not None
+            main = torch.cuda.current_stream()
+            if fork:                   # the 4 us push kernel runs beside the interior rows instead of in front of them
+                comm_stream.wait_stream(main)
+            with torch.cuda.stream(comm_stream if fork else main):
+                if op == 4:
+                    chan.push(b, scale=dw)
+                elif op in (6, 8):
+                    chan.push(b)
                 else:
-                    self.rowop(op, xin, y, b, dw, rows=self.interior, aux=aux)
+                    chan.push(x_ext)
+            A = self._csr_for(op)
+            xk = b if op == 8 else xin
+            if split:
+                core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
+                           rows=None if self.interior_range is not None else self.interior)
+            if fork:
+                main.wait_stream(comm_stream)
             rows = self.boundary if split else None
-            if PEER_INPLACE or op in (4, 6):
-                chan.rowop(self._csr_for(op), op, xin, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
+            if PEER_INPLACE or op in (4, 6, 8):
+                chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             else:
                 chan.unpack(x_ext[n_own:n_own + plan.n_halo])
-                self.rowop(op, xin, y, b, dw, rows=rows, aux=aux)
+                core.rowop(A, kop, xk, y, b=b, dw=dw, rows=rows, aux=aux)
             return
         if op in (4, 6, 8):
             raise ValueError("the fused zero-guess sweep + residual needs the peer transport (halo columns of b, dw)")
@@ -631,7 +631,8 @@ class DistHierarchy:
         # Q = (I - D_w A) P per level: prolongation + first post-smoothing sweep as one pass (see Hierarchy)
         self.fuse_post = bool(fuse_post)
         self.fuse_pre = bool(fuse_pre)
-        self.comm_stream = torch.cuda.Stream() if comm.world > 1 else None
+        # high priority: the tiny push kernels forked onto it are scheduled ahead of the queued CTAs of the interior kernel
+        self.comm_stream = torch.cuda.Stream(priority=-1) if comm.world > 1 else None
         self.levels = []
         self.offsets = []
         lvl = 0
