@@ -117,3 +117,29 @@ def test_error_conventions():
         rp.lloyd_aggregation(A, ratio=0.5, rand="x")
     with pytest.raises(RuntimeError):
         rp.amg_2_v(A, A, np.zeros(36), np.zeros(36))
+
+
+def test_gmres_restatement_converges_and_matches_a_direct_solve():
+    """oracle.multilevel.gmres (the algorithm `accel='gmres'` is held to, parity unpinned against pyamg): preconditioned
+    residual norms never increase inside a restart cycle, the iterate converges to the direct solution, restarts and the
+    iteration cap behave, and an exact preconditioner converges in one step"""
+    import scipy.sparse.linalg as spla
+    A = oml.poisson((17, 15))
+    lv = oml.build_hierarchy(A, ratio=0.1, distance="unit", rand=0, lam_max=[2.0, 1.9, 1.8], max_coarse=20)
+    b = np.random.RandomState(5).randn(A.shape[0])
+    xd = spla.spsolve(sp.csc_matrix(A), b)
+    for restart in (30, 5):
+        x, res, it = oml.gmres(lv, b, tol=1e-10, maxiter=200, restart=restart)
+        assert it == len(res) - 1 and res[-1] <= 1e-10 * res[0] * 10
+        assert np.abs(x - xd).max() <= 1e-7 * np.abs(xd).max()
+        if restart == 30:
+            assert np.all(np.diff(res) <= 1e-12 * res[0])          # one cycle: monotone
+    x, res, it = oml.gmres(lv, b, tol=1e-10, maxiter=7, restart=5)
+    assert it == 7 and len(res) == 8
+    # GMRES needs no more iterations than the stationary V-cycle iteration it accelerates
+    _, res_s = oml.solve(lv, b, tol=1e-8, maxiter=200)
+    _, res_g, it_g = oml.gmres(lv, b, tol=1e-8, maxiter=200, restart=50)
+    assert it_g <= len(res_s) - 1
+    one = [lv[0]]                                                  # single level = exact coarse solve as the preconditioner
+    x, res, it = oml.gmres(one, b, tol=1e-10, maxiter=10)
+    assert it <= 1 and np.abs(x - xd).max() <= 1e-9 * np.abs(xd).max()
