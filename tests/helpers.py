@@ -7,6 +7,9 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["poisson2d_24_unit", "poisson3d_10_unit", "laplace3d_grid_abs", "laplace3d_grid_inv", "randw_same"]
+# shapes of BASELINE configs 3 and 4 (Voronoi jump coefficients, Delaunay P1), produced by the unmodified reference too;
+# held by the CPU oracle tests (the GPU path meets these shapes in tests/test_gpu_configs.py)
+GOLDEN_CASES_CONFIG_SHAPES = ["voronoi_jump_18_inv", "delaunay_600_abs"]
 
 
 def load_golden(name):

@@ -5,10 +5,10 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import pyamg_restated as pr, reference_path as rp, multilevel as oml
-from helpers import GOLDEN_CASES, load_golden, csr_from, assert_csr_close, rel_hist_err, grid_graph
+from helpers import GOLDEN_CASES, GOLDEN_CASES_CONFIG_SHAPES, load_golden, csr_from, assert_csr_close, rel_hist_err, grid_graph
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_CASES_CONFIG_SHAPES)
 def test_restated_path_matches_reference_golden(name):
     z = load_golden(name)
     A, C = csr_from(z, "A"), csr_from(z, "C")
