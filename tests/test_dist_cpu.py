@@ -132,6 +132,77 @@ def _worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
+def _worker3(rank, world, port, q):
+    """three ranks with unequal blocks: halo plans of a middle rank (two neighbours) and the window layout"""
+    try:
+        for p in (ROOT, os.path.join(ROOT, "ml-amg_b200")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from mlamg import distributed as md
+        comm = md.Comm()
+        A = sp.csr_matrix(oml.poisson((9, 14)))              # 5-point grid, x fastest: slabs in y
+        n = A.shape[0]
+        cut = [0, 27, 90, n]
+        lo, hi = cut[rank], cut[rank + 1]
+        Al = sp.csr_matrix(A[lo:hi])
+        col = torch.from_numpy(Al.indices.astype(np.int32))
+        offs = md.partition_offsets(hi - lo, comm)
+        assert list(offs) == cut
+        col_loc, halo = md.localize(col, hi - lo, lo)
+        plan = md.HaloPlan(halo, offs, comm)
+        assert plan.n_halo == (9 if rank in (0, 2) else 18)          # one grid line per neighbour
+        assert [c > 0 for c in plan.recv_counts] == [abs(r - rank) == 1 for r in range(world)]
+        assert plan.send_counts == plan.recv_counts                  # symmetric stencil
+        xg = np.random.RandomState(1).randn(n)
+        x_ext = torch.zeros(hi - lo + plan.n_halo, dtype=torch.float64)
+        x_ext[:hi - lo] = torch.from_numpy(xg[lo:hi])
+        plan.exchange(x_ext, hi - lo)
+        assert np.array_equal(x_ext[hi - lo:].numpy(), xg[halo.numpy()])
+        # window layout: a halo channel (16-byte slots) and the padded coarse gather (every pair connected)
+        sizes = [2, 0, 3]                                            # an EMPTY slice on rank 1
+        specs = [(plan.send_counts, plan.recv_counts, 16), ([sizes[rank] + 1] * world, [s_ + 1 for s_ in sizes], 16)]
+        lay = md.plan_channels(specs, comm)
+        tables = comm.all_gather_obj((lay["region"], lay["nbytes"]))
+        for p_ in range(world):
+            region_p, nbytes_p = tables[p_]
+            for c, (sc, rc, slot) in enumerate(specs):
+                if int(sc[p_]) == 0:
+                    continue
+                off0, off1 = lay["remote"][p_][c]
+                assert off0 % 16 == 0 and off1 - off0 == region_p[c][1] - region_p[c][0]
+                assert region_p[c][0] <= off0 and off0 + int(sc[p_]) * slot <= region_p[c][1] <= nbytes_p
+        # my own regions do not overlap and every sender's segment lies inside them, back to back in rank order
+        rg = lay["region"]
+        assert rg[0][0] == 0 and rg[0][1] <= rg[1][0] and rg[1][1] <= lay["nbytes"]
+        starts = comm.all_gather_obj([lay["remote"][p_][1][0] for p_ in range(world)])   # where each rank writes into p_
+        mine = [starts[s_][rank] for s_ in range(world)]
+        expect = rg[1][0]
+        for s_ in range(world):
+            assert mine[s_] == expect
+            expect += (sizes[s_] + 1) * 16
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+def test_halo_plans_and_window_layout_gloo_world3():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
 def test_distributed_plumbing_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
