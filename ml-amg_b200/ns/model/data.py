@@ -5,6 +5,7 @@ Only the container and the format are mirrored; the dataset generators (pyamg.ga
 plotting helpers are out of scope — `mlamg.problems` generates the named shapes.
 """
 import bz2
+import os
 import pickle
 
 import scipy.sparse as sp
@@ -53,6 +54,14 @@ class Grid:
         if isinstance(A, tuple):
             A = sp.csr_matrix(A)
         return Grid(A, loaded['x'], extra)
+
+
+def load_dir(directory):
+    """every `.grid` file of a directory (data.py:236-242), sorted by name so that dataset order is reproducible"""
+    return [Grid.load(os.path.join(directory, f)) for f in sorted(os.listdir(directory)) if '.grid' in f.lower()]
+
+
+Grid.load_dir = staticmethod(load_dir)
 
 
 def edge_list(A, with_values=True):

@@ -69,6 +69,9 @@ def test_grid_container_roundtrip_and_reference_fixture(tmp_path):
     assert os.path.exists(f + ".grid")
     h = Grid.load(f)
     assert (h.A != A).nnz == 0 and np.array_equal(h.x, x) and h.extra["dim"] == 2 and h.extra["filename"].endswith(".grid")
+    g.save(str(tmp_path / "a_second"))
+    both = Grid.load_dir(str(tmp_path))
+    assert [os.path.basename(x.extra["filename"]) for x in both] == ["a_second.grid", "t.grid"]
     ref = "/root/reference/demos/laplace_3d.grid"             # the reference's only bundled data file (build container only)
     if os.path.exists(ref):
         r = Grid.load(ref)
