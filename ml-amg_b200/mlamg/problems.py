@@ -73,20 +73,31 @@ def voronoi_jump_kappa(centroids, rng, n_seeds=None):
 
 
 # ------------------------------------------------------------------------------------------ assembly
-def p1_stiffness(pts, tris, kappa=None):
-    """P1 stiffness matrix (all nodes), kappa: None (Laplacian) or one value per triangle."""
+def p1_stiffness(pts, tris, kappa=None, tensor=None):
+    """P1 stiffness matrix (all nodes).  kappa: None (Laplacian) or one scalar per triangle; tensor: optional constant
+    symmetric 2x2 diffusion tensor K (a(u,v) = int grad u . K grad v, the rotated-anisotropic shape of
+    ns/model/data.py:301-347)."""
     p0, p1, p2 = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
     # gradients of the barycentric functions: g_i = rot90(edge opposite to i) / (2 area)
     e0, e1, e2 = p2 - p1, p0 - p2, p1 - p0
     area2 = e2[:, 0] * (-e1[:, 1]) - e2[:, 1] * (-e1[:, 0])          # 2 * signed area = cross(p1-p0, p2-p0)
     scale = (1.0 if kappa is None else np.asarray(kappa, dtype=np.float64)) / (2.0 * np.abs(area2))
     E = [e0, e1, e2]
+    if tensor is not None:
+        # grad phi_i = rot90(E_i) / (2 area): with G = rot90, g_i . K g_j = E_i . (G^T K G) E_j
+        K = np.asarray(tensor, dtype=np.float64)
+        G = np.array([[0.0, -1.0], [1.0, 0.0]])
+        M = G.T @ K @ G
     rows, cols, vals = [], [], []
     for i in range(3):
         for j in range(3):
             rows.append(tris[:, i])
             cols.append(tris[:, j])
-            vals.append(scale * (E[i][:, 0] * E[j][:, 0] + E[i][:, 1] * E[j][:, 1]))
+            if tensor is None:
+                vals.append(scale * (E[i][:, 0] * E[j][:, 0] + E[i][:, 1] * E[j][:, 1]))
+            else:
+                Ej = E[j] @ M.T
+                vals.append(scale * (E[i][:, 0] * Ej[:, 0] + E[i][:, 1] * Ej[:, 1]))
     n = pts.shape[0]
     A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
     A.sum_duplicates()
@@ -120,6 +131,39 @@ def voronoi_jump_problem(n_side=64, seed=0, mesh="structured", npts=None, n_seed
     A = sp.csr_matrix(A[order][:, order])
     A.sort_indices()
     return A, p[order], jumps
+
+
+def rotated_anisotropic_problem(n_side=64, epsilon=1e-2, theta=np.pi / 6, mesh="structured", npts=None, seed=0):
+    """2-D rotated-anisotropic diffusion K = Q diag(1, eps) Q^T (the reference's 'anisotropic' dataset,
+    ns/model/data.py:301-347, utils/create_data.py:62-68), P1, Dirichlet, Morton-ordered rows.  -> (A csr, pts)"""
+    if mesh == "structured":
+        pts, tris, bnd = structured_triangles(n_side, n_side)
+    else:
+        pts, tris, bnd = delaunay_triangles(npts or n_side * n_side, seed)
+    c, s_ = np.cos(theta), np.sin(theta)
+    Q = np.array([[c, -s_], [s_, c]])
+    K = Q @ np.diag([1.0, float(epsilon)]) @ Q.T
+    A, p = remove_dirichlet(p1_stiffness(pts, tris, None, tensor=K), pts, bnd)
+    order = morton_order(p)
+    A = sp.csr_matrix(A[order][:, order])
+    A.sort_indices()
+    return A, p[order]
+
+
+def poisson_1d(n, neumann=False, xdim=(0.0, 1.0)):
+    """1-D finite-difference Poisson matrices of ns/model/data.py:244-297 (Dirichlet: n interior points; Neumann: n
+    points with one-sided end rows), scaled by h^-2.  -> (A csr, x coordinates)"""
+    if not neumann:
+        x = np.linspace(xdim[0], xdim[1], n + 2)[1:-1]
+        h = abs(x[1] - x[0])
+        A = (sp.eye(n) * 2 - sp.eye(n, k=-1) - sp.eye(n, k=1)) * (h ** -2.)
+        return A.tocsr(), x
+    x = np.linspace(xdim[0], xdim[1], n)
+    h = abs(x[1] - x[0])
+    A = (sp.eye(n) * 2 - sp.eye(n, k=-1) - sp.eye(n, k=1)).tolil()
+    A[0, 0] = 1; A[0, 1] = -1
+    A[-1, -1] = 1; A[-1, -2] = -1
+    return (A.tocsr() * (h ** -2.)).tocsr(), x
 
 
 def delaunay_laplacian(npts, seed=0):

@@ -36,6 +36,28 @@ def test_voronoi_jump_and_delaunay_shapes():
     assert (half[:, 1].max() - half[:, 1].min()) < 0.75
 
 
+def test_rotated_anisotropic_and_1d_shapes():
+    from mlamg import problems
+    # tensor form reduces to the scalar form for K = kappa I, and to the axis-aligned anisotropic stencil for theta = 0
+    pts, tris, bnd = problems.structured_triangles(6, 6)
+    A_iso = problems.p1_stiffness(pts, tris, None)
+    assert abs(problems.p1_stiffness(pts, tris, None, tensor=np.eye(2)) - A_iso).max() < 1e-13
+    A, p = problems.rotated_anisotropic_problem(8, epsilon=0.01, theta=0.0)
+    d = np.sort(np.unique(np.round(A.data, 10)))
+    assert np.allclose(d, [-1.0, -0.01, 2.02])                       # -1 along x, -eps along y, 2(1+eps) on the diagonal
+    for theta in (0.3, np.pi / 4):
+        A, p = problems.rotated_anisotropic_problem(10, epsilon=1e-3, theta=theta)
+        assert abs(A - A.T).max() < 1e-12 and np.linalg.eigvalsh(A.toarray()).min() > 0
+    A, p = problems.rotated_anisotropic_problem(0, epsilon=0.1, theta=1.0, mesh="delaunay", npts=400)
+    assert abs(A - A.T).max() < 1e-12 and np.linalg.eigvalsh(A.toarray()).min() > 0
+    # 1-D generators (data.py:244-297)
+    A, x = problems.poisson_1d(9)
+    h = x[1] - x[0]
+    assert np.allclose(A.toarray()[4, 3:6] * h * h, [-1, 2, -1]) and A.shape == (9, 9)
+    A, x = problems.poisson_1d(9, neumann=True)
+    assert abs(np.asarray(A.sum(axis=1))).max() < 1e-9                # constants in the null space
+
+
 def test_morton_order_is_a_permutation_and_local():
     from mlamg import problems
     rs = np.random.RandomState(1)
