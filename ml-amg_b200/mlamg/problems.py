@@ -8,6 +8,8 @@ pyamg exists here, so the same *shapes* are generated directly:
     (evaluated at the centroid, as gradgradform does), Dirichlet boundary rows/columns removed;
   * kappa piecewise constant on the Voronoi cells of Ns in {2,3} seeds, 10^U(-4,4) re-drawn until the
     spread exceeds 1e3 (the reference's 'jump' dataset);
+  * rotated-anisotropic diffusion K = Q diag(1, eps) Q^T (the 'anisotropic' dataset, data.py:301-347) and the 1-D
+    finite-difference matrices (data.py:244-297);
   * structured-triangle and Delaunay meshes, Morton (Z-curve) ordering so that contiguous row blocks are
     spatially compact (the row partition of the multi-GPU levels);
   * stand-ins for the GNN outputs of FullAggNet.forward (agg_interp.py:459-481): centres = top-k of a random
