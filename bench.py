@@ -96,7 +96,7 @@ def lam_fn_factory(n):
     exact = 1.0 + np.cos(np.pi / (n + 1))          # rho(D^-1 A) of the Dirichlet 7-point stencil, analytic
 
     def lam(A):
-        return exact if A.shape[0] == n ** 3 else mlamg.lambda_max(A, iters=30)
+        return exact if A.shape[0] == n ** 3 else mlamg.lambda_max(A)
     return lam
 
 

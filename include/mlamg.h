@@ -189,10 +189,15 @@ int mlamg_dense_inverse_f64(int n, double *a, double *work, mlamg_stream_t strea
 /* y = M x, M dense n x n row-major */
 int mlamg_gemv(int dtype, int n, const void *m, const void *x, void *y, mlamg_stream_t stream);
 
-/* largest eigenvalue of D^-1 A by power iteration on device (replaces ARPACK eigs, multigrid.py:105).
- * work: 2n values.  *lambda_host receives the Rayleigh-quotient estimate after `iters` steps. */
-int mlamg_lambda_max(int dtype, int n, const int *rowptr, const int *col, const void *val, int iters,
-                     void *work, double *lambda_host, mlamg_stream_t stream);
+/* |lambda_max(D^-1 A)| to a reported accuracy (replaces ARPACK `eigs(Dinv@A, k=1, which='LM')`, multigrid.py:105).
+ * symmetric: 1 = A is symmetric, 0 = it is not, -1 = test it (two SpMVs).  Symmetric A with a positive diagonal:
+ * Lanczos on D^-1/2 A D^-1/2, stopped when the eigenvalue error estimate min(res, res^2/gap) <= tol*lambda (res = exact
+ * residual norm of the Ritz pair); otherwise power iteration on D^-1 A stopped by the Rayleigh residual <= tol*lambda.
+ * Host outputs (resid/steps/method may be NULL): the eigenvalue, the achieved relative residual of the eigenpair, the
+ * operator applications used, the method (1 Lanczos, 0 power iteration).  All scratch is stream-ordered pool memory. */
+int mlamg_lambda_max(int dtype, int n, long long nnz, const int *rowptr, const int *col, const void *val, double tol,
+                     int max_steps, int symmetric, double *lambda_host, double *resid_host, int *steps_host,
+                     int *method_host, mlamg_stream_t stream);
 
 /* synthetic Dirichlet Poisson stencil (5-point if nz==1, else 7-point), x fastest.
  * nnz = mlamg_poisson_nnz(nx,ny,nz). */

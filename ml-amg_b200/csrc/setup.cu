@@ -296,101 +296,6 @@ __global__ void __launch_bounds__(256) poisson_fill_kernel(int nx, int ny, int n
     if (z < nz - 1) { col[p] = (int)(i + sxy); val[p++] = (T)-1; }
 }
 
-// ------------------------------------------------------------------ power iteration on D^-1 A
-// y = D^-1 A x (warp per row), partial sums of x.y and y.y for the Rayleigh quotient / normalisation
-template <typename T>
-__global__ void __launch_bounds__(256) dinv_a_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                     const T *__restrict__ val, const T *__restrict__ x,
-                                                     T *__restrict__ y, double *__restrict__ partial) {
-    __shared__ double sm[32];
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    T acc = (T)0, d = (T)0;
-    if (row < n) {
-        for (int j = rowptr[row] + lane; j < rowptr[row + 1]; j += 32) {
-            const T v = val[j];
-            const int c = col[j];
-            acc += v * x[c];
-            if (c == row) d += v;
-        }
-    }
-    acc = warp_sum(acc);
-    d = warp_sum(d);
-    double xy = 0.0, yy = 0.0;
-    if (row < n && lane == 0) {
-        const T yi = acc / d;
-        y[row] = yi;
-        xy = (double)x[row] * (double)yi;
-        yy = (double)yi * (double)yi;
-    }
-    xy = block_sum(xy, sm);
-    yy = block_sum(yy, sm);
-    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = xy; partial[2 * blockIdx.x + 1] = yy; }
-}
-
-__global__ void __launch_bounds__(1024) power_reduce_kernel(const double *__restrict__ partial, int nb,
-                                                            double *__restrict__ out /* [xy, yy] */) {
-    __shared__ double sm[32];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nb; i += 1024) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-    a = block_sum(a, sm);
-    b = block_sum(b, sm);
-    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) power_scale_kernel(int n, const T *__restrict__ y, const double *__restrict__ red,
-                                                          T *__restrict__ x) {
-    const double inv = rsqrt(red[1]);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        x[i] = (T)((double)y[i] * inv);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) power_init_kernel(int n, T *__restrict__ x) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        // fixed pseudo-random start with components on every eigenvector (deterministic)
-        unsigned h = (unsigned)i * 2654435761u;
-        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-        x[i] = (T)(0.5 + (double)(h & 0xffffu) / 65536.0) * ((i & 1) ? (T)-1 : (T)1) * (T)rsqrt((double)n);
-    }
-}
-
-template <typename T>
-static int lambda_max_t(int n, const int *rowptr, const int *col, const T *val, int iters, T *work,
-                        double *lambda_host, cudaStream_t s) {
-    if (n <= 0 || iters <= 0) return set_error(MLAMG_EINVAL, "lambda_max: bad n/iters");
-    T *x = work, *y = work + n;
-    const unsigned blocks = cdiv((long long)n * 32, 256);
-    unsigned eb = cdiv(n, 256);
-    if (eb > 148u * 8u) eb = 148u * 8u;
-    Scratch part((size_t)blocks * 2 * sizeof(double), s), red(2 * sizeof(double), s);
-    MLAMG_SCRATCH_OK(part);
-    MLAMG_SCRATCH_OK(red);
-    power_init_kernel<T><<<eb, 256, 0, s>>>(n, x);
-    MLAMG_LAUNCHED();
-    for (int it = 0; it < iters; it++) {
-        dinv_a_kernel<T><<<blocks, 256, 0, s>>>(n, rowptr, col, val, x, y, part.as<double>());
-        MLAMG_LAUNCHED();
-        power_reduce_kernel<<<1, 1024, 0, s>>>(part.as<double>(), (int)blocks, red.as<double>());
-        MLAMG_LAUNCHED();
-        if (it + 1 < iters) {
-            power_scale_kernel<T><<<eb, 256, 0, s>>>(n, y, red.as<double>(), x);
-            MLAMG_LAUNCHED();
-        }
-    }
-    // Rayleigh quotient of the last step: (x.y)/(x.x) with ||x||=1 after scaling -> use sqrt(yy) as the
-    // norm growth and xy as the quotient; report the larger (both converge to |lambda_max| from below).
-    double h[2] = {0, 0};
-    MLAMG_CUDA(cudaMemcpyAsync(h, red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MLAMG_CUDA(cudaStreamSynchronize(s));
-    const double g = sqrt(h[1]);
-    *lambda_host = fabs(h[0]) > g ? fabs(h[0]) : g;
-    return MLAMG_OK;
-}
-
 }  // namespace mlamg
 
 using namespace mlamg;
@@ -541,11 +446,5 @@ int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, 
     return mlamg_poisson_csr_slab(dtype, nx, ny, nz, 0, nz, rowptr, col, val, nullptr, stream);
 }
 
-int mlamg_lambda_max(int dtype, int n, const int *rowptr, const int *col, const void *val, int iters, void *work,
-                     double *lambda_host, mlamg_stream_t stream) {
-    MLAMG_DISPATCH(dtype, return lambda_max_t<T>(n, rowptr, col, (const T *)val, iters, (T *)work, lambda_host,
-                                                 as_stream(stream)));
-    return MLAMG_OK;
-}
 
 }  // extern "C"

@@ -55,7 +55,7 @@ SIGNATURES = {
     "mlamg_csr_to_dense": (I, [I, I, P, P, P, P, P]),
     "mlamg_dense_inverse_f64": (I, [I, P, P, P]),
     "mlamg_gemv": (I, [I, I, P, P, P, P]),
-    "mlamg_lambda_max": (I, [I, I, P, P, P, I, P, P, P]),
+    "mlamg_lambda_max": (I, [I, I, LL, P, P, P, D, I, I, P, P, P, P, P]),
     "mlamg_poisson_nnz": (LL, [I, I, I]),
     "mlamg_poisson_csr": (I, [I, I, I, I, P, P, P, P]),
     "mlamg_poisson_csr_slab": (I, [I, I, I, I, I, I, P, P, P, P, P]),

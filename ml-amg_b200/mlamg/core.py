@@ -485,13 +485,19 @@ def sort_rows(A):
     return A
 
 
-def lambda_max(A, iters=40):
-    """|lambda_max(D^-1 A)| by power iteration on device (stand-in for ARPACK, multigrid.py:105)."""
-    n = A.shape[0]
-    work = torch.empty(2 * n, dtype=A.dtype, device=A.val.device)
-    lam = ctypes.c_double(0.0)
-    check(lib.mlamg_lambda_max(dt(A.val), n, ptr(A.rowptr), ptr(A.col), ptr(A.val), int(iters), ptr(work),
-                               ctypes.byref(lam), stream()))
+def lambda_max(A, tol=1e-13, maxiter=6000, symmetric=None, info=None):
+    """|lambda_max(D^-1 A)| on the device to a reported accuracy (the reference calls ARPACK, multigrid.py:105).
+    Symmetric A: Lanczos on D^-1/2 A D^-1/2 until the eigenvalue error estimate is <= tol*lambda; otherwise a
+    power iteration with a Rayleigh-residual stopping rule.  symmetric=None tests symmetry with two SpMVs.
+    info (optional dict) receives {'residual', 'steps', 'method'}."""
+    lam, res = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    steps, method = ctypes.c_int(0), ctypes.c_int(0)
+    sym = -1 if symmetric is None else (1 if symmetric else 0)
+    check(lib.mlamg_lambda_max(dt(A.val), A.shape[0], A.nnz, ptr(A.rowptr), ptr(A.col), ptr(A.val), float(tol), int(maxiter),
+                               sym, ctypes.byref(lam), ctypes.byref(res), ctypes.byref(steps), ctypes.byref(method),
+                               stream()))
+    if info is not None:
+        info.update(residual=res.value, steps=steps.value, method="lanczos" if method.value == 1 else "power")
     return lam.value
 
 

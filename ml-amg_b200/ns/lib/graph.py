@@ -49,9 +49,16 @@ def lloyd_aggregation(C, ratio=0.03, distance='unit', maxiter=10, rand=None):
     if rand is not None and not isinstance(rand, (int, np.integer, np.random.RandomState)):
         raise TypeError('rand should be an integer seed value or a random state')
     core.require_cuda()
-    data = np.real(C.data) if C.dtype == complex else C.data
+    data = C.data
     if distance == 'unit':
-        data = np.ones_like(data).astype(float)     # reference: float64 unit lengths
+        data = np.ones_like(np.real(data)).astype(float)     # reference: float64 unit lengths
+        distance_dev = 'same'
+    elif np.iscomplexobj(data):
+        # reference order (:201-223): the transform acts on the complex entries (abs = modulus), the real part is
+        # taken afterwards
+        data = {'abs': lambda d: abs(d), 'inv': lambda d: 1.0 / abs(d), 'same': lambda d: d,
+                'min': lambda d: d - d.min()}[distance](data)
+        data = np.ascontiguousarray(np.real(data))
         distance_dev = 'same'
     else:
         distance_dev = distance

@@ -42,11 +42,12 @@ def test_config2_poisson3d_128_setup_and_pcg_full_size():
     A = mlamg.poisson((n, n, n), torch.float64)
     exact = 1.0 + np.cos(np.pi / (n + 1))           # rho(D^-1 A) of the Dirichlet 7-point stencil
     H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=0.027, distance="unit", maxiter=10, rand=0,
-                              lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M, iters=30),
+                              lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M),
                               max_coarse=1000, max_levels=8)
     assert len(H.levels) >= 3 and H.levels[0].A.shape[0] == n ** 3 and H.levels[0].A.nnz == 14581760
-    lam_pi = mlamg.lambda_max(A, iters=200)
-    assert exact - 2e-2 < lam_pi <= exact + 1e-12    # power iteration approaches the analytic value from below
+    info = {}
+    lam_l = mlamg.lambda_max(A, info=info)           # Lanczos at full size against the analytic value
+    assert abs(lam_l - exact) <= 1e-10 * exact and info["method"] == "lanczos", (lam_l, exact, info)
     # every aggregate index is used, every node is aggregated, Galerkin operators are symmetric
     lab = H.levels[0].labels
     nc = H.levels[1].A.shape[0]

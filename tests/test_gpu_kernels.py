@@ -6,7 +6,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import random_csr, assert_csr_close, assert_csr_bitwise, assert_same_pattern
+from helpers import random_csr, assert_csr_close, assert_csr_bitwise, assert_same_pattern, GOLDEN_CASES, GOLDEN_CASES_CONFIG_SHAPES, load_golden, csr_from
 from oracle import multilevel as oml
 
 pytestmark = pytest.mark.gpu
@@ -208,12 +208,46 @@ def test_dense_inverse_and_singular():
         mlamg.dense_inverse(mlamg.DeviceCSR.from_scipy(S))
 
 
-def test_lambda_max_power_iteration():
+def test_lambda_max_lanczos_known_answers():
+    """|lambda_max(D^-1 A)| against the analytic spectrum of the Dirichlet stencils: Lanczos with a reported residual."""
     import mlamg
-    n = 24
-    lam = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(oml.poisson((n, n))), iters=200)
-    exact = 1 + np.cos(np.pi / (n + 1))
-    assert exact * 0.97 <= lam <= exact * (1 + 1e-9)
+    for shape in ((24, 24), (40, 33), (12, 10, 9)):
+        info = {}
+        lam = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(oml.poisson(shape)), info=info)
+        exact = 1 + sum(np.cos(np.pi / (m + 1)) for m in shape) / len(shape)
+        assert abs(lam - exact) <= 1e-12 * exact, (shape, lam, exact, info)
+        assert info["method"] == "lanczos" and info["residual"] < 1e-5 and info["steps"] < 2000
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_CASES_CONFIG_SHAPES)
+def test_lambda_max_vs_reference_arpack_golden(name):
+    """the value the UNMODIFIED reference obtained from ARPACK (tests/golden/make_golden.py) on every golden problem;
+    `randw_same` is symmetric too, the `laplace3d_grid` cases are the reference's own fixture"""
+    import mlamg
+    z = load_golden(name)
+    A = csr_from(z, "A")
+    info = {}
+    lam = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(A), info=info)
+    ref = float(z["lam_max"])
+    assert abs(lam - ref) <= 1e-10 * ref, (lam, ref, info)
+
+
+def test_lambda_max_nonsymmetric_and_fp32():
+    """non-symmetric operator: monitored power iteration on D^-1 A vs scipy's dense eigenvalues; fp32: Lanczos to 1e-5"""
+    import mlamg
+    rs = np.random.RandomState(5)
+    n = 300
+    A = (sp.random(n, n, density=0.03, random_state=rs, format="csr") + sp.diags(np.linspace(1.0, 3.0, n))).tocsr()
+    A.sort_indices()
+    ref = np.abs(np.linalg.eigvals((sp.diags(1.0 / A.diagonal()) @ A).toarray())).max()
+    info = {}
+    lam = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(A), tol=1e-10, maxiter=20000, info=info)
+    assert info["method"] == "power"
+    assert abs(lam - ref) <= 1e-6 * ref, (lam, ref, info)
+    P = oml.poisson((30, 30)).astype(np.float32)
+    info = {}
+    lam32 = mlamg.lambda_max(mlamg.DeviceCSR.from_scipy(P), tol=1e-6, info=info)
+    assert abs(lam32 - (1 + np.cos(np.pi / 31))) < 2e-5, (lam32, info)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

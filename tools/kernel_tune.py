@@ -22,7 +22,7 @@ def main():
     A = mlamg.poisson((n, n, n), torch.float64)
     exact = 1.0 + np.cos(np.pi / (n + 1))
     H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=0.027, distance="unit", maxiter=10, rand=0,
-                              lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M, iters=30),
+                              lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M),
                               max_coarse=1000, max_levels=8)
 
     def gtime(fn, reps=10):

@@ -50,7 +50,7 @@ def config2():
     A = mlamg.poisson((n, n, n), torch.float64)
     H, t_setup = sync_time(lambda: mlamg.build_hierarchy(
         A, aggregates="lloyd", ratio=0.027, distance="unit", maxiter=10, rand=0,
-        lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M, iters=30), max_coarse=1000, max_levels=8))
+        lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M), max_coarse=1000, max_levels=8))
     b = mlamg.spmv(A, torch.ones(n ** 3, dtype=torch.float64, device="cuda"))
     (x, res), t_solve = sync_time(lambda: H.solve(b, tol=1e-8, maxiter=100, accel="cg", return_residuals=True))
     (x, res), t_solve = sync_time(lambda: H.solve(b, tol=1e-8, maxiter=100, accel="cg", return_residuals=True))

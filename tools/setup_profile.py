@@ -43,7 +43,7 @@ def main():
         t0 = time.perf_counter()
         A = mlamg.poisson((n, n, n), torch.float64)
         H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=0.027, distance="unit", maxiter=10, rand=0,
-                                  lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M, iters=30),
+                                  lam_max=lambda M: exact if M.shape[0] == n ** 3 else mlamg.lambda_max(M),
                                   max_coarse=1000, max_levels=8)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
