@@ -13,9 +13,12 @@ right-hand side.  metric = GDOF/s (fine DOFs x cycles / s / 1e9; V-cycles/s repo
               b -> H2D -> V-cycle -> D2H -> host x, copies inside the timed region
   roofline  : the dominant kernel (fused Jacobi sweep on the fine level), CUDA-event duration per launch
               from an instrumented repeat of the timed steps, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the oracle's scipy V-cycle on the SAME hierarchy (downloaded), 1 host core (scipy
-              sparsetools is single-threaded), a bounded number of cycles
-  --impl reference : the oracle port end to end on the host (own CPU setup at a bounded size).
+  setup_parity : the oracle builds the hierarchy from the same A on the host (its own Lloyd, P, P^T A P, ~1 min at 256^3)
+              and every level is compared with the GPU's: labels / moved seeds array_equal, P and A_l bit-identical
+  cpu_baseline : the oracle's scipy V-cycle on the ORACLE-built hierarchy, 1 host core (scipy sparsetools is
+              single-threaded), a bounded number of cycles; its result is also the full-size parity check of the GPU cycle
+  --impl reference : the oracle port end to end on the host: its own CPU setup of the SAME workload (256^3), then
+              `steps` V(1,1) cycles timed one by one.
 """
 import argparse
 import json
@@ -91,12 +94,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def lam_fn_factory(n):
+def lam_fn_factory(n, lams_out=None):
+    """lambda_max rule of BOTH arms: the fine level uses the analytic rho(D^-1 A) = 1 + cos(pi/(n+1)) of the Dirichlet
+    7-point stencil (ARPACK on 16.7 M rows is 160 s+ and is not part of the timed setup); every coarser
+    level is solved for — Lanczos to 1e-13 on the device here, ARPACK (`eigsh` on D^-1/2 A D^-1/2) in the reference arm."""
     import mlamg
-    exact = 1.0 + np.cos(np.pi / (n + 1))          # rho(D^-1 A) of the Dirichlet 7-point stencil, analytic
+    exact = 1.0 + np.cos(np.pi / (n + 1))
 
     def lam(A):
-        return exact if A.shape[0] == n ** 3 else mlamg.lambda_max(A)
+        v = exact if A.shape[0] == n ** 3 else mlamg.lambda_max(A)
+        if lams_out is not None:
+            lams_out.append(v)
+        return v
+    return lam
+
+
+def lam_fn_reference(n):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    exact = 1.0 + np.cos(np.pi / (n + 1))
+
+    def lam(A):
+        if A.shape[0] == n ** 3:
+            return exact
+        d = 1.0 / np.sqrt(A.diagonal())
+        B = sp.diags(d) @ A @ sp.diags(d)           # same spectrum as D^-1 A (multigrid.py:105), symmetric -> eigsh
+        return float(np.abs(spla.eigsh(B, k=1, which="LA", return_eigenvectors=False)).max())
     return lam
 
 
@@ -121,8 +144,9 @@ def run_ours(args):
         return run_ours_distributed(args, rank, world, local, cpus)
     t_setup0 = time.time()
     A = mlamg.poisson((n, n, n), torch.float64)
+    lams = []
     H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=RATIO, distance="unit", maxiter=10, rand=0,
-                              lam_max=lam_fn_factory(n), max_coarse=1000, max_levels=8)
+                              lam_max=lam_fn_factory(n, lams), max_coarse=1000, max_levels=8)
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup0
     N = A.shape[0]
@@ -251,15 +275,7 @@ def run_ours(args):
                 "cycle_bytes_baseline_formula": b_std, "cycle_frac_baseline_formula": round(b_std / ms / 1e6 / peak, 4),
                 "fine_level_kernels": kern,
                 "spmv_and_smoother": extra}
-    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tr):
-        try:
-            key = ("psmooth0_fine_bytes_per_launch" if "OP_PSMOOTH0" in dom["kernel"] else
-                   "residual_scaled_fine_bytes_per_launch" if "OP_RESIDUAL" in dom["kernel"] else
-                   "reszero_fine_bytes_per_launch" if "OP_RESZERO" in dom["kernel"] else "jacobi_fine_bytes_per_launch")
-            roofline["traffic"] = json.load(open(tr)).get(key)
-        except Exception:
-            pass
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(dom["kernel"])
 
     # --- e2e: host buffers through the C ABI (H2D + cycle + D2H inside the timed region)
     hb = torch.from_numpy(np.random.RandomState(1).randn(N)).pin_memory()
@@ -275,18 +291,77 @@ def run_ours(args):
     e2e = {"value": round(N / e2e_s / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
            "ms_per_step": round(e2e_s * 1e3, 3)}
 
-    # --- CPU baseline: the oracle's scipy cycle on the same hierarchy, bounded sample
-    cpu = cpu_baseline_same_hierarchy(H, hb.numpy(), hx.numpy(), args.cpu_cycles) if args.cpu_cycles > 0 else None
+    # --- setup parity + CPU baseline: the oracle builds the hierarchy from the same A on the host (its own Lloyd, P, RAP),
+    # every level is compared with the GPU's, and the oracle's cycle on ITS hierarchy is timed and compared with the GPU's
+    hx_cycle = hx.numpy()                       # result of the last e2e apply: one zero-guess V(1,1) on hb
+    parity, cpu = None, None
+    if args.cpu_cycles > 0:
+        ref_levels, parity = oracle_setup_parity(H, n, lams)
+        cpu = cpu_baseline(ref_levels, hb.numpy(), hx_cycle, args.cpu_cycles)
 
     out = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(n, 1), "dof": N, "nnz": A0.nnz, "levels": [l.A.shape[0] for l in H.levels],
-                      "operator_complexity": round(H.operator_complexity(), 4), "cycle": "V(1,1) zero-guess",
-                      "l2_policy": f"inputs larger than L2 (fine operator {A0.nnz * 12 / 1e9:.1f} GB vs 126 MB L2)", "setup_s": round(setup_s, 2)},
+           "config": common_config(n, 1),
+           "detail": {"nnz": A0.nnz, "levels": [l.A.shape[0] for l in H.levels],
+                      "operator_complexity": round(H.operator_complexity(), 4),
+                      "l2_policy": f"inputs larger than L2 (fine operator {A0.nnz * 12 / 1e9:.1f} GB vs 126 MB L2)",
+                      "setup_s": round(setup_s, 2), "lambda_max_per_level": [round(v, 12) for v in lams]},
+           "setup_parity": parity,
            "vcycles_per_s": round(1e3 / ms, 2), "clocks": clk, "e2e": e2e, "gpu_launches": kernels_per_cycle * args.steps,
            "kernels_per_cycle": kernels_per_cycle, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(out))
+
+
+def common_config(n, ngpu):
+    """the keys both arms print identically (the reference arm runs the same workload)"""
+    return {"workload": workload_name(n, ngpu), "dof": n ** 3 * ngpu, "dof_per_gpu": n ** 3, "cycle": "V(1,1) zero-guess",
+            "aggregation": f"lloyd ratio {RATIO} unit rand 0 maxiter 10", "max_coarse": 1000}
+
+
+def ncu_traffic(kernel_label):
+    """DRAM bytes per launch of the dominant kernel from the round's `ncu --set full` capture (tools/ncu_traffic.py wrote
+    profiles/traffic_r02.json).  The record carries the sha256 of csrc/apply.cu at capture time: if the kernel source has
+    changed since, the number is stale and null is reported instead."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    try:
+        rec = json.load(open(path))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "ml-amg_b200", "csrc", "apply.cu"), "rb").read()).hexdigest()
+        if rec.get("apply_cu_sha256") != sha:
+            return None, "profiles/traffic_r02.json is stale (apply.cu changed since the ncu capture)"
+        for op, val in rec["dram_bytes_per_launch"].items():
+            if op in kernel_label:
+                return val, rec.get("source")
+    except Exception as exc:       # noqa: BLE001
+        return None, f"no capture ({type(exc).__name__})"
+    return None, "kernel not in the capture"
+
+
+def oracle_setup_parity(H, n, lams):
+    """oracle.multilevel.build_hierarchy on the host from the same A (given the omegas the GPU used, so that every level
+    can be compared bit for bit) vs the GPU-built hierarchy."""
+    from oracle import multilevel as oml
+    t0 = time.time()
+    ref = oml.build_hierarchy(oml.poisson((n, n, n)), ratio=RATIO, distance="unit", maxiter=10, rand=0, lam_max=list(lams),
+                              max_coarse=1000, max_levels=8)
+    t_cpu = time.time() - t0
+
+    def same_csr(G, S):
+        G = G.to_scipy()
+        return bool(G.shape == S.shape and np.array_equal(G.indptr, S.indptr) and np.array_equal(G.indices, S.indices)
+                    and np.array_equal(G.data, S.data))
+    par = {"levels_equal": len(ref) == len(H.levels), "labels_equal": [], "roots_equal": [], "P_bitwise": [],
+           "A_bitwise": [], "oracle_setup_s": round(t_cpu, 1)}
+    for Lg, Lr in zip(H.levels, ref):
+        par["A_bitwise"].append(same_csr(Lg.A, Lr.A))
+        if Lr.P is not None and Lg.P is not None:
+            par["labels_equal"].append(bool(np.array_equal(Lg.labels.cpu().numpy(), Lr.labels)))
+            par["roots_equal"].append(bool(np.array_equal(Lg.roots.cpu().numpy(), Lr.roots)))
+            par["P_bitwise"].append(same_csr(Lg.P, Lr.P))
+    par["ok"] = bool(par["levels_equal"] and all(par["labels_equal"]) and all(par["roots_equal"]) and all(par["P_bitwise"])
+                     and all(par["A_bitwise"]))
+    return ref, par
 
 
 def run_ours_distributed(args, rank, world, local, cpus=None):
@@ -426,17 +501,10 @@ def run_ours_distributed(args, rank, world, local, cpus=None):
     dist.destroy_process_group()
 
 
-def cpu_baseline_same_hierarchy(H, b, x_gpu, cycles):
-    """oracle.multilevel.vcycle (scipy, 1 core) on the hierarchy downloaded from the device; also the
-    full-size parity check of the GPU cycle (x_gpu = GPU result of one zero-guess V(1,1) on b)."""
+def cpu_baseline(levels, b, x_gpu, cycles):
+    """oracle.multilevel.vcycle (scipy, 1 core) on the ORACLE-built hierarchy; also the full-size parity check of the
+    GPU cycle (x_gpu = GPU result of one zero-guess V(1,1) on b, on the GPU-built hierarchy)."""
     from oracle import multilevel as oml
-    levels = []
-    for lev in H.levels:
-        L = oml.Level()
-        L.A = lev.A.to_scipy()
-        if lev.P is not None:
-            L.P, L.R, L.dw = lev.P.to_scipy(), lev.R.to_scipy(), lev.dw.cpu().numpy()
-        levels.append(L)
     x = oml.vcycle(levels, b.copy(), None, 1, 1)           # warm-up + parity
     rel = float(np.abs(x - x_gpu).max() / np.abs(x).max())
     ts = []
@@ -469,37 +537,42 @@ def cpu_baseline_same_hierarchy(H, b, x_gpu, cycles):
     return {"value": round(N / min(ts) / 1e9, 5), "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(),
             "fine_level_ops_scipy": cpu_ops,
             "kind": "port", "sample": f"{len(ts)} full-size V(1,1) cycles of the oracle (scipy, single-threaded) on the "
-            f"same hierarchy, best of {len(ts)}; {min(ts):.2f} s per cycle", "parity_rel_err_vs_gpu_cycle": rel}
+            f"hierarchy the oracle built itself, best of {len(ts)}; {min(ts):.2f} s per cycle", "parity_rel_err_vs_gpu_cycle": rel}
 
 
 # ------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: scipy + the restated pyamg C loops, single-threaded
+    like scipy/pyamg themselves) on the SAME workload: full CPU setup at n^3, then `steps` V(1,1) cycles.  At N > 1 the
+    workload is N independent-size slabs of n^3 DOF each (weak scaling): rank 0 runs the per-GPU share (one n^3 problem)
+    as the bounded sample — throughput per DOF is what the driver's ratio needs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import multilevel as oml
-    n = args.ref_n
+    n = args.ref_n if args.ref_n > 0 else args.n
     t0 = time.time()
     A = oml.poisson((n, n, n))
-    exact = 1.0 + np.cos(np.pi / (n + 1))
-    levels = oml.build_hierarchy(A, ratio=RATIO, distance="unit", maxiter=10, rand=0,
-                                 lam_max=lambda M: exact if M.shape[0] == n ** 3 else 2.0, max_coarse=1000, max_levels=8)
+    levels = oml.build_hierarchy(A, ratio=RATIO, distance="unit", maxiter=10, rand=0, lam_max=lam_fn_reference(n),
+                                 max_coarse=1000, max_levels=8)
     setup_s = time.time() - t0
     N = A.shape[0]
     b = np.random.RandomState(0).randn(N)
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(min(max(args.warmup, 1), 2)):       # scipy has no warm-up effects beyond the first touch of the arrays
         oml.vcycle(levels, b.copy(), None, 1, 1)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oml.vcycle(levels, b.copy(), None, 1, 1)
     s = (time.perf_counter() - t0) / args.steps
     val = round(N / s / 1e9, 5)
-    sample = (f"each step = one oracle V(1,1) cycle on a {n}^3 sample of the workload (per-DOF throughput; "
-              f"CPU setup {setup_s:.1f} s untimed); scipy sparsetools is single-threaded")
+    sample = (f"each step = one oracle V(1,1) cycle on the full {n}^3 problem" + (f" (= one GPU's share of the {args.gpus}-GPU "
+              f"weak-scaling workload)" if args.gpus > 1 else "") + f"; CPU setup {setup_s:.1f} s untimed, like the GPU arm's; "
+              "scipy sparsetools and the pyamg loops are single-threaded")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": max(args.warmup, 1), "ms_per_step": round(s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": round(s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args.n, args.gpus), "sample_dof": N},
+           "config": common_config(args.n, args.gpus),
+           "detail": {"sample_dof": N, "levels": [l.A.shape[0] for l in levels], "setup_s": round(setup_s, 2)},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(), "kind": "port",
                             "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -513,7 +586,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="grid side per GPU")
-    ap.add_argument("--ref-n", type=int, default=128, help="grid side of the reference arm's bounded sample")
+    ap.add_argument("--ref-n", type=int, default=0, help="grid side of the reference arm (0 = the same --n as the GPU arm)")
     ap.add_argument("--cpu-cycles", type=int, default=3, help="oracle cycles timed for cpu_baseline (0 = skip)")
     ap.add_argument("--profile", action="store_true", help="wrap `steps` plain-launch cycles in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
