@@ -266,13 +266,26 @@ int mlamg_hierarchy_use_graph(mlamg_hierarchy_t h, int enable);
  * zero_guess != 0: x is treated as 0 on entry (preconditioner apply). */
 int mlamg_vcycle(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, int zero_guess,
                  mlamg_stream_t stream);
-/* stationary iteration x <- V(x, b) until ||b-Ax||_2 <= tol_abs or maxiter.  res_host[maxiter+1]
+/* Both solvers below are device resident: scalars, residual history and the convergence flag stay in HBM, the loop is a
+ * CUDA-graph WHILE node whose body is one iteration (V-cycle included) — one graph launch and one host synchronisation
+ * per solve.  mlamg_solver_loop_mode: 1 = WHILE node in use, -1 = host-driven fallback (driver without conditional
+ * nodes), 0 = no solve yet; MLAMG_SOLVER_HOST_LOOP=1 in the environment forces the fallback.
+ * stationary iteration x <- V(x, b) until ||b-Ax||_2 <= tol_abs or maxiter.  res_host[maxiter+1]
  * (entry 0 = initial residual).  MLAMG.py:189-195 / multigrid.py:173-199 loop with Jacobi smoothing. */
 int mlamg_solve(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double tol_abs,
                 int maxiter, double *res_host, int *niter_host, mlamg_stream_t stream);
+/* the loop of ns/lib/multigrid.py:173-199 (amg_2_v) and MLAMG.py:189-195 in full: flags select the error measure
+ * (XNORM: ||x||_2, the `error_tol` mode), the mean removal of the singular mode (:186-187) and whether the initial
+ * iterate is tested (the reference loops always run one iteration first). */
+#define MLAMG_SOLVE_XNORM 1
+#define MLAMG_SOLVE_REMOVE_MEAN 2
+#define MLAMG_SOLVE_NO_INITIAL_CHECK 4
+int mlamg_solve_ex(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, int flags, double tol_abs,
+                   int maxiter, double *res_host, int *niter_host, mlamg_stream_t stream);
 /* V-cycle preconditioned CG; stops when ||r||_2 <= rtol*||b||_2.  res_host[maxiter+1]. */
 int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter,
               double *res_host, int *niter_host, mlamg_stream_t stream);
+int mlamg_solver_loop_mode(mlamg_hierarchy_t h);
 
 /* Preconditioner apply with HOST buffers (PETSc PC apply shape: MLAMG.py:199-212, PyAMG.py:118-120):
  * H2D(b) -> `cycles` V-cycles from a zero guess -> D2H(x), all inside the call; returns after x_host

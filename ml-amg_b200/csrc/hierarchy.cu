@@ -8,104 +8,11 @@
 // sweep, ping-ponging between two vectors; from a zero guess the first sweep is x = dw .* b and
 // needs no pass over A.  Per level and V(1,1) cycle the operator is therefore read twice
 // (residual + post-smooth) on coarse levels and on a zero-guess fine level.
-#include <math.h>
-#include <vector>
-#include "common.cuh"
+#include "hierarchy.cuh"
 
 namespace mlamg {
 
-template <typename T> int spmv_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
-template <typename T>
-int spmv_perm_t(int, long long, const int *, const int *, const T *, const T *, T *, const int *, cudaStream_t);
-template <typename T> int spmv_add_t(int, long long, const int *, const int *, const T *, const T *, T *, cudaStream_t);
-template <typename T>
-int residual_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, double *, cudaStream_t);
-template <typename T>
-int jacobi_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
-template <typename T> int jacobi_zero_t(int, const T *, const T *, T *, cudaStream_t);
-template <typename T>
-int reszero_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
-template <typename T>
-int reszero_scaled_t(int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, double *, cudaStream_t);
-template <typename T>
-int psmooth0_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *,
-                     cudaStream_t);
-template <typename T>
-int residual_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, T *, cudaStream_t);
-template <typename T>
-int psmooth_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *,
-                    cudaStream_t);
-template <typename T>
-int reszero_scaled_range_t(int, int, long long, const int *, const int *, const T *, const T *, const T *, T *, T *, cudaStream_t);
-template <typename T>
-int psmooth_t(int, long long, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
-template <typename T>
-int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
-                 cudaStream_t);
-template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
-
-struct Csr {
-    int n = 0;          // rows
-    long long nnz = 0;
-    const int *rowptr = nullptr;
-    const int *col = nullptr;
-    const void *val = nullptr;
-};
-
-struct LevelData {
-    Csr A, P, R;
-    Csr Q;                                                  // optional (I - D_w A) P: prolongation fused with the first post sweep
-    bool has_Q = false;
-    const void *val_scaled = nullptr;                       // optional values of A D_w (a_ij * dw_j) on A's pattern
-    const void *dw = nullptr;
-    const int *r_order = nullptr;                           // optional processing order of the rows of R
-    const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A
-    const void *sell_val = nullptr;
-    bool has_A = false, has_PR = false;
-    void *x = nullptr, *tmp = nullptr, *b = nullptr, *r = nullptr;   // owned work vectors
-};
-
-}  // namespace mlamg
-
-namespace mlamg {
-// Host-buffer apply (mlamg_vcycle_host): the right-hand side arrives and the result leaves in row chunks on a copy
-// stream; the first fine-level pass runs chunk by chunk as soon as the columns it gathers have arrived, the last one
-// hands every finished chunk to the D2H copy — the two PCIe transfers overlap the two largest kernels.
-constexpr int PIPE_CHUNKS = 8;
-struct HostPipe {
-    bool ready = false;
-    cudaStream_t cs = nullptr;
-    cudaEvent_t in_ev[PIPE_CHUNKS] = {}, out_ev[PIPE_CHUNKS] = {}, fork = nullptr;
-    int row_lo[PIPE_CHUNKS + 1] = {};
-    int need[PIPE_CHUNKS] = {};          // chunk whose arrival completes the columns gathered by the rows of chunk k
-    int nchunks = 0;
-};
-}  // namespace mlamg
-
-struct mlamg_hierarchy {
-    int dtype = MLAMG_F64;
-    size_t esz = 8;
-    std::vector<mlamg::LevelData> lv;
-    const void *coarse_inv = nullptr;
-    bool finalized = false;
-    bool use_graph = false;
-    // PCG work vectors (level-0 sized), allocated lazily
-    void *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_ap = nullptr;
-    double *dscal = nullptr;     // device scalars
-    double *hscal = nullptr;     // pinned host mirror
-    void *host_b = nullptr, *host_x = nullptr;   // device staging of the *_host entry points
-    mlamg::HostPipe pipe;
-    // CUDA graph cache of one V-cycle
-    cudaStream_t cap_stream = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    const void *g_b = nullptr;
-    void *g_x = nullptr;
-    int g_nu1 = -1, g_nu2 = -1, g_zero = -1;
-};
-
-namespace mlamg {
-
-static int check_handle(mlamg_hierarchy_t h) {
+int check_handle(mlamg_hierarchy_t h) {
     if (!h) return set_error(MLAMG_EINVAL, "null hierarchy handle");
     return MLAMG_OK;
 }
@@ -266,13 +173,13 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
     return MLAMG_OK;
 }
 
-static int vcycle_dispatch(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess,
+int vcycle_dispatch(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess,
                            cudaStream_t s) {
     MLAMG_DISPATCH(h->dtype, return vcycle_enqueue<T>(h, (const T *)b, (T *)x, nu1, nu2, zero_guess, s));
     return MLAMG_OK;
 }
 
-static int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
+int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess, cudaStream_t s) {
     if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
     if (nu1 < 0 || nu2 < 0) return set_error(MLAMG_EINVAL, "negative sweep count");
     if (b == x) return set_error(MLAMG_EINVAL, "vcycle: b aliases x");
@@ -294,25 +201,6 @@ static int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int n
         h->g_b = b; h->g_x = x; h->g_nu1 = nu1; h->g_nu2 = nu2; h->g_zero = zero_guess ? 1 : 0;
     }
     MLAMG_CUDA(cudaGraphLaunch(h->gexec, s));
-    return MLAMG_OK;
-}
-
-// turns CUDA-graph replay of the cycle on for the lifetime of a solver call (the host syncs of the dot products
-// would otherwise expose the launch time of every kernel of the cycle), restoring the caller's setting afterwards
-struct GraphScope {
-    mlamg_hierarchy *h;
-    bool saved;
-    explicit GraphScope(mlamg_hierarchy *hh) : h(hh), saved(hh->use_graph) { h->use_graph = true; }
-    ~GraphScope() { h->use_graph = saved; }
-};
-
-static int ensure_pcg(mlamg_hierarchy *h) {
-    if (h->pcg_r) return MLAMG_OK;
-    const size_t bytes = (size_t)h->lv[0].A.n * h->esz;
-    MLAMG_CUDA(cudaMalloc(&h->pcg_r, bytes));
-    MLAMG_CUDA(cudaMalloc(&h->pcg_z, bytes));
-    MLAMG_CUDA(cudaMalloc(&h->pcg_p, bytes));
-    MLAMG_CUDA(cudaMalloc(&h->pcg_ap, bytes));
     return MLAMG_OK;
 }
 
@@ -364,13 +252,6 @@ static int ensure_pipe(mlamg_hierarchy *h, cudaStream_t s) {
         P.need[k] = need;
     }
     P.ready = true;
-    return MLAMG_OK;
-}
-
-static int fetch_scalar(mlamg_hierarchy *h, int idx, double *out, cudaStream_t s) {
-    MLAMG_CUDA(cudaMemcpyAsync(h->hscal + idx, h->dscal + idx, sizeof(double), cudaMemcpyDeviceToHost, s));
-    MLAMG_CUDA(cudaStreamSynchronize(s));
-    *out = h->hscal[idx];
     return MLAMG_OK;
 }
 
@@ -487,8 +368,6 @@ int mlamg_hierarchy_finalize(mlamg_hierarchy_t h, mlamg_stream_t stream) {
             MLAMG_CUDA(cudaMalloc(&lev.r, bytes));
         }
     }
-    MLAMG_CUDA(cudaMalloc(&h->dscal, 8 * sizeof(double)));
-    MLAMG_CUDA(cudaMallocHost(&h->hscal, 8 * sizeof(double)));
     h->finalized = true;
     return MLAMG_OK;
 }
@@ -501,9 +380,7 @@ int mlamg_hierarchy_destroy(mlamg_hierarchy_t h) {
         if (lev.tmp) cudaFree(lev.tmp);
         if (lev.r) cudaFree(lev.r);
     }
-    if (h->pcg_r) { cudaFree(h->pcg_r); cudaFree(h->pcg_z); cudaFree(h->pcg_p); cudaFree(h->pcg_ap); }
-    if (h->dscal) cudaFree(h->dscal);
-    if (h->hscal) cudaFreeHost(h->hscal);
+    solver_state_free(h);
     if (h->host_b) cudaFree(h->host_b);
     if (h->host_x) cudaFree(h->host_x);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
@@ -559,81 +436,6 @@ double mlamg_hierarchy_cycle_bytes(mlamg_hierarchy_t h, int nu1, int nu2, int ze
 int mlamg_vcycle(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, int zero_guess, mlamg_stream_t stream) {
     MLAMG_TRY(check_handle(h));
     return vcycle_run(h, b, x, nu1, nu2, zero_guess, as_stream(stream));
-}
-
-int mlamg_solve(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double tol_abs, int maxiter,
-                double *res_host, int *niter_host, mlamg_stream_t stream) {
-    MLAMG_TRY(check_handle(h));
-    cudaStream_t s = as_stream(stream);
-    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
-    if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "solve: bad maxiter/res_host");
-    MLAMG_TRY(ensure_pcg(h));
-    GraphScope graph_on(h);      // b and x are fixed across the iterations: every cycle after the first is one graph launch
-    const Csr &A = h->lv[0].A;
-    int it = 0;
-    double nrm2 = 0.0;
-    MLAMG_TRY(mlamg_residual_csr(h->dtype, A.n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, h->pcg_r, h->dscal, stream));
-    MLAMG_TRY(fetch_scalar(h, 0, &nrm2, s));
-    res_host[0] = sqrt(nrm2);
-    while (it < maxiter && !(res_host[it] <= tol_abs)) {
-        MLAMG_TRY(vcycle_run(h, b, x, nu1, nu2, 0, s));
-        MLAMG_TRY(mlamg_residual_csr(h->dtype, A.n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, h->pcg_r, h->dscal, stream));
-        MLAMG_TRY(fetch_scalar(h, 0, &nrm2, s));
-        it++;
-        res_host[it] = sqrt(nrm2);
-    }
-    if (niter_host) *niter_host = it;
-    return MLAMG_OK;
-}
-
-int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter, double *res_host,
-              int *niter_host, mlamg_stream_t stream) {
-    MLAMG_TRY(check_handle(h));
-    cudaStream_t s = as_stream(stream);
-    if (!h->finalized) return set_error(MLAMG_EINVAL, "hierarchy not finalized");
-    if (maxiter < 0 || !res_host) return set_error(MLAMG_EINVAL, "pcg: bad maxiter/res_host");
-    MLAMG_TRY(ensure_pcg(h));
-    GraphScope graph_on(h);      // the preconditioner is always applied to (r, z): one graph launch per iteration
-    const Csr &A = h->lv[0].A;
-    const int n = A.n, dt = h->dtype;
-    void *r = h->pcg_r, *z = h->pcg_z, *p = h->pcg_p, *ap = h->pcg_ap;
-    double bb = 0.0, rr = 0.0, rz = 0.0, pap = 0.0;
-    MLAMG_TRY(mlamg_dot(dt, n, b, b, h->dscal + 1, stream));
-    MLAMG_TRY(mlamg_residual_csr(dt, n, (int)A.nnz, A.rowptr, A.col, A.val, x, b, r, h->dscal, stream));
-    MLAMG_TRY(fetch_scalar(h, 1, &bb, s));
-    MLAMG_TRY(fetch_scalar(h, 0, &rr, s));
-    const double nb = sqrt(bb);
-    const double stop = rtol * (nb != 0.0 ? nb : 1.0);
-    res_host[0] = sqrt(rr);
-    int it = 0;
-    if (res_host[0] <= stop || maxiter == 0) { if (niter_host) *niter_host = 0; return MLAMG_OK; }
-    MLAMG_TRY(vcycle_run(h, r, z, nu1, nu2, 1, s));
-    MLAMG_CUDA(cudaMemcpyAsync(p, z, (size_t)n * h->esz, cudaMemcpyDeviceToDevice, s));
-    MLAMG_TRY(mlamg_dot(dt, n, r, z, h->dscal + 2, stream));
-    MLAMG_TRY(fetch_scalar(h, 2, &rz, s));
-    for (it = 1; it <= maxiter; it++) {
-        MLAMG_TRY(mlamg_spmv_csr(dt, n, (int)A.nnz, A.rowptr, A.col, A.val, p, ap, stream));
-        MLAMG_TRY(mlamg_dot(dt, n, p, ap, h->dscal + 3, stream));
-        MLAMG_TRY(fetch_scalar(h, 3, &pap, s));
-        const double alpha = rz / pap;
-        MLAMG_TRY(mlamg_axpby(dt, n, alpha, p, 1.0, x, stream));
-        MLAMG_TRY(mlamg_axpby(dt, n, -alpha, ap, 1.0, r, stream));
-        MLAMG_TRY(mlamg_dot(dt, n, r, r, h->dscal, stream));
-        MLAMG_TRY(fetch_scalar(h, 0, &rr, s));
-        res_host[it] = sqrt(rr);
-        if (res_host[it] <= stop) break;
-        if (it == maxiter) break;
-        MLAMG_TRY(vcycle_run(h, r, z, nu1, nu2, 1, s));
-        double rz_new = 0.0;
-        MLAMG_TRY(mlamg_dot(dt, n, r, z, h->dscal + 2, stream));
-        MLAMG_TRY(fetch_scalar(h, 2, &rz_new, s));
-        const double beta = rz_new / rz;
-        rz = rz_new;
-        MLAMG_TRY(mlamg_axpby(dt, n, 1.0, z, beta, p, stream));
-    }
-    if (it > maxiter) it = maxiter;
-    if (niter_host) *niter_host = it;
-    return MLAMG_OK;
 }
 
 int mlamg_vcycle_host(mlamg_hierarchy_t h, const void *b_host, void *x_host, int nu1, int nu2, int cycles,

@@ -79,7 +79,9 @@ SIGNATURES = {
     "mlamg_hierarchy_use_graph": (I, [P, I]),
     "mlamg_vcycle": (I, [P, P, P, I, I, I, P]),
     "mlamg_solve": (I, [P, P, P, I, I, D, I, P, P, P]),
+    "mlamg_solve_ex": (I, [P, P, P, I, I, I, D, I, P, P, P]),
     "mlamg_pcg": (I, [P, P, P, I, I, D, I, P, P, P]),
+    "mlamg_solver_loop_mode": (I, [P]),
     "mlamg_vcycle_host": (I, [P, P, P, I, I, I, P]),
     "mlamg_peer_alloc": (I, [LL, P, P]),
     "mlamg_peer_open": (I, [P, P]),

@@ -128,7 +128,7 @@ class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
     def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
-                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True, fuse_pre=True):
+                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True, fuse_pre=True, coarse_inv=None):
         """levels: list[Level] in the REFERENCE numbering (what setup produced and what parity is checked on).
 
         renumber (default on): the cycle runs on apply copies whose coarse levels are renumbered spatially
@@ -153,7 +153,8 @@ class Hierarchy:
         for lev in levels[:-1]:
             if lev.dw is None:
                 lev.dw = core.smoother_diag(lev.A, smoother, jacobi_weight)
-        self.coarse_inv = core.dense_inverse(levels[-1].A)
+        # coarse_inv: caller-supplied dense (pseudo-)inverse of the coarsest operator (the singular mode of amg_2_v)
+        self.coarse_inv = core.dense_inverse(levels[-1].A) if coarse_inv is None else coarse_inv.to(self.dtype).contiguous()
         self.renumbered = bool(renumber) and len(levels) > 2
         self._apply = self._renumbered_copies() if self.renumbered else [(l.A, l.P, l.R, l.dw) for l in levels]
         self._h = ctypes.c_void_p()
@@ -298,6 +299,21 @@ class Hierarchy:
         out = xd.cpu().numpy() if is_np else xd
         return (out, hist) if return_residuals else out
 
+    def solve_device(self, b, x, tol=1e-8, maxiter=100, nu1=1, nu2=1, accel="cg"):
+        """solve() on device tensors without any host copy of the vectors: x (initial guess) is updated in place.
+        -> (x, residual history)"""
+        res = (ctypes.c_double * (maxiter + 1))()
+        nit = ctypes.c_int(0)
+        if accel == "cg":
+            check(lib.mlamg_pcg(self._h, ptr(b), ptr(x), nu1, nu2, tol, maxiter, res, ctypes.byref(nit), stream()))
+        elif accel is None:
+            nb = float(torch.linalg.vector_norm(b).item())
+            check(lib.mlamg_solve(self._h, ptr(b), ptr(x), nu1, nu2, tol * (nb if nb != 0 else 1.0), maxiter, res,
+                                  ctypes.byref(nit), stream()))
+        else:
+            raise NotImplementedError(f"solve_device: accel={accel!r}")
+        return x, np.array(res[:nit.value + 1])
+
     def _gmres(self, b, x, tol, maxiter, nu1, nu2, restart):
         """Left-preconditioned GMRES(restart), modified Gram-Schmidt + Givens; x updated in place.  The operator
         applications (A v, one V-cycle per Krylov vector) and the dot products / updates run in libmlamg_b200.so;
@@ -357,12 +373,23 @@ class Hierarchy:
                 break
         return np.array(res)
 
-    def solve_abs(self, b, x, tol_abs, maxiter, nu1=1, nu2=1):
-        """Stationary iteration with an ABSOLUTE residual tolerance (MLAMG.py:189-195), device tensors."""
+    SOLVE_XNORM, SOLVE_REMOVE_MEAN, SOLVE_NO_INITIAL_CHECK = 1, 2, 4
+
+    def solve_abs(self, b, x, tol_abs, maxiter, nu1=1, nu2=1, flags=0):
+        """Stationary iteration with an ABSOLUTE tolerance (MLAMG.py:189-195, multigrid.py:173-199), device tensors, x
+        updated in place.  The whole loop runs on the device (one graph launch, one host sync).  flags: SOLVE_XNORM
+        measures ||x|| instead of ||b - A x||, SOLVE_REMOVE_MEAN subtracts the mean after every cycle,
+        SOLVE_NO_INITIAL_CHECK always runs one cycle first.  -> (x, history incl. the initial value)."""
         res = (ctypes.c_double * (maxiter + 1))()
         nit = ctypes.c_int(0)
-        check(lib.mlamg_solve(self._h, ptr(b), ptr(x), nu1, nu2, float(tol_abs), maxiter, res, ctypes.byref(nit), stream()))
+        check(lib.mlamg_solve_ex(self._h, ptr(b), ptr(x), nu1, nu2, int(flags), float(tol_abs), maxiter, res, ctypes.byref(nit),
+                                 stream()))
         return x, np.array(res[:nit.value + 1])
+
+    @property
+    def loop_mode(self):
+        """'while-node' when the solver loops run as a CUDA-graph WHILE node, 'host' for the fallback, None before a solve"""
+        return {1: "while-node", -1: "host", 0: None}[int(lib.mlamg_solver_loop_mode(self._h))]
 
     def apply_host(self, b_host, x_host, nu1=1, nu2=1, cycles=1):
         """Preconditioner apply on HOST arrays (PETSc PC.apply shape): H2D, V-cycle(s), D2H inside the call.

@@ -83,33 +83,76 @@ def smoothed_aggregation_jacobi(A, Agg, omega=None, lam_max=None):
     return mlamg.sa_prolongator(Ad, Aggd, omega).to_scipy()
 
 
-class _TwoLevel:
-    """Device state of the two-level cycle shared by amg_2_v / amg_2_v_torch / the PC plugin."""
+MAX_DENSE_COARSE = 8192      # coarse operators up to this size get an explicit dense inverse (2 x 0.5 GB of fp64 at the limit)
 
-    def __init__(self, A, P, singular=False):
+
+class _TwoLevel:
+    """Device state of the two-level cycle shared by amg_2_v / amg_2_v_torch / the PC plugin.
+
+    Coarse solve (the reference factorises A_H once with SuperLU, :168 / MLAMG.py:122):
+      k <= max_dense : explicit dense inverse (cuSOLVER getrf/getrs once), one GEMV per iteration.  C1 (k = 6 554):
+                       0.34 GB, 60 us per apply.
+      k >  max_dense : the dense inverse would need 2 k^2 doubles (C2, k = 56 624: 51 GB) — A_H gets its own multilevel
+                       hierarchy instead and every coarse solve is an inner V-cycle-preconditioned CG to a relative
+                       residual of 1e-14 (an exact solve to rounding; a few MB).  A_H must be SPD for that.
+    singular=True (lsqr min-norm solve, :179) needs the dense pseudo-inverse and is limited to k <= max_dense."""
+
+    def __init__(self, A, P, singular=False, max_dense=None):
+        max_dense = MAX_DENSE_COARSE if max_dense is None else max_dense
         self.A = core.DeviceCSR.wrap(A)
         self.P = core.DeviceCSR.wrap(P, self.A.dtype)
         self.R = core.transpose(self.P)
         self.AH = mlamg.galerkin(self.A, self.P, self.R)
+        k = self.AH.shape[0]
+        self.inner = None
+        self.AHinv = None
         if singular:
+            if k > max_dense:
+                raise mlamg.MlamgError(3, f"singular two-level solve: coarse size {k} exceeds the dense pseudo-inverse limit "
+                                          f"{max_dense}")
             # lsqr min-norm solve of the singular coarse problem (:179) -> dense pseudo-inverse
             dense = torch.zeros(self.AH.shape, dtype=torch.float64, device="cuda")
-            core.check(core.lib.mlamg_csr_to_dense(1, self.AH.shape[0], core.ptr(self.AH.rowptr), core.ptr(self.AH.col),
+            core.check(core.lib.mlamg_csr_to_dense(1, k, core.ptr(self.AH.rowptr), core.ptr(self.AH.col),
                                                    core.ptr(self.AH.astype(torch.float64).val), core.ptr(dense),
                                                    core.stream()))
             self.AHinv = torch.linalg.pinv(dense).to(self.A.dtype).contiguous()
-        else:
+        elif k <= max_dense:
             self.AHinv = core.dense_inverse(self.AH)
+        else:
+            self.inner = mlamg.build_hierarchy(self.AH, aggregates="lloyd", ratio=0.1, distance="unit", rand=0,
+                                               max_coarse=1000, max_levels=12)
         n = self.A.shape[0]
         self.r = torch.empty(n, dtype=self.A.dtype, device="cuda")
-        self.rc = torch.empty(self.AH.shape[0], dtype=self.A.dtype, device="cuda")
+        self.rc = torch.empty(k, dtype=self.A.dtype, device="cuda")
         self.ec = torch.empty_like(self.rc)
+        self._H = {}
+
+    def coarse_solve(self, rc, ec):
+        if self.inner is None:
+            return core.gemv(self.AHinv, rc, out=ec)
+        ec.zero_()
+        _, hist = self.inner.solve_device(rc, ec, tol=1e-14 if self.A.dtype == torch.float64 else 1e-6, maxiter=200, accel="cg")
+        if not hist[-1] <= 1e-12 * max(hist[0], 1e-300) and self.A.dtype == torch.float64:
+            raise SingularCoarseError(4, f"inner coarse solve stalled at a relative residual of {hist[-1] / hist[0]:.2e} "
+                                         "(is P^T A P symmetric positive definite?)")
+        return ec
 
     def coarse_correct(self, b, x):
         core.residual(self.A, x, b, out=self.r)
         core.spmv(self.R, self.r, out=self.rc)
-        core.gemv(self.AHinv, self.rc, out=self.ec)
+        self.coarse_solve(self.rc, self.ec)
         core.spmv_add(self.P, self.ec, x)
+
+    def hierarchy(self, smoother, jacobi_weight):
+        """the two levels as an mlamg Hierarchy (dense coarse level): its stationary solve runs the whole
+        amg_2_v / MLAMG loop on the device"""
+        key = (smoother, float(jacobi_weight))
+        if key not in self._H:
+            from mlamg.hierarchy import Level, Hierarchy
+            L0, L1 = Level(self.A), Level(self.AH)
+            L0.P, L0.R = self.P, self.R
+            self._H[key] = Hierarchy([L0, L1], smoother=smoother, jacobi_weight=jacobi_weight, coarse_inv=self.AHinv)
+        return self._H[key]
 
 
 def amg_2_v(A, P, b, x,
@@ -124,7 +167,9 @@ def amg_2_v(A, P, b, x,
     """Two-level AMG solver -> (x, conv_factor, err, num_iterations)  (reference :111-210).
 
     Tolerances are absolute; err[i] = ||b - A x||_2 if res_tol is set else ||x||_2; a singular
-    coarse operator returns (x, 1.0, err, 0) without raising, as the reference does."""
+    coarse operator returns (x, 1.0, err, 0) without raising, as the reference does.
+    smoother='gauss_seidel' (the reference's pyamg sweep, bit-exact level-scheduled kernel) runs the loop from the
+    host; 'jacobi' / 'l1_jacobi' run the whole loop on the device (one graph launch, mlamg_solve_ex)."""
     if res_tol is None and error_tol is None:
         raise RuntimeError('One of res_tol or error_tol must be set!')
     tol = res_tol if res_tol is not None else error_tol
@@ -136,37 +181,47 @@ def amg_2_v(A, P, b, x,
     Ad = tl.A
     bd = core.as_vec(np.asarray(b), Ad.dtype)
     xd = core.as_vec(np.asarray(x), Ad.dtype).clone()
-    tmp = torch.empty_like(xd)
-    if smoother == 'gauss_seidel':
-        sched = core.GaussSeidelSchedule(Ad)
-    elif smoother in ('jacobi', 'l1_jacobi'):
-        dw = core.smoother_diag(Ad, smoother, jacobi_weight)
-    else:
+    if smoother not in ('gauss_seidel', 'jacobi', 'l1_jacobi'):
         raise ValueError(f'unknown smoother {smoother!r}')
 
-    def relax(xd, tmp, steps):
+    if smoother != 'gauss_seidel' and tl.inner is None:
+        H = tl.hierarchy(smoother, jacobi_weight)
+        flags = H.SOLVE_NO_INITIAL_CHECK | (H.SOLVE_XNORM if res_tol is None else 0) | (H.SOLVE_REMOVE_MEAN if singular else 0)
+        _, hist = H.solve_abs(bd, xd, tol, max_iter, pre_smoothing_steps, post_smoothing_steps, flags)
+        nit = len(hist) - 1
+        err[:nit] = hist[1:]
+        if nit < max_iter or (nit and hist[-1] <= tol):
+            err = err[:nit]
+    else:
+        tmp = torch.empty_like(xd)
         if smoother == 'gauss_seidel':
-            sched.sweep(bd, xd, iterations=steps)
-            return xd, tmp
-        for _ in range(steps):
-            core.jacobi_sweep(Ad, dw, bd, xd, tmp)
-            xd, tmp = tmp, xd
-        return xd, tmp
-
-    for i in range(max_iter):
-        xd, tmp = relax(xd, tmp, pre_smoothing_steps)
-        tl.coarse_correct(bd, xd)
-        xd, tmp = relax(xd, tmp, post_smoothing_steps)
-        if singular:
-            xd -= xd.mean()
-        if res_tol is not None:
-            _, e = core.residual(Ad, xd, bd, out=tl.r, norm=True)
+            sched = core.GaussSeidelSchedule(Ad)
         else:
-            e = float(np.sqrt(core.dot(xd, xd)))
-        err[i] = e
-        if e <= tol:
-            err = err[:i + 1]
-            break
+            dw = core.smoother_diag(Ad, smoother, jacobi_weight)
+
+        def relax(xd, tmp, steps):
+            if smoother == 'gauss_seidel':
+                sched.sweep(bd, xd, iterations=steps)
+                return xd, tmp
+            for _ in range(steps):
+                core.jacobi_sweep(Ad, dw, bd, xd, tmp)
+                xd, tmp = tmp, xd
+            return xd, tmp
+
+        for i in range(max_iter):
+            xd, tmp = relax(xd, tmp, pre_smoothing_steps)
+            tl.coarse_correct(bd, xd)
+            xd, tmp = relax(xd, tmp, post_smoothing_steps)
+            if singular:
+                xd -= xd.mean()
+            if res_tol is not None:
+                _, e = core.residual(Ad, xd, bd, out=tl.r, norm=True)
+            else:
+                e = float(np.sqrt(core.dot(xd, xd)))
+            err[i] = e
+            if e <= tol:
+                err = err[:i + 1]
+                break
 
     if len(err) != 1:
         try:

@@ -70,7 +70,12 @@ class MLAMG(PCBase):
         return x
 
     def amg_2_v(self, P, b, x, pre_smoothing_steps=1, post_smoothing_steps=1, max_iter=500):
-        """Reference :148-197 on device tensors; stops when ||b - A x||_2 <= amg_rtol (absolute)."""
+        """Reference :148-197 on device tensors; stops when ||b - A x||_2 <= amg_rtol (absolute).  With a dense coarse
+        level the whole loop runs on the device (mlamg_solve_ex: one graph launch, one host sync per apply)."""
+        if self.two.inner is None:
+            H = self.two.hierarchy('jacobi', self.jacobi_weight)
+            H.solve_abs(b, x, self.amg_rtol, max_iter, pre_smoothing_steps, post_smoothing_steps, H.SOLVE_NO_INITIAL_CHECK)
+            return x
         for _ in range(max_iter):
             x = self.jacobi(b, x, nu=pre_smoothing_steps)
             self.two.coarse_correct(b, x)

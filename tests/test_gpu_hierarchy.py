@@ -277,17 +277,137 @@ class _FakePC:
         return self.m, self.m
 
 
-def test_pc_plugins():
+def test_pc_plugins_vs_oracle():
+    """MLAMG.apply against the restated MLAMG.py:148-212 (same seeded random guess, same P): identical iterate to
+    rounding; PyAMG.apply against the oracle's multilevel hierarchy + preconditioned GMRES."""
+    import scipy.sparse.linalg as spla
     from ns.preconditioner.MLAMG import MLAMG
     from ns.preconditioner.PyAMG import PyAMG
     A = oml.poisson((20, 20))
-    b = np.random.RandomState(0).randn(400)
-    # MLAMG stops on the absolute residual (MLAMG.py:194); PyAMG's GMRES stops on the preconditioned residual
-    for cls, tol in ((MLAMG, 2e-8), (PyAMG, 1e-6 * np.linalg.norm(b))):
-        pc = _FakePC(A)
-        p = cls()
-        p.initialize(pc)
-        X, Y = _FakeVec(b), _FakeVec(None)
-        np.random.seed(0)
-        p.apply(pc, X, Y)
-        assert np.linalg.norm(b - A @ Y.out) <= tol
+    n = A.shape[0]
+    b = np.random.RandomState(0).randn(n)
+    # --- MLAMG: P is built as the plugin builds it (Lloyd ratio 0.1 unit rand 0, SA with the ARPACK omega) and injected,
+    # so that both sides iterate on identical operators
+    Agg, _, _ = rp.lloyd_aggregation(A, ratio=0.1, distance="unit", rand=0)
+    P = sp.csr_matrix(rp.smoothed_aggregation_jacobi(A, Agg, omega=(4.0 / 3.0) / rp.lambda_max_dinv_a(A)))
+    pc = _FakePC(A)
+    pc.appctx["mlamg_P"] = P
+    p = MLAMG()
+    p.initialize(pc)
+    X, Y = _FakeVec(b), _FakeVec(None)
+    np.random.seed(0)
+    p.apply(pc, X, Y)
+    np.random.seed(0)
+    x0 = np.random.normal(size=n)                                   # the plugin's random guess (MLAMG.py:209)
+    lu = spla.splu(sp.csc_matrix(P.T @ A @ P), permc_spec="COLAMD")
+    x_ref, it_ref = rp.mlamg_amg_2_v(A, P, lu.solve, sp.diags((2.0 / 3.0) / A.diagonal()), b, x0, amg_rtol=1e-8)
+    assert np.linalg.norm(b - A @ Y.out) <= 1e-8 * (1 + 1e-6)
+    assert np.abs(Y.out - x_ref).max() <= 1e-11 * np.abs(x_ref).max(), np.abs(Y.out - x_ref).max()
+    # the same loop through the stationary solver of the two-level hierarchy: iteration count + history
+    H = p.two.hierarchy("jacobi", 2.0 / 3.0)
+    xd = torch.from_numpy(x0).cuda()
+    _, hist = H.solve_abs(torch.from_numpy(b).cuda(), xd, 1e-8, 500, 1, 1, H.SOLVE_NO_INITIAL_CHECK)
+    assert len(hist) - 1 == it_ref, (len(hist) - 1, it_ref)
+    assert H.loop_mode in ("while-node", "host")
+    # default construction (no injected P): the plugin's own Lloyd + Lanczos-omega P gives the same solve to 1e-8
+    pc2 = _FakePC(A)
+    p2 = MLAMG()
+    p2.initialize(pc2)
+    Y2 = _FakeVec(None)
+    np.random.seed(0)
+    p2.apply(pc2, X, Y2)
+    assert np.abs(Y2.out - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+    # --- PyAMG: multilevel hierarchy + left-preconditioned GMRES (PyAMG.py:94,119)
+    pc3 = _FakePC(A)
+    q = PyAMG()
+    q.initialize(pc3)
+    Y3 = _FakeVec(None)
+    q.apply(pc3, X, Y3)
+    lams = [(4.0 / 3.0) / L.omega_sa for L in q.Amg.levels[:-1]]
+    ref = oml.build_hierarchy(A, ratio=0.1, distance="unit", rand=0, lam_max=lams, max_levels=10, max_coarse=500)
+    xr, res_r, it_r = oml.gmres(ref, b, tol=1e-8, maxiter=200)
+    assert np.abs(Y3.out - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+def test_solver_loops_while_node_equals_host_fallback(monkeypatch):
+    """the device-resident PCG / stationary loops: the CUDA-graph WHILE node and the host-driven fallback run the same
+    kernels in the same order -> identical histories and iterates; both against the oracle"""
+    import mlamg
+    A = oml.poisson((40, 36))
+    n = A.shape[0]
+    b = np.random.RandomState(3).randn(n)
+    lam = [2.0, 1.9, 1.8]
+    ref = oml.build_hierarchy(A, ratio=0.1, distance="unit", rand=0, lam_max=lam, max_coarse=30)
+    out = {}
+    for mode in ("while", "host"):
+        if mode == "host":
+            monkeypatch.setenv("MLAMG_SOLVER_HOST_LOOP", "1")
+        H = mlamg.build_hierarchy(A, aggregates="lloyd", ratio=0.1, distance="unit", rand=0, lam_max=lam, max_coarse=30)
+        xg, res_g = H.solve(b, tol=1e-9, maxiter=100, accel="cg", return_residuals=True)
+        xs, res_s = H.solve(b, tol=1e-6, maxiter=100, return_residuals=True)
+        x2, res_2 = H.solve(b, tol=1e-9, maxiter=7, accel="cg", return_residuals=True)       # maxiter reached
+        x3, res_3 = H.solve(np.zeros(n), tol=1e-9, maxiter=7, accel="cg", return_residuals=True)   # converged at entry
+        assert len(res_2) == 8 and len(res_3) == 1
+        out[mode] = (xg, res_g, xs, res_s, H.loop_mode)
+    assert out["host"][4] == "host"
+    if out["while"][4] == "while-node":
+        for i in range(4):
+            assert np.array_equal(out["while"][i], out["host"][i])
+    xr, res_r, it_r = oml.pcg(ref, b, tol=1e-9, maxiter=100)
+    assert len(out["while"][1]) - 1 == it_r and hist_err0(out["while"][1], res_r) < RTOL64 * 10
+    xr, res_r = oml.solve(ref, b, tol=1e-6, maxiter=100)
+    assert len(out["while"][3]) == len(res_r) and hist_err0(out["while"][3], res_r) < RTOL64
+
+
+def test_amg_2_v_modes_on_device_loop():
+    """amg_2_v with Jacobi smoothing runs behind mlamg_solve_ex: error_tol mode (||x||), singular mode (pseudo-inverse +
+    mean removal), max_iter exhaustion — all against the restated reference loop"""
+    import ns.lib.multigrid as mg
+    z = load_golden("poisson2d_24_unit")
+    A, P = csr_from(z, "A"), csr_from(z, "P")
+    n = A.shape[0]
+    x0 = np.random.RandomState(0).randn(n)
+    x0 /= np.linalg.norm(x0, 2)
+    kw = dict(smoother="jacobi", jacobi_weight=2 / 3)
+    ref = rp.amg_2_v(A, P, np.zeros(n), x0, error_tol=1e-9, pre_smoothing_steps=2, post_smoothing_steps=1, **kw)
+    got = mg.amg_2_v(A, P, np.zeros(n), x0, error_tol=1e-9, pre_smoothing_steps=2, post_smoothing_steps=1, **kw)
+    assert got[3] == ref[3] and hist_err0(got[2], ref[2]) < RTOL64 and abs(got[1] - ref[1]) < 1e-9
+    ref = rp.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-30, max_iter=12, **kw)
+    got = mg.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-30, max_iter=12, **kw)
+    assert got[3] == ref[3] == 12 and len(got[2]) == 12 and hist_err0(got[2], ref[2]) < RTOL64
+    # singular (pure Neumann) problem: graph Laplacian of the grid, constant null space
+    G = sp.csr_matrix(oml.poisson((12, 11)))
+    G = G - sp.diags(G.diagonal())
+    L = (sp.diags(-np.asarray(G.sum(axis=1)).ravel()) + G).tocsr()
+    Agg, _, _ = rp.lloyd_aggregation(L, ratio=0.15, distance="unit", rand=0)
+    Pn = sp.csr_matrix(rp.smoothed_aggregation_jacobi(L, Agg, omega=2.0 / 3.0))
+    m = L.shape[0]
+    b = np.random.RandomState(1).randn(m)
+    b -= b.mean()
+    ref = rp.amg_2_v(L, Pn, b, np.zeros(m), res_tol=1e-8, singular=True, **kw)
+    got = mg.amg_2_v(L, Pn, b, np.zeros(m), res_tol=1e-8, singular=True, **kw)
+    # the reference solves the singular coarse problem with lsqr at its default 1e-6 tolerances; the exact pseudo-inverse
+    # used here agrees with it to that accuracy only
+    assert abs(got[3] - ref[3]) <= 1 and hist_err0(got[2][:8], ref[2][:8]) < 1e-4
+
+
+def test_two_level_inner_hierarchy_coarse_solve():
+    """coarse operators above the dense limit are solved by an inner AMG-preconditioned CG (rtol 1e-14): same two-level
+    histories as the dense coarse inverse"""
+    import ns.lib.multigrid as mg
+    z = load_golden("poisson2d_24_unit")
+    A, P = csr_from(z, "A"), csr_from(z, "P")
+    n = A.shape[0]
+    x0 = np.random.RandomState(0).randn(n)
+    x0 /= np.linalg.norm(x0, 2)
+    ref = rp.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-10)
+    old = mg.MAX_DENSE_COARSE
+    try:
+        mg.MAX_DENSE_COARSE = 16
+        got = mg.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-10)
+        gotj = mg.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-10, smoother="jacobi", jacobi_weight=2 / 3)
+    finally:
+        mg.MAX_DENSE_COARSE = old
+    assert got[3] == ref[3] and hist_err0(got[2], ref[2]) < RTOL64 * 10
+    refj = rp.amg_2_v(A, P, np.zeros(n), x0, res_tol=1e-10, smoother="jacobi", jacobi_weight=2 / 3)
+    assert gotj[3] == refj[3] and hist_err0(gotj[2], refj[2]) < RTOL64 * 10

@@ -1,5 +1,6 @@
 """Timed runs of the BASELINE.json configurations other than the bench workload (development aid).
 
+    python tools/run_configs.py 1            # 2D 5-point 256^2, the reference's canonical two-level path, CPU oracle timed beside
     python tools/run_configs.py 2            # 3D 7-point 128^3: setup + AMG-preconditioned CG (1 GPU)
     python tools/run_configs.py 3            # 2D Voronoi jump diffusion, 4M DOF, GNN-style aggregates and P weights (1 GPU)
     torchrun --nproc-per-node N tools/run_configs.py 4 [npts]   # Delaunay P1 Laplacian, row-partitioned over N GPUs
@@ -43,6 +44,69 @@ def cycle_ms(H, b, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
+def config1():
+    """utils/evaluate_dataset.py:59-101 -> ns/lib/graph.py:156-239 -> ns/lib/multigrid.py:102-210 at 256^2, stage by
+    stage, second (warm) call timed; the CPU oracle (scipy + restated pyamg C loops, 1 core) beside every stage."""
+    import mlamg
+    import ns.lib.graph as g
+    import ns.lib.multigrid as mg
+    from oracle import multilevel as oml, reference_path as rp
+    A = oml.poisson((256, 256))
+    n = A.shape[1]
+    b = np.zeros(n)
+    x = np.random.RandomState(0).randn(n)
+    x /= np.linalg.norm(x, 2)
+
+    def warm(fn, reps=2):
+        out = None
+        for _ in range(reps):
+            out, t = sync_time(fn)
+        return out, t
+
+    def cpu(fn):
+        t = time.perf_counter()
+        out = fn()
+        return out, time.perf_counter() - t
+    (Agg, roots, seeds), t_agg = warm(lambda: g.lloyd_aggregation(A, ratio=0.1, distance="unit", rand=0))
+    (Agg_c, roots_c, _), t_agg_c = cpu(lambda: rp.lloyd_aggregation(A, ratio=0.1, distance="unit", rand=0))
+    info = {}
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    lam, t_lam = warm(lambda: mlamg.lambda_max(Ad, info=info))
+    lam_c, t_lam_c = cpu(lambda: rp.lambda_max_dinv_a(A))
+    P, t_p = warm(lambda: mg.smoothed_aggregation_jacobi(A, Agg, omega=(4.0 / 3.0) / lam))
+    P_c, t_p_c = cpu(lambda: sp_csr(rp.smoothed_aggregation_jacobi(A, Agg_c, omega=(4.0 / 3.0) / lam_c)))
+    out = {"config": 1, "workload": "poisson2d_5pt_256^2 lloyd 0.1 unit rand 0 + SA P + amg_2_v(res_tol 1e-10), fp64",
+           "dof": n, "coarse": int(Agg.shape[1]), "labels_equal": bool(np.array_equal(Agg.indices, Agg_c.indices)),
+           "lambda_max": {"gpu": lam, "cpu_arpack": lam_c, "lanczos_steps": info.get("steps"), "residual": info.get("residual")},
+           "stages_ms": {"lloyd_aggregation": [round(t_agg * 1e3, 2), round(t_agg_c * 1e3, 2)],
+                         "lambda_max": [round(t_lam * 1e3, 2), round(t_lam_c * 1e3, 2)],
+                         "smoothed_aggregation_jacobi": [round(t_p * 1e3, 2), round(t_p_c * 1e3, 2)]},
+           "stages_ms_columns": ["gpu (warm, incl. H2D/D2H of the scipy in/outputs)", "cpu oracle (1 core)"]}
+    for sm in ("gauss_seidel", "jacobi"):
+        kw = dict(res_tol=1e-10, jacobi_weight=2.0 / 3.0, smoother=sm)
+        got, t_g = warm(lambda: mg.amg_2_v(A, P, b, x.copy(), **kw))
+        ref, t_c = cpu(lambda: rp.amg_2_v(A, P_c, b, x.copy(), **kw))
+        out["stages_ms"][f"amg_2_v[{sm}]"] = [round(t_g * 1e3, 2), round(t_c * 1e3, 2)]
+        out[f"amg_2_v[{sm}]"] = {"iterations": [int(got[3]), int(ref[3])], "conv_factor": [float(got[1]), float(ref[1])],
+                                 "history_err0": float(np.max(np.abs(got[2] - ref[2])) / ref[2][0])}
+    # inside amg_2_v[jacobi] on the GPU: two-level setup vs the device-resident loop
+    tl, t_setup = warm(lambda: mg._TwoLevel(A, P))
+    H, t_h = sync_time(lambda: tl.hierarchy("jacobi", 2.0 / 3.0))
+    bd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    xd = torch.from_numpy(x).cuda()
+    H.solve_abs(bd, xd.clone(), 1e-10, 500, 1, 1, H.SOLVE_NO_INITIAL_CHECK)
+    x2 = xd.clone()
+    (_, hist), t_loop = sync_time(lambda: H.solve_abs(bd, x2, 1e-10, 500, 1, 1, H.SOLVE_NO_INITIAL_CHECK))
+    out["amg_2_v[jacobi]_gpu_breakdown_ms"] = {"galerkin+dense_inverse": round(t_setup * 1e3, 2), "Q/scaled copies + handle": round(t_h * 1e3, 2),
+                                               "loop": round(t_loop * 1e3, 2), "iterations": len(hist) - 1, "loop_mode": H.loop_mode}
+    print(json.dumps(out), flush=True)
+
+
+def sp_csr(M):
+    import scipy.sparse as sp
+    return sp.csr_matrix(M)
+
+
 def config2():
     import mlamg
     n = 128
@@ -57,7 +121,7 @@ def config2():
     ms = cycle_ms(H, b)
     print(json.dumps({"config": 2, "workload": "poisson3d_7pt_128^3 setup + PCG(V(1,1) Jacobi) rtol 1e-8", "dof": n ** 3,
                       "levels": [l.A.shape[0] for l in H.levels], "setup_s": round(t_setup, 3), "pcg_iterations": len(res) - 1,
-                      "pcg_solve_ms": round(t_solve * 1e3, 2), "final_rel_residual": float(res[-1] / np.linalg.norm(b.cpu().numpy())),
+                      "pcg_solve_ms": round(t_solve * 1e3, 2), "pcg_loop_mode": H.loop_mode, "final_rel_residual": float(res[-1] / np.linalg.norm(b.cpu().numpy())),
                       "vcycle_ms": round(ms, 4), "vcycle_gdof_per_s": round(n ** 3 / ms / 1e6, 2)}), flush=True)
 
 
@@ -150,7 +214,9 @@ def config4(npts):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "2"
-    if which == "2":
+    if which == "1":
+        config1()
+    elif which == "2":
         config2()
     elif which == "3":
         config3()
