@@ -300,7 +300,7 @@ def test_pc_plugins_vs_oracle():
     np.random.seed(0)
     x0 = np.random.normal(size=n)                                   # the plugin's random guess (MLAMG.py:209)
     lu = spla.splu(sp.csc_matrix(P.T @ A @ P), permc_spec="COLAMD")
-    x_ref, it_ref = rp.mlamg_amg_2_v(A, P, lu.solve, sp.diags((2.0 / 3.0) / A.diagonal()), b, x0, amg_rtol=1e-8)
+    x_ref, it_ref = rp.mlamg_amg_2_v(A, P, lu.solve, sp.diags((2.0 / 3.0) / A.diagonal()), b, x0.copy(), amg_rtol=1e-8)
     assert np.linalg.norm(b - A @ Y.out) <= 1e-8 * (1 + 1e-6)
     assert np.abs(Y.out - x_ref).max() <= 1e-11 * np.abs(x_ref).max(), np.abs(Y.out - x_ref).max()
     # the same loop through the stationary solver of the two-level hierarchy: iteration count + history
