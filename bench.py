@@ -40,8 +40,11 @@ METRIC = "vcycle_gdof_per_s"
 UNIT = "GDOF/s"
 
 
-def workload_name(n, ngpu):
-    return (f"poisson3d_7pt_{n}^3_per_gpu_fp64_lloyd{RATIO}_SA_V(1,1)_jacobi" + (f"_x{ngpu}gpu_zslab" if ngpu > 1 else ""))
+def workload_name(n, ngpu, geometry="cube"):
+    if ngpu == 1:
+        return f"poisson3d_7pt_{n}^3_per_gpu_fp64_lloyd{RATIO}_SA_V(1,1)_jacobi"
+    nx, ny, nzl = (2 * n, 2 * n, n // 4) if geometry == "cube" else (n, n, n)
+    return (f"poisson3d_7pt_{n}^3_per_gpu_fp64_lloyd{RATIO}_SA_V(1,1)_jacobi_x{ngpu}gpu_zslab_global_{nx}x{ny}x{nzl * ngpu}")
 
 
 def measured_peak():
@@ -313,9 +316,9 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-def common_config(n, ngpu):
+def common_config(n, ngpu, geometry="cube"):
     """the keys both arms print identically (the reference arm runs the same workload)"""
-    return {"workload": workload_name(n, ngpu), "dof": n ** 3 * ngpu, "dof_per_gpu": n ** 3, "cycle": "V(1,1) zero-guess",
+    return {"workload": workload_name(n, ngpu, geometry), "dof": n ** 3 * ngpu, "dof_per_gpu": n ** 3, "cycle": "V(1,1) zero-guess",
             "aggregation": f"lloyd ratio {RATIO} unit rand 0 maxiter 10", "max_coarse": 1000}
 
 
@@ -364,9 +367,34 @@ def oracle_setup_parity(H, n, lams):
     return ref, par
 
 
+def dist_parity(args, comm):
+    """Before timing: the row-partitioned hierarchy on the SAME N ranks at a reduced per-rank size against the partitioned
+    CPU oracle (tests/dist_check.py: Lloyd labels, P and Galerkin operators bit for bit, V-cycle, PCG history and
+    iteration count).  Every rank checks its own rows; the verdicts are combined with an allreduce."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dist_check
+    t0 = time.time()
+    out = dist_check.run_check(args.parity_n, comm, geometry=args.geometry, verbose=True, extras=False)
+    flags = torch.tensor([int(out["ok"]), int(out["labels_equal"]), int(out["P_bitwise"]), int(out["A_bitwise"]),
+                          int(out["pcg_iters_equal"])], dtype=torch.int64, device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    errs = torch.tensor([out["vcycle_rel_err"], out["pcg_hist_err"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    f = [bool(v) for v in flags.cpu()]
+    return {"ok": f[0], "labels_equal": f[1], "P_bitwise": f[2], "A_bitwise": f[3], "pcg_iters_equal": f[4],
+            "vcycle_rel_err": float(errs[0]), "pcg_hist_err": float(errs[1]), "pcg_iterations": out["pcg_iterations"],
+            "dof_per_gpu": out["dof_per_gpu"], "ranks": comm.world, "geometry": args.geometry,
+            "dist_levels": out["dist_levels"], "tail_levels": out["tail_levels"], "halo_transport": out["halo_transport"],
+            "oracle": "oracle.multilevel.build_hierarchy_partitioned (scipy + restated pyamg loops) on every rank",
+            "seconds": round(time.time() - t0, 1)}
+
+
 def run_ours_distributed(args, rank, world, local, cpus=None):
-    """Weak scaling: n^3 DOF per GPU, global grid n x n x (n*world) in z-slabs, row-partitioned levels with
-    NCCL halo exchange overlapped with the interior rows, coarse levels replicated below 500k rows.
+    """Weak scaling: n^3 DOF per GPU in z-slabs (geometry 'cube': (2n) x (2n) x (n/4) per rank, i.e. the 512^3 cube of
+    BASELINE.json config 5 at n = 256 on 8 GPUs; 'slab': n x n x n per rank), row-partitioned levels with the peer-memory
+    halo exchange overlapped with the interior rows, coarse levels replicated below `--replicate-below` rows.
     value = global DOFs x cycles / max-over-ranks device time."""
     import torch
     import torch.distributed as dist
@@ -374,11 +402,20 @@ def run_ours_distributed(args, rank, world, local, cpus=None):
     from mlamg import core, distributed as md
     n = args.n
     comm = md.Comm()
+    parity = dist_parity(args, comm) if args.parity_n > 0 else None
+    if parity is not None and not parity["ok"]:
+        if rank == 0:
+            print(json.dumps({"error": "multi-GPU parity check failed; nothing was timed", "parity": parity}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(3)
+    torch.cuda.synchronize()
+    dist.barrier()
     t0 = time.time()
-    rowptr, col, val = md.poisson_slab(n, world, rank)
-    lam0 = 1.0 + (2.0 * np.cos(np.pi / (n + 1)) + np.cos(np.pi / (n * world + 1))) / 3.0    # analytic, anisotropic box
+    rowptr, col, val = md.poisson_slab(n, world, rank, geometry=args.geometry)
+    lam0 = md.slab_lambda_max(n, world, args.geometry)      # analytic, the global box
     H = md.DistHierarchy(rowptr, col, val, comm, ratio=RATIO, distance="unit", maxiter=10, rand=0,
-                         lam_max=[lam0], max_levels=8, max_coarse=1000, replicate_below=500000)
+                         lam_max=[lam0], max_levels=8, max_coarse=1000, replicate_below=args.replicate_below)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     N_loc = n ** 3
@@ -470,10 +507,12 @@ def run_ours_distributed(args, rank, world, local, cpus=None):
         out = {"metric": METRIC, "value": round(N_loc * world / ms / 1e6, 4), "unit": UNIT, "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(n, world), "dof": N_loc * world, "dof_per_gpu": N_loc,
-                          "distributed_levels": [int(o[-1]) for o in H.offsets[:-1]],
-                          "replicated_levels": [l.A.shape[0] for l in H.tail.levels], "cycle": "V(1,1) zero-guess",
-                          "halo_entries_fine": L0.A.plan.n_halo,
+               "config": common_config(n, world, args.geometry),
+               "parity": parity,
+               "detail": {"distributed_levels": [int(o[-1]) for o in H.offsets[:-1]],
+                          "replicated_levels": [l.A.shape[0] for l in H.tail.levels], "replicate_below": args.replicate_below,
+                          "halo_entries_fine": L0.A.plan.n_halo, "geometry": args.geometry,
+                          "slab_per_rank": list(md.slab_geometry(n, world, args.geometry)),
                           "halo_transport": ("tagged peer stores into CUDA-IPC windows over NVLink, boundary rows gather the halo in "
                                              "place, interior rows in between (no collective in the cycle)" if H.halo == "peer"
                                              else "NCCL all-to-all on a side stream overlapped with the interior rows"),
@@ -571,7 +610,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": common_config(args.n, args.gpus),
+           "config": common_config(args.n, args.gpus, args.geometry),
            "detail": {"sample_dof": N, "levels": [l.A.shape[0] for l in levels], "setup_s": round(setup_s, 2)},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "cores_available": os.cpu_count(), "kind": "port",
                             "sample": sample},
@@ -588,6 +627,11 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="grid side per GPU")
     ap.add_argument("--ref-n", type=int, default=0, help="grid side of the reference arm (0 = the same --n as the GPU arm)")
     ap.add_argument("--cpu-cycles", type=int, default=3, help="oracle cycles timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--geometry", default="cube", choices=["cube", "slab"],
+                    help="N > 1: 'cube' = z-slabs of (2n)x(2n)x(n/4) (512^3 global at n=256 on 8 GPUs, BASELINE config 5), "
+                         "'slab' = n x n x n per rank (global n x n x nN)")
+    ap.add_argument("--replicate-below", type=int, default=500000, help="N > 1: global rows below which levels are replicated")
+    ap.add_argument("--parity-n", type=int, default=48, help="N > 1: per-GPU grid side of the pre-timing parity check (0 = skip)")
     ap.add_argument("--profile", action="store_true", help="wrap `steps` plain-launch cycles in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -62,7 +62,7 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
 template <typename T, int LANES, int OP, bool NORM, bool HALO, int NBT>
 // 32 registers / 8 CTAs per SM for every variant with <= 4 entries in flight per lane (none spills): the row ops are
 // latency-bound gathers, occupancy is what hides them (restriction 136 -> 126 us with 8 instead of 6 CTAs per SM)
-__global__ void __launch_bounds__(ROW_THREADS, (!HALO && NBT <= 4) ? 8 : (NBT <= 4 ? 6 : 4))
+__global__ void __launch_bounds__(ROW_THREADS, NBT <= 4 ? 8 : 4)
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
                  const T *__restrict__ dw, T *y, double *__restrict__ partial,

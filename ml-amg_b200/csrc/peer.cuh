@@ -49,35 +49,59 @@ __device__ __forceinline__ void ll_store(float *slot_base, long long i, float v,
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
 
-// spin until element i of the region carries `tag`; on timeout record the error and return what is there
-__device__ __forceinline__ double ll_load(const double *slot_base, long long i, unsigned tag, unsigned long long *state) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(slot_base) + i;
+// Element i of the region is valid once it carries `tag`.  Fast path (inlined into the consuming row-op kernel): one
+// volatile load and a compare — in the overlapped cycle the value has almost always landed.  Slow path (out of line, so
+// that the spin state costs the row-op kernels no registers): spin with a wall-clock timeout.  A timeout sets the
+// channel's error word [3] and returns what is there; once the word is set every later wait on the channel gives up at
+// once (one dead peer costs one timeout per kernel, not one per halo element), and the host side refuses to use the
+// result (DistHierarchy checks the word after every solve / at every synchronisation point).
+static __device__ __noinline__ uint4 ll_spin16(const uint4 *p, unsigned tag, unsigned long long *state) {
     uint4 v;
     unsigned long long t0 = 0;
     for (unsigned spins = 0;; spins++) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
         if (v.y == tag && v.w == tag) break;
-        if (spins == 1024u) t0 = ll_global_ns();
-        if (spins > 1024u && (spins & 1023u) == 0u && ll_global_ns() - t0 > LL_TIMEOUT_NS) {
-            atomicExch(state + 3, 1ull);
-            break;
+        if ((spins & 1023u) == 0u) {
+            if (*(volatile unsigned long long *)(state + 3) != 0ull) break;      // the channel already timed out
+            if (spins == 0u) t0 = ll_global_ns();
+            else if (ll_global_ns() - t0 > LL_TIMEOUT_NS) {
+                atomicExch(state + 3, 1ull);
+                break;
+            }
         }
     }
-    return __hiloint2double((int)v.z, (int)v.x);
+    return v;
 }
-__device__ __forceinline__ float ll_load(const float *slot_base, long long i, unsigned tag, unsigned long long *state) {
-    const uint2 *p = reinterpret_cast<const uint2 *>(slot_base) + i;
+static __device__ __noinline__ uint2 ll_spin8(const uint2 *p, unsigned tag, unsigned long long *state) {
     uint2 v;
     unsigned long long t0 = 0;
     for (unsigned spins = 0;; spins++) {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
         if (v.y == tag) break;
-        if (spins == 1024u) t0 = ll_global_ns();
-        if (spins > 1024u && (spins & 1023u) == 0u && ll_global_ns() - t0 > LL_TIMEOUT_NS) {
-            atomicExch(state + 3, 1ull);
-            break;
+        if ((spins & 1023u) == 0u) {
+            if (*(volatile unsigned long long *)(state + 3) != 0ull) break;
+            if (spins == 0u) t0 = ll_global_ns();
+            else if (ll_global_ns() - t0 > LL_TIMEOUT_NS) {
+                atomicExch(state + 3, 1ull);
+                break;
+            }
         }
     }
+    return v;
+}
+
+__device__ __forceinline__ double ll_load(const double *slot_base, long long i, unsigned tag, unsigned long long *state) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(slot_base) + i;
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    if (!(v.y == tag && v.w == tag)) v = ll_spin16(p, tag, state);
+    return __hiloint2double((int)v.z, (int)v.x);
+}
+__device__ __forceinline__ float ll_load(const float *slot_base, long long i, unsigned tag, unsigned long long *state) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(slot_base) + i;
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    if (v.y != tag) v = ll_spin8(p, tag, state);
     return __uint_as_float(v.x);
 }
 

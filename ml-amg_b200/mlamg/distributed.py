@@ -189,6 +189,7 @@ class HaloPlan:
     def __init__(self, halo_ids, offsets, comm):
         self.comm = comm
         self.halo_ids = halo_ids
+        self.offsets = offsets
         self.n_halo = int(halo_ids.numel())
         lo = int(offsets[comm.rank])
         own = owners_of(halo_ids, offsets)
@@ -226,6 +227,10 @@ PEER_SPLIT_MIN_NNZ = int(_os.environ.get("MLAMG_PEER_SPLIT_MIN_NNZ", 2_000_000))
 PEER_FORK_PUSH = _os.environ.get("MLAMG_PEER_FORK_PUSH", "1") == "1"
 # 1: the consuming row-op reads halo values in place from the receive region; 0: unpack kernel + plain row-op
 PEER_INPLACE = _os.environ.get("MLAMG_PEER_INPLACE", "1") == "1"
+# boundary rows (the HALO kernel, which spins on values that have not landed) on the forked high-priority stream right
+# behind the push, BESIDE the interior rows instead of after them: their few CTAs are scheduled ahead of the interior
+# kernel's queued CTAs and wait for the neighbours' stores while the interior rows keep the SMs busy
+PEER_BOUNDARY_SIDE = _os.environ.get("MLAMG_PEER_BOUNDARY_SIDE", "1") == "1"
 _ALIGN = 256
 
 
@@ -574,12 +579,18 @@ class DistOperator:
                     chan.push(x_ext)
             A = self._csr_for(op)
             xk = b if op == 8 else xin
+            rows = self.boundary if split else None
+            side = fork and PEER_BOUNDARY_SIDE and (PEER_INPLACE or op in (4, 6, 8))
+            if side:                   # boundary rows right behind the push on the side stream, beside the interior rows
+                with torch.cuda.stream(comm_stream):
+                    chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             if split:
                 core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
                            rows=None if self.interior_range is not None else self.interior)
             if fork:
                 main.wait_stream(comm_stream)
-            rows = self.boundary if split else None
+            if side:
+                return
             if PEER_INPLACE or op in (4, 6, 8):
                 chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             else:
@@ -757,23 +768,59 @@ class DistHierarchy:
             Lc.dw = Lc.dw[order].contiguous()
             Lc.perm_new2old = order
 
-    def _lambda_max(self, L, iters=30):
-        """power iteration on D^-1 A with the distributed SpMV (replaces ARPACK, multigrid.py:105)"""
-        n = L.n
-        dinv = core.smoother_diag(L.A.csr, "jacobi", 1.0)
-        g = torch.Generator(device="cpu").manual_seed(1234 + self.comm.rank)
-        x = torch.zeros(L.A.n_ext, dtype=self.dtype, device="cuda")
-        x[:n] = torch.rand(n, generator=g, dtype=torch.float64).to(device="cuda", dtype=self.dtype) + 0.5
-        y = torch.empty(n, dtype=self.dtype, device="cuda")
-        lam = 0.0
-        for _ in range(iters):
-            nrm = np.sqrt(self.comm.allreduce_sum(core.dot(x[:n], x[:n])))
-            x[:n] /= nrm
-            L.A.apply(0, x, y, overlap=False)
-            y *= dinv
-            lam = self.comm.allreduce_sum(core.dot(x[:n], y))
-            x[:n] = y
-        return abs(lam)
+    def _lambda_max(self, L, tol=1e-13, maxiter=6000, info=None):
+        """|lambda_max(D^-1 A)| of a row-partitioned level: Lanczos on D^-1/2 A D^-1/2 with the distributed SpMV — the
+        same recurrence, start vector (a hash of the GLOBAL row index, so the sequence does not depend on the
+        partition), check schedule and stopping rule as csrc/eigen.cu (replaces ARPACK, multigrid.py:105).  Two
+        8-byte allreduces per step.  The levels of this path are Galerkin products of a symmetric operator."""
+        from scipy.linalg import eigh_tridiagonal
+        comm, n = self.comm, L.n
+        dev = L.A.csr.val.device
+        s = torch.sqrt(core.smoother_diag(L.A.csr, "jacobi", 1.0))                     # 1/sqrt(a_ii)
+        lo = int(L.A.plan.offsets[comm.rank]) if hasattr(L.A.plan, "offsets") else 0
+        i = (torch.arange(n, device=dev, dtype=torch.int64) + lo) & 0xFFFFFFFF
+        h = (i * 2654435761) & 0xFFFFFFFF
+        h = h ^ (h >> 15)
+        h = (h * 2246822519) & 0xFFFFFFFF
+        h = h ^ (h >> 13)
+        v = (0.5 + (h & 0xFFFF).to(torch.float64) / 65536.0) * torch.where((h & 0x10000) != 0, -1.0, 1.0)
+        v = v.to(self.dtype)
+        v /= np.sqrt(comm.allreduce_sum(core.dot(v, v)))
+        vprev = torch.zeros_like(v)
+        xe = torch.zeros(L.A.n_ext, dtype=self.dtype, device=dev)
+        w = torch.empty(n, dtype=self.dtype, device=dev)
+        al, be, nxt = [], [], 20
+        theta, res_rel, steps = 0.0, 1.0, 0
+        for j in range(maxiter):
+            torch.mul(v, s, out=xe[:n])
+            L.A.apply(0, xe, w, overlap=False)
+            w *= s
+            a = comm.allreduce_sum(core.dot(v, w))
+            al.append(a)
+            core.axpby(-a, v, 1.0, w)
+            if be:
+                core.axpby(-be[-1], vprev, 1.0, w)
+            bnorm = np.sqrt(comm.allreduce_sum(core.dot(w, w)))
+            be.append(bnorm)
+            steps = j + 1
+            if steps == nxt or steps == maxiter:
+                if steps > 1:
+                    ev, evec = eigh_tridiagonal(np.array(al), np.array(be[:-1]))
+                else:
+                    ev, evec = np.array(al), np.ones((1, 1))
+                k = int(np.argmax(np.abs(ev)))
+                theta = float(abs(ev[k]))
+                gap = float(np.min(np.abs(np.delete(np.abs(ev), k) - theta))) if steps > 1 else 0.0
+                res = bnorm * abs(float(evec[-1, k]))
+                res_rel = res / theta if theta > 0 else 0.0
+                if min(res, res * res / gap if gap > 0 else res) <= tol * theta or bnorm <= 1e-300:
+                    break
+                nxt = steps + max(10, steps // 4)
+            vprev, v = v, vprev
+            torch.mul(w, 1.0 / bnorm, out=v)
+        if info is not None:
+            info.update(residual=res_rel, steps=steps, method="lanczos")
+        return theta
 
     # ---------------------------------------------------------------------------------------------
     def _alloc(self):
@@ -835,7 +882,9 @@ class DistHierarchy:
         return cs
 
     def check_exchange(self):
-        """host sync + raise if any peer exchange timed out"""
+        """host sync + raise if any peer exchange timed out.  `pcg` calls it before returning; `vcycle` and the replay
+        callable of `capture` only ENQUEUE work, so a caller that consumes their result directly must call this after
+        its own synchronisation (bench.py and tests/dist_check.py do)."""
         for cs in self._chansets.values():
             cs.check()
 
@@ -916,9 +965,11 @@ class DistHierarchy:
             x_out.copy_(xc)
         return x_out
 
-    def capture(self, b, x_out, nu1=1, nu2=1):
+    def capture(self, b, x_out, nu1=1, nu2=1, checked=False):
         """Capture one cycle (kernels + NCCL exchanges + side-stream fork/joins) into a CUDA graph and return a
-        replay callable.  b / x_out are baked in (update them in place).  All ranks must call this together."""
+        replay callable.  b / x_out are baked in (update them in place).  All ranks must call this together.
+        checked=True: the callable synchronises and raises if a halo wait timed out (for callers that read x_out right
+        away); the default only enqueues — follow it with check_exchange()."""
         self.vcycle(b, x_out, nu1, nu2)          # warm-up: every lazy buffer exists before capture
         self.vcycle(b, x_out, nu1, nu2)
         torch.cuda.synchronize()
@@ -928,6 +979,11 @@ class DistHierarchy:
             self.vcycle(b, x_out, nu1, nu2)
         torch.cuda.synchronize()
         self._graph = g
+        if checked:
+            def replay_checked():
+                g.replay()
+                self.check_exchange()
+            return replay_checked
         return g.replay
 
     def _tail_local_b(self):
@@ -993,6 +1049,7 @@ class DistHierarchy:
             rz_new = self.gdot(r, z)
             core.axpby(1.0, z, rz_new / rz, p)
             rz = rz_new
+        self.check_exchange()          # a halo wait that timed out returned stale values: never hand such a result out
         return x, np.array(res), it
 
     def cycle_bytes(self, nu1=1, nu2=1):
@@ -1019,15 +1076,36 @@ def n_tail_all(h):
     return int(h.tail_offsets[-1])
 
 
-def poisson_slab(n, world, rank, dtype=torch.float64):
-    """rows of rank's z-slab of the global n x n x (n*world) Dirichlet 7-point grid, GLOBAL column ids"""
-    nzg = n * world
-    z0 = n * rank
-    N = n * n * n
+def slab_geometry(n, world, geometry="cube"):
+    """(nx, ny, nz_local) of one rank's z-slab, n^3 DOF per rank either way.
+    'slab': n x n x n per rank, global n x n x (n*world).
+    'cube' (BASELINE.json config 5): (2n) x (2n) x (n/4) per rank for world > 1 — at n = 256 slabs of 512^2 x 64, the
+    global grid 512 x 512 x (64*world) is the 512^3 cube at 8 GPUs (134 217 728 DOF)."""
+    if geometry == "slab" or world == 1:
+        return n, n, n
+    if geometry != "cube":
+        raise ValueError(f"unknown geometry {geometry!r}")
+    if n % 4:
+        raise ValueError("cube geometry needs n divisible by 4")
+    return 2 * n, 2 * n, n // 4
+
+
+def poisson_slab(n, world, rank, dtype=torch.float64, geometry="slab"):
+    """rows of rank's z-slab of the global Dirichlet 7-point grid (see slab_geometry), GLOBAL column ids"""
+    nx, ny, nzl = slab_geometry(n, world, geometry)
+    nzg = nzl * world
+    z0 = nzl * rank
+    N = nx * ny * nzl
     rowptr = torch.empty(N + 1, dtype=torch.int32, device="cuda")
     col = torch.empty(7 * N, dtype=torch.int32, device="cuda")
     val = torch.empty(7 * N, dtype=dtype, device="cuda")
     nnz = ctypes.c_longlong(0)
-    check(lib.mlamg_poisson_csr_slab(core.dt(val), n, n, nzg, z0, n, core.ptr(rowptr), core.ptr(col), core.ptr(val),
+    check(lib.mlamg_poisson_csr_slab(core.dt(val), nx, ny, nzg, z0, nzl, core.ptr(rowptr), core.ptr(col), core.ptr(val),
                                      ctypes.byref(nnz), core.stream()))
     return rowptr, col[:nnz.value].clone(), val[:nnz.value].clone()
+
+
+def slab_lambda_max(n, world, geometry="slab"):
+    """analytic rho(D^-1 A) of the global Dirichlet 7-point box"""
+    nx, ny, nzl = slab_geometry(n, world, geometry)
+    return 1.0 + (np.cos(np.pi / (nx + 1)) + np.cos(np.pi / (ny + 1)) + np.cos(np.pi / (nzl * world + 1))) / 3.0

@@ -1,6 +1,6 @@
 """Multi-rank parity check of the row-partitioned hierarchy against the partitioned CPU oracle.
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [n]
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py [n] [--cube] [--delaunay]
 
 Each rank owns a z-slab of the global n x n x (n_z*world) Poisson grid.  Checks (per rank, its rows):
 aggregates bit-exact, P and the Galerkin operator of every distributed level bit-identical to the global
@@ -17,21 +17,17 @@ import torch
 import torch.distributed as dist
 
 
-def main():
-    delaunay = len(sys.argv) > 1 and sys.argv[1] == "--delaunay"
-    n = int(sys.argv[2 if delaunay else 1]) if len(sys.argv) > (2 if delaunay else 1) else (4000 if delaunay else 12)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def run_check(n, comm, geometry="slab", delaunay=False, verbose=True, extras=True):
+    """Build the row-partitioned hierarchy on this communicator and hold it to the partitioned CPU oracle.
+    -> dict(ok, labels_equal, P_bitwise, A_bitwise, vcycle_rel_err, pcg_iters_equal, pcg_hist_err, ...) for THIS rank.
+    extras: also the transport/graph self-consistency checks (skipped by bench.py's pre-timing parity leg)."""
     import mlamg
     from mlamg import distributed as md
     from oracle import multilevel as oml
+    rank, world = comm.rank, comm.world
+    saved = (md.OVERLAP_MIN_NNZ, md.PEER_SPLIT_MIN_NNZ)
     md.OVERLAP_MIN_NNZ = 0          # exercise the interior/boundary overlap path even on tiny levels
     md.PEER_SPLIT_MIN_NNZ = 0
-    comm = md.Comm()
     if delaunay:
         # BASELINE config 4 shape: P1 Laplacian on a Delaunay mesh of n random points (Morton-ordered rows, ~7 entries
         # per row), contiguous row blocks.  Every rank generates the same global matrix and keeps its rows.
@@ -47,22 +43,26 @@ def main():
         kw = dict(ratio=0.08, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
                   replicate_below=max(60, N // 20))
     else:
-        rowptr, col, val = md.poisson_slab(n, world, rank)
-        N_loc = n ** 3
+        rowptr, col, val = md.poisson_slab(n, world, rank, geometry=geometry)
+        nx, ny, nzl = md.slab_geometry(n, world, geometry)
+        N_loc = nx * ny * nzl
         offsets = [r * N_loc for r in range(world + 1)]
         lam = [2.0, 1.9, 1.8, 1.7, 1.6]
         kw = dict(ratio=0.06, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
                   replicate_below=max(60, N_loc * world // 40))
-        A = oml.poisson((n, n, n * world))
+        A = oml.poisson((nx, ny, nzl * world))
     H = md.DistHierarchy(rowptr, col, val, comm, **kw)
     ref, offs = oml.build_hierarchy_partitioned(A, offsets, **kw)
-    ok = True
+    out = {"ok": True, "labels_equal": True, "P_bitwise": True, "A_bitwise": True, "failed": []}
 
-    def check(name, cond):
-        nonlocal ok
+    def check(name, cond, key=None):
         if not cond:
-            ok = False
-            print(f"[rank {rank}] FAIL {name}", flush=True)
+            out["ok"] = False
+            out["failed"].append(name)
+            if key:
+                out[key] = False
+            if verbose:
+                print(f"[rank {rank}] FAIL {name}", flush=True)
 
     check("number of distributed levels", len(H.levels) == len(offs) - 1 and len(H.levels) >= 1)
     check("total levels", len(H.levels) + len(H.tail.levels) == len(ref))
@@ -71,11 +71,11 @@ def main():
         check(f"L{l} offsets", list(H.offsets[l]) == list(offs[l]))
         clo = int(H.offsets[l + 1][rank])
         lab = L.labels.cpu().numpy().astype(np.int64)
-        check(f"L{l} labels", np.array_equal(np.where(lab >= 0, lab + clo, -1), ref[l].labels[lo:hi]))
+        check(f"L{l} labels", np.array_equal(np.where(lab >= 0, lab + clo, -1), ref[l].labels[lo:hi]), "labels_equal")
         Pg = L.P_global.to_scipy()
         Pr = sp.csr_matrix(ref[l].P[lo:hi])
-        check(f"L{l} P pattern", np.array_equal(Pg.indptr, Pr.indptr) and np.array_equal(Pg.indices, Pr.indices))
-        check(f"L{l} P bits", Pg.nnz == Pr.nnz and np.array_equal(Pg.data, Pr.data))
+        check(f"L{l} P pattern", np.array_equal(Pg.indptr, Pr.indptr) and np.array_equal(Pg.indices, Pr.indices), "P_bitwise")
+        check(f"L{l} P bits", Pg.nnz == Pr.nnz and np.array_equal(Pg.data, Pr.data), "P_bitwise")
     # Galerkin operators: level l+1 rows of this rank (distributed) / whole matrix (tail)
     for l in range(1, len(H.levels)):
         L = H.levels[l]
@@ -89,25 +89,27 @@ def main():
         Ar = sp.csr_matrix(sp.csr_matrix(ref[l].A[lo:hi])[order])
         Ar.sort_indices()
         check(f"L{l} A bits", np.array_equal(Ag.indptr, Ar.indptr) and np.array_equal(Ag.indices, Ar.indices)
-              and np.array_equal(Ag.data, Ar.data))
+              and np.array_equal(Ag.data, Ar.data), "A_bitwise")
     nd = len(H.levels)
     for k, Lt in enumerate(H.tail.levels):
         At, Ar = Lt.A.to_scipy(), ref[nd + k].A
         check(f"tail{k} A bits", At.shape == Ar.shape and np.array_equal(At.indptr, Ar.indptr)
-              and np.array_equal(At.indices, Ar.indices) and np.array_equal(At.data, Ar.data))
+              and np.array_equal(At.indices, Ar.indices) and np.array_equal(At.data, Ar.data), "A_bitwise")
     # cycles
     lo, hi = offsets[rank], offsets[rank + 1]
     bg = np.random.RandomState(0).randn(A.shape[0])
     b = torch.from_numpy(bg[lo:hi]).cuda()
     x = torch.empty_like(b)
+    out["vcycle_rel_err"] = 0.0
     for nu1, nu2 in ((1, 1), (2, 2)):
         H.vcycle(b, x, nu1, nu2)
         xr = oml.vcycle(ref, bg.copy(), None, nu1, nu2)
-        err = np.abs(x.cpu().numpy() - xr[lo:hi]).max() / np.abs(xr).max()
+        err = float(np.abs(x.cpu().numpy() - xr[lo:hi]).max() / np.abs(xr).max())
+        out["vcycle_rel_err"] = max(out["vcycle_rel_err"], err)
         check(f"vcycle({nu1},{nu2}) rel err {err:.2e}", err < 1e-12)
-    if world > 1 and H.halo != "peer":
+    if world > 1 and H.halo != "peer" and verbose:
         print(f"[rank {rank}] peer transport unavailable: cycles above ran on the NCCL transport", flush=True)
-    if world > 1 and H.halo == "peer":
+    if extras and world > 1 and H.halo == "peer":
         # the same cycle on the other halo transport (NCCL all-to-all vs peer windows) and without the
         # interior/boundary split agrees to rounding (the threads-per-row heuristic depends on the launch size);
         # repeated eager cycles and CUDA-graph replays of the peer cycle agree bit for bit
@@ -134,20 +136,45 @@ def main():
         torch.cuda.synchronize()
         check("CUDA-graph replay of the peer cycle agrees bitwise", torch.equal(x, x_peer))
         H.check_exchange()
-    for overlap in (True, False):
+    out["pcg_iters_equal"], out["pcg_hist_err"] = True, 0.0
+    xr, res_r, it_r = oml.pcg(ref, bg, tol=1e-8, maxiter=100)
+    for overlap in ((True, False) if extras else (True,)):
         H.overlap = overlap
         xs, res, it = H.pcg(b, tol=1e-8, maxiter=100)
-        xr, res_r, it_r = oml.pcg(ref, bg, tol=1e-8, maxiter=100)
-        e = np.max(np.abs(res - res_r[:len(res)])) / res_r[0]
-        check(f"pcg overlap={overlap} iterations {it} vs {it_r}, history err {e:.2e}", it == it_r and e < 1e-11)
+        e = float(np.max(np.abs(res - res_r[:len(res)])) / res_r[0])
+        out["pcg_hist_err"] = max(out["pcg_hist_err"], e)
+        check(f"pcg overlap={overlap} iterations {it} vs {it_r}, history err {e:.2e}", it == it_r and e < 1e-11, "pcg_iters_equal")
         check("pcg solution", np.abs(xs.cpu().numpy() - xr[lo:hi]).max() <= 1e-9 * np.abs(xr).max())
-    print(f"[rank {rank}] {'PASS' if ok else 'FAIL'}: {len(H.levels)} distributed + {len(H.tail.levels)} replicated levels, "
-          f"halo {H.levels[0].A.plan.n_halo} entries", flush=True)
+    H.overlap = True
+    out.update(dist_levels=len(H.levels), tail_levels=len(H.tail.levels), halo_entries=int(H.levels[0].A.plan.n_halo),
+               dof_per_gpu=int(hi - lo), halo_transport=H.halo, pcg_iterations=int(it_r))
+    H._graph = None
     if world > 1:
         H.close()
+    md.OVERLAP_MIN_NNZ, md.PEER_SPLIT_MIN_NNZ = saved
+    return out
+
+
+def main():
+    args = [a for a in sys.argv[1:]]
+    delaunay = "--delaunay" in args
+    geometry = "cube" if "--cube" in args else "slab"
+    nums = [a for a in args if not a.startswith("--")]
+    n = int(nums[0]) if nums else (4000 if delaunay else 12)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mlamg import distributed as md
+    out = run_check(n, md.Comm(), geometry=geometry, delaunay=delaunay)
+    print(f"[rank {rank}] {'PASS' if out['ok'] else 'FAIL'}: {out['dist_levels']} distributed + {out['tail_levels']} replicated "
+          f"levels, halo {out['halo_entries']} entries, {geometry if not delaunay else 'delaunay'}", flush=True)
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if out["ok"] else 1)
 
 
 if __name__ == "__main__":

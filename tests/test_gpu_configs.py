@@ -7,7 +7,7 @@
             histories), the 4M-DOF size through size-independent properties (shortest-path fixed point,
             pattern/row-sum identities of P = P_hat Agg, symmetry and checksum of P^T A P, linearity and
             symmetry of the V-cycle operator);
-  config 4  unstructured P1 Laplacian on a Delaunay mesh, row-partitioned: tools/dist_check.py --delaunay
+  config 4  unstructured P1 Laplacian on a Delaunay mesh, row-partitioned: tests/dist_check.py --delaunay
             against the partitioned oracle (world 1 in-process, world 2 when two GPUs are visible).
 """
 import os
@@ -191,7 +191,7 @@ def _run_dist(nproc, args):
     if nproc > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                 "--master-port", "29519"]
-    cmd += [os.path.join(ROOT, "tools", "dist_check.py")] + [str(a) for a in args]
+    cmd += [os.path.join(ROOT, "tests", "dist_check.py")] + [str(a) for a in args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=900)
 
 
