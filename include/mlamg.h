@@ -209,6 +209,11 @@ int mlamg_poisson_csr(int dtype, int nx, int ny, int nz, int *rowptr, int *col, 
 int mlamg_poisson_csr_slab(int dtype, int nx, int ny, int nz, int z0, int nz_local, int *rowptr, int *col,
                            void *val, long long *nnz_host, mlamg_stream_t stream);
 
+/* HOST routine (no device work): the first k entries of numpy's legacy `RandomState(seed).permutation(n)` — the Lloyd
+ * seeds of ns/lib/graph.py:229-231 — bit-identical to numpy (MT19937 + reversed Fisher-Yates with masked rejection
+ * sampling).  out_host: k ints of host memory. */
+int mlamg_legacy_permutation_head(unsigned seed, long long n, long long k, int *out_host);
+
 /* ------------------------------------------------------------------ aggregation */
 
 /* pyamg.graph.bellman_ford (agg_interp.py:475): nearest = seed NODE ID, -1 unreachable; bit-exact

@@ -15,6 +15,7 @@
 // j* >= i or j* did not change in sweep s, else Z_s(j*) — a chain through strictly smaller indices
 // that is resolved by pointer jumping.  Nothing here depends on thread scheduling, so results are
 // identical run to run and identical to the sequential loops.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mlamg {
@@ -67,6 +68,86 @@ bf_relax_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ c
         xcur[i] = m;
         *changed = 1;
     }
+}
+
+// Frontier form of the same pass (pattern-symmetric graphs): a row is evaluated only when one of its inputs changed since
+// its last evaluation.  Three byte-flag arrays: `fin` rows to evaluate in this pass (each evaluated row clears its own
+// entry — nobody else touches fin during the pass), `fout` rows for the next pass of this sweep, `fnext` rows for the
+// first pass of the NEXT sweep.  A row j that lowers its value marks its readers (= its own neighbours, the pattern being
+// symmetric): ORDERED — readers i > j read xcur[j] in this very sweep -> fout; readers i < j read xprev[j], i.e. see the
+// change one sequential sweep later -> fnext.  !ORDERED — every reader reads xcur -> fout.  The relaxation is monotone
+// and every reader of a changed value is re-evaluated afterwards, so the fixed point (hence every distance, label and
+// sweep count) is the one of the full passes; only the work differs: after the first passes of a sweep a few percent
+// of the rows are active.
+template <typename T, bool ORDERED>
+__global__ void __launch_bounds__(AGG_THREADS)
+bf_relax_frontier_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ w,
+                         const T *__restrict__ xprev, T *xcur, unsigned char *fin, unsigned char *fout,
+                         unsigned char *fnext, int *__restrict__ changed) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    const bool act = i < n && fin[i] != 0;
+    if (!__any_sync(0xffffffffu, act)) return;
+    T own = Limits<T>::max();
+    T m = Limits<T>::max();
+    int start = 0, end = 0;
+    if (act) {
+        start = rowptr[i];
+        end = rowptr[i + 1];
+        own = __ldcg(&xcur[i]);
+        m = own;
+        for (int jj = start + lane; jj < end; jj += AGG_LANES) {
+            const int j = col[jj];
+            const T xj = (!ORDERED || j < i) ? __ldcg(&xcur[j]) : xprev[j];
+            const T d = w[jj] + xj;
+            if (d < m) m = d;
+        }
+    }
+    m = group_min8(m);
+    if (act && lane == 0) fin[i] = 0;
+    if (act && m < own) {
+        if (lane == 0) {
+            xcur[i] = m;
+            *changed = 1;
+        }
+        for (int jj = start + lane; jj < end; jj += AGG_LANES) {
+            const int j = col[jj];
+            if (j == i) continue;
+            if (!ORDERED || j > i) fout[j] = 1;
+            else fnext[j] = 1;
+        }
+    }
+}
+
+// *asym = 1 unless every stored entry (i, j) has a stored partner (j, i)
+__global__ void __launch_bounds__(AGG_THREADS)
+pattern_symmetric_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, int *__restrict__ asym) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    if (i >= n) return;
+    for (int jj = rowptr[i] + lane; jj < rowptr[i + 1]; jj += AGG_LANES) {
+        const int j = col[jj];
+        if (j == i) continue;
+        bool found = false;
+        if (j >= 0 && j < n)
+            for (int kk = rowptr[j]; kk < rowptr[j + 1]; kk++)
+                if (col[kk] == (int)i) { found = true; break; }
+        if (!found) { *asym = 1; return; }
+    }
+}
+
+// rows next to a seed are the only ones the first pass can change
+__global__ void __launch_bounds__(AGG_THREADS)
+seed_mark_kernel(int k, const int *__restrict__ seeds, const int *__restrict__ rowptr, const int *__restrict__ col,
+                 unsigned char *__restrict__ flags) {
+    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long sidx = gt / AGG_LANES;
+    const int lane = threadIdx.x & (AGG_LANES - 1);
+    if (sidx >= k) return;
+    const int node = seeds[sidx];
+    for (int jj = rowptr[node] + lane; jj < rowptr[node + 1]; jj += AGG_LANES) flags[col[jj]] = 1;
 }
 
 // Labels of sweep s (see file header).  link[i] = j* when Z_s(i) must be taken from Z_s(j*) which is
@@ -181,11 +262,13 @@ template <typename T>
 struct BfWork {
     T *xa, *xb;
     int *za, *zb, *la, *lb;
+    unsigned char *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;   // frontier flags (all zero between runs); null = full passes
 };
 
 // Emulates the sequential sweeps to their fixed point.  On entry x/z hold the initial state; on exit
 // they hold the final distances / labels.  Returns the number of sequential sweeps (incl. the final
 // no-change sweep) in *sweeps.
+// `first_flags`: frontier runs only — the rows to evaluate in the first pass of the first sweep (consumed, left zero).
 template <typename T>
 static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, const T *w, T *x, int *z,
                                   BfWork<T> wk, Flags &fl, int *sweeps, cudaStream_t s) {
@@ -193,18 +276,29 @@ static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, cons
     const unsigned eb = cdiv(n, AGG_THREADS);
     T *xprev = wk.xa, *xcur = wk.xb;
     int *zprev = wk.za, *zcur = wk.zb;
+    const bool frontier = wk.f0 != nullptr;
+    // frontier: fnext carries the initial rows (set by the caller in wk.f2); fin / fout are zero
+    unsigned char *fin = wk.f0, *fout = wk.f1, *fnext = wk.f2;
     MLAMG_CUDA(cudaMemcpyAsync(xprev, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
     MLAMG_CUDA(cudaMemcpyAsync(zprev, z, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
     int nsweeps = 0;
     for (;;) {
         nsweeps++;
         MLAMG_CUDA(cudaMemcpyAsync(xcur, xprev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        if (frontier) {      // rows whose higher neighbours changed during the previous sweep; fin and fout are all zero here
+            unsigned char *t = fin; fin = fnext; fnext = t;
+        }
         bool any = false;
         for (;;) {   // fixed point of sweep `nsweeps`
             MLAMG_TRY(fl.clear(s));
-            bf_relax_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fl.dev);
+            if (frontier)
+                bf_relax_frontier_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fin, fout, fnext,
+                                                                             fl.dev);
+            else
+                bf_relax_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fl.dev);
             MLAMG_LAUNCHED();
             MLAMG_TRY(fl.fetch(s));
+            if (frontier) { unsigned char *t = fin; fin = fout; fout = t; }
             if (!fl.host[0]) break;
             any = true;
         }
@@ -232,17 +326,24 @@ static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, cons
     return MLAMG_OK;
 }
 
-// order-free fixed point (distances only), in place on x
+// order-free fixed point (distances only), in place on x.  Frontier runs: wk.f0 holds the rows of the first pass.
 template <typename T>
-static int bf_free_fixed_point(int n, const int *rowptr, const int *col, const T *w, T *x, Flags &fl, cudaStream_t s) {
+static int bf_free_fixed_point(int n, const int *rowptr, const int *col, const T *w, T *x, BfWork<T> wk, Flags &fl,
+                               cudaStream_t s) {
     const unsigned gb = cdiv((long long)n * AGG_LANES, AGG_THREADS);
+    unsigned char *fin = wk.f0, *fout = wk.f1;
     for (;;) {
         MLAMG_TRY(fl.clear(s));
-        bf_relax_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fl.dev);
+        if (fin)
+            bf_relax_frontier_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fin, fout, fout, fl.dev);
+        else
+            bf_relax_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fl.dev);
         MLAMG_LAUNCHED();
         MLAMG_TRY(fl.fetch(s));
+        if (fin) { unsigned char *t = fin; fin = fout; fout = t; }
         if (!fl.host[0]) break;
     }
+    // the last pass changed nothing, so it marked nothing: fin / fout are zero again
     return MLAMG_OK;
 }
 
@@ -251,17 +352,35 @@ static int alloc_work(int n, cudaStream_t s, Scratch &buf, BfWork<T> *wk) {
     MLAMG_SCRATCH_OK(buf);
     unsigned char *p = buf.as<unsigned char>();
     const size_t nx = ((size_t)n * sizeof(T) + 255) & ~(size_t)255, ni = ((size_t)n * sizeof(int) + 255) & ~(size_t)255;
+    const size_t nf = ((size_t)n + 255) & ~(size_t)255;
     wk->xa = (T *)p; p += nx;
     wk->xb = (T *)p; p += nx;
     wk->za = (int *)p; p += ni;
     wk->zb = (int *)p; p += ni;
     wk->la = (int *)p; p += ni;
-    wk->lb = (int *)p;
+    wk->lb = (int *)p; p += ni;
+    wk->f0 = p; p += nf;
+    wk->f1 = p; p += nf;
+    wk->f2 = p;
+    MLAMG_CUDA(cudaMemsetAsync(wk->f0, 0, 3 * nf, s));
     return MLAMG_OK;
 }
 static size_t work_bytes(int n, size_t tsize) {
     const size_t nx = ((size_t)n * tsize + 255) & ~(size_t)255, ni = ((size_t)n * sizeof(int) + 255) & ~(size_t)255;
-    return 2 * nx + 4 * ni + 256;
+    const size_t nf = ((size_t)n + 255) & ~(size_t)255;
+    return 2 * nx + 4 * ni + 3 * nf + 256;
+}
+
+// frontier passes need a symmetric pattern (a row's neighbours are its readers); MLAMG_AGG_FRONTIER=0 forces full passes
+static int frontier_usable(int n, const int *rowptr, const int *col, Flags &fl, bool *ok, cudaStream_t s) {
+    const char *env = getenv("MLAMG_AGG_FRONTIER");
+    if (env && env[0] == '0') { *ok = false; return MLAMG_OK; }
+    MLAMG_TRY(fl.clear(s));
+    pattern_symmetric_kernel<<<cdiv((long long)n * AGG_LANES, AGG_THREADS), AGG_THREADS, 0, s>>>(n, rowptr, col, fl.dev + 3);
+    MLAMG_LAUNCHED();
+    MLAMG_TRY(fl.fetch(s));
+    *ok = fl.host[3] == 0;
+    return MLAMG_OK;
 }
 
 template <typename T>
@@ -280,6 +399,13 @@ static int bellman_ford_t(int n, const int *rowptr, const int *col, const T *w, 
     MLAMG_LAUNCHED();
     if (nseeds > 0) {
         seed_init_kernel<T, false><<<cdiv(nseeds, AGG_THREADS), AGG_THREADS, 0, s>>>(nseeds, seeds, dist, nearest);
+        MLAMG_LAUNCHED();
+    }
+    bool frontier = false;
+    MLAMG_TRY(frontier_usable(n, rowptr, col, fl, &frontier, s));
+    if (!frontier) wk.f0 = wk.f1 = wk.f2 = nullptr;
+    else if (nseeds > 0) {
+        seed_mark_kernel<<<cdiv((long long)nseeds * AGG_LANES, AGG_THREADS), AGG_THREADS, 0, s>>>(nseeds, seeds, rowptr, col, wk.f2);
         MLAMG_LAUNCHED();
     }
     int rc = bf_ordered_fixed_point<T>(n, rowptr, col, w, dist, nearest, wk, fl, sweeps_host, s);
@@ -305,11 +431,15 @@ lloyd_boundary_kernel(int n, const int *__restrict__ rowptr, const int *__restri
     if (i < n && lane == 0) is_boundary[i] = b;
 }
 
+// flags (optional): every row is evaluated in the first inward pass
 template <typename T>
 __global__ void __launch_bounds__(AGG_THREADS) lloyd_inward_init_kernel(int n, const int *__restrict__ is_boundary,
-                                                                        T *__restrict__ x) {
+                                                                        T *__restrict__ x, unsigned char *__restrict__ flags) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] = is_boundary[i] ? (T)0 : Limits<T>::max();
+    if (i < n) {
+        x[i] = is_boundary[i] ? (T)0 : Limits<T>::max();
+        if (flags) flags[i] = is_boundary[i] ? 0 : 1;      // a boundary node sits at distance 0: it can never improve
+    }
 }
 
 // per-cluster maximum of the inward distance (order-preserving key), then the first index attaining it
@@ -360,6 +490,9 @@ static int lloyd_cluster_t(int n, const int *rowptr, const int *col, const T *w,
     MLAMG_SCRATCH_OK(best);
     MLAMG_SCRATCH_OK(arg);
     const unsigned gb = cdiv((long long)n * AGG_LANES, AGG_THREADS), eb = cdiv(n, AGG_THREADS), kb = cdiv(k, AGG_THREADS);
+    bool frontier = false;
+    MLAMG_TRY(frontier_usable(n, rowptr, col, fl, &frontier, s));
+    if (!frontier) wk.f0 = wk.f1 = wk.f2 = nullptr;
     int it = 0;
     for (it = 0; it < maxiter;) {
         // reset + seeds
@@ -369,16 +502,20 @@ static int lloyd_cluster_t(int n, const int *rowptr, const int *col, const T *w,
         MLAMG_LAUNCHED();
         seed_init_kernel<T, true><<<kb, AGG_THREADS, 0, s>>>(k, seeds, dist, clusters);
         MLAMG_LAUNCHED();
+        if (frontier) {
+            seed_mark_kernel<<<cdiv((long long)k * AGG_LANES, AGG_THREADS), AGG_THREADS, 0, s>>>(k, seeds, rowptr, col, wk.f2);
+            MLAMG_LAUNCHED();
+        }
         // outward propagation with sequential tie-breaking
         MLAMG_TRY(bf_ordered_fixed_point<T>(n, rowptr, col, w, dist, clusters, wk, fl, nullptr, s));
         // cluster boundaries -> distance 0, interior -> max
         lloyd_boundary_kernel<<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, clusters, bnd.as<int>());
         MLAMG_LAUNCHED();
-        lloyd_inward_init_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, bnd.as<int>(), dist);
+        lloyd_inward_init_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, bnd.as<int>(), dist, wk.f0);
         MLAMG_LAUNCHED();
         // inward propagation: labels of interior nodes cannot change (all their neighbours carry the
         // same label), so only the order-independent distances are needed
-        MLAMG_TRY(bf_free_fixed_point<T>(n, rowptr, col, w, dist, fl, s));
+        MLAMG_TRY(bf_free_fixed_point<T>(n, rowptr, col, w, dist, wk, fl, s));
         // seed update
         MLAMG_CUDA(cudaMemsetAsync(best.p, 0, (size_t)k * sizeof(unsigned long long), s));
         fill_kernel<int><<<ew_blocks(k), AGG_THREADS, 0, s>>>(k, 0x7fffffff, arg.as<int>());

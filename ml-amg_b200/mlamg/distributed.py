@@ -35,6 +35,7 @@ from ._lib import lib, check
 # communicator helpers
 # =====================================================================================================
 import os as _os
+import time as _time
 
 # overlap the halo exchange only when the interior kernel is long compared with an exchange (~40 us)
 OVERLAP_MIN_NNZ = int(_os.environ.get("MLAMG_OVERLAP_MIN_NNZ", 20_000_000))
@@ -623,6 +624,27 @@ class DistLevel:
     pass
 
 
+class _StageTimer:
+    """per-stage wall-clock of the distributed setup (MLAMG_SETUP_PROFILE=1: device-synchronised; off: no-op)"""
+
+    def __init__(self):
+        self.on = _os.environ.get("MLAMG_SETUP_PROFILE", "0") == "1"
+        self.acc = {}
+        self._t = None
+
+    def start(self):
+        if self.on:
+            torch.cuda.synchronize()
+            self._t = _time.perf_counter()
+
+    def lap(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            now = _time.perf_counter()
+            self.acc[name] = self.acc.get(name, 0.0) + now - self._t
+            self._t = now
+
+
 class DistHierarchy:
     """Distributed levels followed by a replicated single-GPU hierarchy."""
 
@@ -646,6 +668,7 @@ class DistHierarchy:
         self.comm_stream = torch.cuda.Stream(priority=-1) if comm.world > 1 else None
         self.levels = []
         self.offsets = []
+        self.setup_profile = _StageTimer()
         lvl = 0
         cur = (rowptr, col_global, val)
         offs = partition_offsets(rowptr.numel() - 1, comm)
@@ -661,7 +684,10 @@ class DistHierarchy:
             lvl += 1
         self.offsets.append(offs)
         # replicated tail
+        T_ = self.setup_profile
+        T_.start()
         g_rowptr, g_col, g_val = gather_csr(*cur, comm)
+        T_.lap("tail_gather")
         n_glob = int(offs[-1])
         Ag = core.DeviceCSR(g_rowptr, g_col.to(torch.int32), g_val, (n_glob, n_glob))
         lam_tail = lam_max
@@ -672,13 +698,17 @@ class DistHierarchy:
         self.tail = hmod.build_hierarchy(Ag, aggregates="lloyd", ratio=ratio, distance=distance, maxiter=maxiter, rand=rand,
                                          lam_max=lam_tail, max_levels=max(1, max_levels - lvl), max_coarse=max_coarse,
                                          smoother=smoother, jacobi_weight=jacobi_weight)
+        T_.lap("tail_hierarchy")
         self.tail_offsets = offs
         if renumber:
             self._renumber()
+        T_.lap("renumber")
         if self.fuse_pre:
             for L in self.levels:
                 L.A.build_scaled(L.dw)
+        T_.lap("scaled_copy")
         self._alloc()
+        T_.lap("alloc")
 
     # ---------------------------------------------------------------------------------------------
     def _build_level(self, cur, offs, lvl, ratio, distance, maxiter, rand, lam_max, smoother, jacobi_weight):
@@ -689,16 +719,21 @@ class DistHierarchy:
         lo = int(offs[rank])
         L = DistLevel()
         L.n = n_own
+        T_ = self.setup_profile
+        T_.start()
         # 1. aggregates on the diagonal block
         b_rp, b_col, b_val = diag_block(rowptr, colg, val, n_own, lo)
         G = core.DeviceCSR(b_rp, b_col, b_val, (n_own, n_own))
+        T_.lap("diag_block")
         labels, nc_local, roots, seeds = hmod.lloyd_labels(G, ratio=ratio, distance=distance, maxiter=maxiter, rand=rand)
+        T_.lap("lloyd")
         coffs = partition_offsets(nc_local, comm)
         clo = int(coffs[rank])
         nc_glob = int(coffs[-1])
         L.labels = labels
         # 2. A in ext numbering, halo labels
         L.A = DistOperator(rowptr, colg, val, n_own, lo, offs, comm)
+        T_.lap("dist_operator_A")
         lab_ext = torch.full((L.A.n_ext,), -1, dtype=torch.int32, device=val.device)
         lab_ext[:n_own] = torch.where(labels >= 0, labels + clo, labels)
         L.A.plan.exchange(lab_ext, n_own)
@@ -712,32 +747,45 @@ class DistHierarchy:
             lam = lam_max[lvl] if lvl < len(lam_max) else None
             lam = self._lambda_max(L) if lam is None else float(lam)
         L.omega_sa = (4.0 / 3.0) / lam
+        T_.lap("labels_exchange+lambda")
         Pg = core.drop_zeros(core.spgemm(core.sa_smoother(L.A.csr, L.omega_sa), Agg_ext))
+        T_.lap("P_spgemm")
         # 4. Galerkin product in scipy's evaluation order: X^T = A^T P ; A_H^T = P^T X^T ; transpose
         t_rp, t_col, t_val = dist_transpose(rowptr, colg, val, offs, offs, comm)
+        T_.lap("transpose_A")
         At = DistOperator(t_rp, t_col, t_val, n_own, lo, offs, comm)
+        T_.lap("dist_operator_At")
         f_rp, f_col, f_val = fetch_rows(Pg.rowptr, Pg.col, Pg.val, offs, At.plan.halo_ids, comm)
         e_rp, e_col, e_val = csr_vstack([(Pg.rowptr, Pg.col, Pg.val), (f_rp, f_col, f_val)])
+        T_.lap("fetch_P_rows")
         Xt = core.spgemm(At.csr, core.DeviceCSR(e_rp, e_col, e_val, (At.n_ext, nc_glob)))
+        T_.lap("AtP_spgemm")
         r_rp, r_col, r_val = dist_transpose(Pg.rowptr, Pg.col, Pg.val, offs, coffs, comm)
+        T_.lap("transpose_P")
         L.R = DistOperator(r_rp, r_col, r_val, n_own, lo, offs, comm)
+        T_.lap("dist_operator_R")
         f_rp, f_col, f_val = fetch_rows(Xt.rowptr, Xt.col, Xt.val, offs, L.R.plan.halo_ids, comm)
         e_rp, e_col, e_val = csr_vstack([(Xt.rowptr, Xt.col, Xt.val), (f_rp, f_col, f_val)])
+        T_.lap("fetch_X_rows")
         AHt = core.spgemm(L.R.csr, core.DeviceCSR(e_rp, e_col, e_val, (L.R.n_ext, nc_glob)))
+        T_.lap("RX_spgemm")
         h_rp, h_col, h_val = dist_transpose(AHt.rowptr, AHt.col, AHt.val, coffs, coffs, comm)
         AH = core.drop_zeros(core.DeviceCSR(h_rp, h_col, h_val, (nc_local, nc_glob)))
+        T_.lap("transpose_AH")
         # 5. apply structures
         L.P = DistOperator(Pg.rowptr, Pg.col, Pg.val, nc_local, clo, coffs, comm)
         L.P_global = Pg
         L.dw = core.smoother_diag(L.A.csr, smoother, jacobi_weight)
         L.nc = nc_local
         L.Q = None
+        T_.lap("dist_operator_P")
         if self.fuse_post:
             # rows of P for every column of my rows of A (owned + halo fine nodes), then Q = (I - D_w A) P
             f_rp, f_col, f_val = fetch_rows(Pg.rowptr, Pg.col, Pg.val, offs, L.A.plan.halo_ids, comm)
             e_rp, e_col, e_val = csr_vstack([(Pg.rowptr, Pg.col, Pg.val), (f_rp, f_col, f_val)])
             Qg = hmod.post_operator(L.A.csr, core.DeviceCSR(e_rp, e_col, e_val, (L.A.n_ext, nc_glob)), L.dw)
             L.Q = DistOperator(Qg.rowptr, Qg.col, Qg.val, nc_local, clo, coffs, comm)
+        T_.lap("Q_operator")
         return L, (AH.rowptr, AH.col, AH.val), coffs
 
     def _renumber(self):

@@ -43,13 +43,19 @@ def lloyd_seeds(N, ratio, rand):
     """Seeding of ns/lib/graph.py:214-231 (host RNG: it defines the reference's seeds)."""
     if ratio <= 0 or ratio > 1:
         raise ValueError("ratio must be > 0.0 and <= 1.0")
+    num_seeds = int(np.ceil(ratio * N))
+    if isinstance(rand, (int, np.integer)) and not isinstance(rand, bool) and 0 <= int(rand) < 2 ** 32 and N < 2 ** 31:
+        # integer seed: the same draws as RandomState(rand).permutation(N), by the extension's host routine (numpy's own
+        # loop is the largest single item of the setup at 16.7 M rows)
+        out = np.empty(num_seeds, dtype=np.int32)
+        check(lib.mlamg_legacy_permutation_head(int(rand), int(N), num_seeds, out.ctypes.data_as(ctypes.c_void_p)))
+        return out.astype(np.int64)
     if rand is None:
         rand = np.random
     elif isinstance(rand, (int, np.integer)):
         rand = np.random.RandomState(int(rand))
     elif not isinstance(rand, np.random.RandomState):
         raise TypeError("rand should be an integer seed value or a random state")
-    num_seeds = int(np.ceil(ratio * N))
     return rand.permutation(N)[:num_seeds]
 
 

@@ -91,3 +91,15 @@ def test_lanczos_stopping_rule_reaches_machine_precision(ql):
         vp, v = v, w / be[-1]
     exact = 1 + (np.cos(np.pi / 49) + np.cos(np.pi / 41)) / 2
     assert abs(theta - exact) <= 1e-13 * exact and j < 1000
+
+
+def test_legacy_permutation_head_is_numpys():
+    """mlamg_legacy_permutation_head (host routine of the extension) == RandomState(seed).permutation(n)[:k], the Lloyd
+    seeding of ns/lib/graph.py:229-231, for many (seed, n) incl. the sizes of configs 1 and 2"""
+    from mlamg._lib import lib, check
+    for seed, n in [(0, 1), (0, 2), (3, 7), (0, 576), (1, 1000), (7, 65536), (0, 65536), (123456789, 100003),
+                    (2 ** 32 - 1, 5000), (0, 2097152)]:
+        k = max(1, int(np.ceil(0.1 * n)))
+        out = np.empty(k, dtype=np.int32)
+        check(lib.mlamg_legacy_permutation_head(seed, n, k, out.ctypes.data_as(ctypes.c_void_p)))
+        assert np.array_equal(out, np.random.RandomState(seed).permutation(n)[:k]), (seed, n)

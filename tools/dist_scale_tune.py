@@ -52,7 +52,8 @@ def main():
         x = torch.empty_like(b)
         res = {"n": n, "world": world, "geometry": geometry, "replicate_below": rb, "setup_s": round(setup_s, 2),
                "dist_levels": [int(o[-1]) for o in H.offsets[:-1]], "tail": [l.A.shape[0] for l in H.tail.levels],
-               "halo_fine": H.levels[0].A.plan.n_halo}
+               "halo_fine": H.levels[0].A.plan.n_halo,
+               "setup_stages_s": {k: round(v, 3) for k, v in H.setup_profile.acc.items()}}
         for side in (True, False):
             md.PEER_BOUNDARY_SIDE = side
             replay = H.capture(b, x, 1, 1)

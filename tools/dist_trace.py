@@ -1,6 +1,6 @@
 """Per-kernel timeline of ONE distributed V-cycle on rank 0 (development aid; kineto trace, nothing is replayed).
 
-    torchrun --nproc-per-node 2 tools/dist_trace.py [n]
+    torchrun --nproc-per-node 2 tools/dist_trace.py [n] [cube|slab] [replicate_below]
 
 Prints, in launch order, every kernel of one CUDA-graph replay of the cycle with its duration — the multi-GPU
 counterpart of the ncu launch list of the single-GPU cycle (ncu must not wrap multi-rank runs with spinning kernels)."""
@@ -22,12 +22,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from mlamg import distributed as md
     comm = md.Comm()
-    rowptr, col, val = md.poisson_slab(n, world, rank)
+    geometry = sys.argv[2] if len(sys.argv) > 2 else "cube"
+    rb = int(sys.argv[3]) if len(sys.argv) > 3 else 500000
+    rowptr, col, val = md.poisson_slab(n, world, rank, geometry=geometry)
     b = torch.from_numpy(np.random.RandomState(rank).randn(n ** 3)).cuda()
     x = torch.empty_like(b)
-    lam0 = 1.0 + (2.0 * np.cos(np.pi / (n + 1)) + np.cos(np.pi / (n * world + 1))) / 3.0
+    lam0 = md.slab_lambda_max(n, world, geometry)
     H = md.DistHierarchy(rowptr, col, val, comm, ratio=0.027, distance="unit", maxiter=10, rand=0, lam_max=[lam0],
-                         max_levels=8, max_coarse=1000, replicate_below=500000)
+                         max_levels=8, max_coarse=1000, replicate_below=rb)
     replay = H.capture(b, x, 1, 1)
     for _ in range(50):
         replay()
@@ -49,7 +51,7 @@ def main():
             rows.append({"t_us": round(e.time_range.start - t0, 1), "dur_us": round(e.time_range.end - e.time_range.start, 1),
                          "kernel": e.name[:110]})
         span = last[-1].time_range.end - t0
-        print(json.dumps({"n": n, "world": world, "kernels_in_cycle": len(last), "cycle_span_us": round(span, 1),
+        print(json.dumps({"n": n, "world": world, "geometry": geometry, "replicate_below": rb, "kernels_in_cycle": len(last), "cycle_span_us": round(span, 1),
                           "sum_kernel_us": round(sum(r["dur_us"] for r in rows), 1)}))
         for r in rows:
             print(f'{r["t_us"]:9.1f} {r["dur_us"]:8.1f}  {r["kernel"]}')
