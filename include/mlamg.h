@@ -221,6 +221,8 @@ int mlamg_legacy_permutation_head(unsigned seed, long long n, long long k, int *
  * receives the number of sequential sweeps emulated. */
 int mlamg_bellman_ford(int dtype, int n, const int *rowptr, const int *col, const void *w, int nseeds,
                        const int *seeds, void *dist, int *nearest, int *sweeps_host, mlamg_stream_t stream);
+/* profiling aid: counters of the aggregation calls of this process (passes, sweeps, rows evaluated; see aggregation.cu) */
+int mlamg_agg_stats(long long *out8, int reset);
 /* pyamg.graph.lloyd_cluster (graph.py:232): seeds[k] in/out, clusters = seed INDEX or -1.
  * *iters_host (may be NULL) receives the Lloyd iterations executed. */
 int mlamg_lloyd_cluster(int dtype, int n, const int *rowptr, const int *col, const void *w, int k,

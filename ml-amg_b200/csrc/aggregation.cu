@@ -16,6 +16,7 @@
 // that is resolved by pointer jumping.  Nothing here depends on thread scheduling, so results are
 // identical run to run and identical to the sequential loops.
 #include <stdlib.h>
+#include <time.h>
 #include "common.cuh"
 
 namespace mlamg {
@@ -71,51 +72,93 @@ bf_relax_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ c
 }
 
 // Frontier form of the same pass (pattern-symmetric graphs): a row is evaluated only when one of its inputs changed since
-// its last evaluation.  Three byte-flag arrays: `fin` rows to evaluate in this pass (each evaluated row clears its own
-// entry — nobody else touches fin during the pass), `fout` rows for the next pass of this sweep, `fnext` rows for the
-// first pass of the NEXT sweep.  A row j that lowers its value marks its readers (= its own neighbours, the pattern being
+// its last evaluation.  Three byte-flag arrays: `fin` rows to evaluate in this pass (compacted into a row list and cleared
+// by frontier_compact_kernel), `fout` rows for the next pass of this sweep, `fnext` rows for the first pass of the NEXT
+// sweep.  A row j that lowers its value marks its readers (= its own neighbours, the pattern being
 // symmetric): ORDERED — readers i > j read xcur[j] in this very sweep -> fout; readers i < j read xprev[j], i.e. see the
 // change one sequential sweep later -> fnext.  !ORDERED — every reader reads xcur -> fout.  The relaxation is monotone
 // and every reader of a changed value is re-evaluated afterwards, so the fixed point (hence every distance, label and
 // sweep count) is the one of the full passes; only the work differs: after the first passes of a sweep a few percent
 // of the rows are active.
+// fin -> list of flagged rows (order arbitrary), fin cleared; *count = rows listed.  Each thread scans 16 flags with one
+// 128-bit load (the flag arrays are 256-byte aligned and padded): a pass over the byte flags costs n bytes of traffic
+// and n/16 threads, where a grid of 8 lanes per row would cost n*8 threads of launch work per pass even when a handful
+// of rows are active.
+__global__ void __launch_bounds__(AGG_THREADS)
+frontier_compact_kernel(int n, unsigned char *__restrict__ fin, int *__restrict__ list, int *__restrict__ count) {
+    const long long t = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const long long i0 = t * 16;
+    uint4 f = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 < n) f = *reinterpret_cast<const uint4 *>(fin + i0);         // bytes past n inside the padded array are zero
+    const unsigned wv[4] = {f.x, f.y, f.z, f.w};
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) mine += __popc(wv[k] & 0x01010101u);     // flags are 0 / 1
+    // warp-level exclusive scan of the per-thread counts, one global atomic per warp
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if ((wv[k] >> (8 * bb)) & 1u) list[base++] = (int)(i0 + 4 * k + bb);
+        *reinterpret_cast<uint4 *>(fin + i0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 template <typename T, bool ORDERED>
 __global__ void __launch_bounds__(AGG_THREADS)
-bf_relax_frontier_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ w,
-                         const T *__restrict__ xprev, T *xcur, unsigned char *fin, unsigned char *fout,
-                         unsigned char *fnext, int *__restrict__ changed) {
-    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
-    const long long i = gt / AGG_LANES;
+bf_relax_frontier_kernel(const int *__restrict__ list, const int *__restrict__ count, const int *__restrict__ rowptr,
+                         const int *__restrict__ col, const T *__restrict__ w, const T *__restrict__ xprev, T *xcur,
+                         unsigned char *fout, unsigned char *fnext, int *__restrict__ changed) {
     const int lane = threadIdx.x & (AGG_LANES - 1);
-    const bool act = i < n && fin[i] != 0;
-    if (!__any_sync(0xffffffffu, act)) return;
-    T own = Limits<T>::max();
-    T m = Limits<T>::max();
-    int start = 0, end = 0;
-    if (act) {
-        start = rowptr[i];
-        end = rowptr[i + 1];
-        own = __ldcg(&xcur[i]);
-        m = own;
-        for (int jj = start + lane; jj < end; jj += AGG_LANES) {
-            const int j = col[jj];
-            const T xj = (!ORDERED || j < i) ? __ldcg(&xcur[j]) : xprev[j];
-            const T d = w[jj] + xj;
-            if (d < m) m = d;
+    const int nact = *count;
+    const long long ngroups = (long long)gridDim.x * (AGG_THREADS / AGG_LANES);
+    // uniform trip count per warp: every lane takes part in the group shuffles
+    const long long g0 = ((long long)blockIdx.x * AGG_THREADS + threadIdx.x) / AGG_LANES;
+    const long long w0 = g0 - ((threadIdx.x & 31) / AGG_LANES);          // first group of this warp
+    for (long long base = w0; base < nact; base += ngroups) {
+        const long long g = base + ((threadIdx.x & 31) / AGG_LANES);
+        const bool act = g < nact;
+        T own = Limits<T>::max();
+        T m = Limits<T>::max();
+        int start = 0, end = 0, i = 0;
+        if (act) {
+            i = list[g];
+            start = rowptr[i];
+            end = rowptr[i + 1];
+            own = __ldcg(&xcur[i]);
+            m = own;
+            for (int jj = start + lane; jj < end; jj += AGG_LANES) {
+                const int j = col[jj];
+                const T xj = (!ORDERED || j < i) ? __ldcg(&xcur[j]) : xprev[j];
+                const T d = w[jj] + xj;
+                if (d < m) m = d;
+            }
         }
-    }
-    m = group_min8(m);
-    if (act && lane == 0) fin[i] = 0;
-    if (act && m < own) {
-        if (lane == 0) {
-            xcur[i] = m;
-            *changed = 1;
-        }
-        for (int jj = start + lane; jj < end; jj += AGG_LANES) {
-            const int j = col[jj];
-            if (j == i) continue;
-            if (!ORDERED || j > i) fout[j] = 1;
-            else fnext[j] = 1;
+        m = group_min8(m);
+        if (act && m < own) {
+            if (lane == 0) {
+                xcur[i] = m;
+                *changed = 1;
+            }
+            for (int jj = start + lane; jj < end; jj += AGG_LANES) {
+                const int j = col[jj];
+                if (j == i) continue;
+                if (!ORDERED || j > i) fout[j] = 1;
+                else fnext[j] = 1;
+            }
         }
     }
 }
@@ -152,20 +195,46 @@ seed_mark_kernel(int k, const int *__restrict__ seeds, const int *__restrict__ r
 
 // Labels of sweep s (see file header).  link[i] = j* when Z_s(i) must be taken from Z_s(j*) which is
 // itself produced in this sweep, -1 when zcur[i] is final.
+// stage 1 (one thread per row): rows whose distance did not drop in this sweep keep their label; the others are listed
 template <typename T>
 __global__ void __launch_bounds__(AGG_THREADS)
-bf_label_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ w,
-                const T *__restrict__ xprev, const T *__restrict__ xcur, const int *__restrict__ zprev,
-                int *__restrict__ zcur, int *__restrict__ link, int *__restrict__ pending, int *__restrict__ error) {
-    const long long gt = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
-    const long long i = gt / AGG_LANES;
+bf_label_scan_kernel(int n, const T *__restrict__ xprev, const T *__restrict__ xcur, const int *__restrict__ zprev,
+                     int *__restrict__ zcur, int *__restrict__ link, int *__restrict__ list, int *__restrict__ count) {
+    const long long i = (long long)blockIdx.x * AGG_THREADS + threadIdx.x;
+    const bool updated = i < n && xcur[i] < xprev[i];
+    if (i < n && !updated) {
+        zcur[i] = zprev[i];
+        link[i] = -1;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, updated);
+    if (ballot == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (updated) list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)i;
+}
+
+// stage 2 (8 lanes per listed row): the first CSR-order neighbour attaining the new distance decides the label
+template <typename T>
+__global__ void __launch_bounds__(AGG_THREADS)
+bf_label_kernel(const int *__restrict__ list, const int *__restrict__ count, const int *__restrict__ rowptr,
+                const int *__restrict__ col, const T *__restrict__ w, const T *__restrict__ xprev,
+                const T *__restrict__ xcur, const int *__restrict__ zprev, int *__restrict__ zcur, int *__restrict__ link,
+                int *__restrict__ pending, int *__restrict__ error) {
     const int lane = threadIdx.x & (AGG_LANES - 1);
-    int first = 0x7fffffff;
-    bool updated = false;
-    if (i < n) {
-        const T xi = xcur[i];
-        updated = xi < xprev[i];
-        if (updated) {
+    const int nact = *count;
+    const long long ngroups = (long long)gridDim.x * (AGG_THREADS / AGG_LANES);
+    const long long g0 = ((long long)blockIdx.x * AGG_THREADS + threadIdx.x) / AGG_LANES;
+    const long long w0 = g0 - ((threadIdx.x & 31) / AGG_LANES);
+    for (long long base = w0; base < nact; base += ngroups) {
+        const long long g = base + ((threadIdx.x & 31) / AGG_LANES);
+        const bool act = g < nact;
+        int first = 0x7fffffff;
+        int i = 0;
+        if (act) {
+            i = list[g];
+            const T xi = xcur[i];
             for (int jj = rowptr[i] + lane; jj < rowptr[i + 1]; jj += AGG_LANES) {
                 const int j = col[jj];
                 const T xj = (j < i) ? xcur[j] : xprev[j];
@@ -173,24 +242,21 @@ bf_label_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ c
                 if (d == xi) { first = jj; break; }
             }
         }
-    }
-    first = group_min8i(first);
-    if (i < n && lane == 0) {
-        if (!updated) {
-            zcur[i] = zprev[i];
-            link[i] = -1;
-        } else if (first == 0x7fffffff) {
-            *error = 1;
-            zcur[i] = zprev[i];
-            link[i] = -1;
-        } else {
-            const int j = col[first];
-            if (j < i && xcur[j] < xprev[j]) {
-                link[i] = j;
-                *pending = 1;
-            } else {
-                zcur[i] = zprev[j];
+        first = group_min8i(first);
+        if (act && lane == 0) {
+            if (first == 0x7fffffff) {
+                *error = 1;
+                zcur[i] = zprev[i];
                 link[i] = -1;
+            } else {
+                const int j = col[first];
+                if (j < i && xcur[j] < xprev[j]) {
+                    link[i] = j;
+                    *pending = 1;
+                } else {
+                    zcur[i] = zprev[j];
+                    link[i] = -1;
+                }
             }
         }
     }
@@ -237,25 +303,60 @@ static unsigned ew_blocks(int n) {
     return b > 148u * 16u ? 148u * 16u : b;
 }
 
-struct Flags {        // pinned host mirror of a few device flags
+// counters of the last aggregation calls (debug / profiling aid, read by mlamg_agg_stats)
+static long long g_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ordered passes, free passes, sweeps, chain passes, active rows (ordered), active rows (free), lloyd iterations, unused
+
+static inline long long now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec;
+}
+
+// grid of the frontier relaxation (grid-stride over the active-row list whose length lives on the device)
+static unsigned frontier_grid(int n) {
+    const unsigned need = cdiv((long long)n * AGG_LANES, AGG_THREADS);
+    return need < 148u * 32u ? need : 148u * 32u;
+}
+
+// Pinned host mirror of a few device flags.  The buffers are allocated once per (thread, device) and reused by every
+// aggregation call: cudaMallocHost / cudaFreeHost per call cost tens to hundreds of milliseconds on some hosts and made
+// the Lloyd time erratic (0.17 - 0.58 s for identical device work).
+struct FlagBuffers {
+    int device = -1;
+    int *dev = nullptr;
+    int *host = nullptr;
+};
+static thread_local FlagBuffers g_flagbuf;
+
+struct Flags {
     int *dev = nullptr;
     int *host = nullptr;
     int init() {
-        MLAMG_CUDA(cudaMalloc(&dev, 4 * sizeof(int)));
-        MLAMG_CUDA(cudaMallocHost(&host, 4 * sizeof(int)));
+        int d = 0;
+        MLAMG_CUDA(cudaGetDevice(&d));
+        if (g_flagbuf.device != d) {          // first use on this device (buffers of another device stay allocated)
+            g_flagbuf.dev = nullptr;
+            g_flagbuf.host = nullptr;
+            MLAMG_CUDA(cudaMalloc(&g_flagbuf.dev, 4 * sizeof(int)));
+            MLAMG_CUDA(cudaMallocHost(&g_flagbuf.host, 4 * sizeof(int)));
+            g_flagbuf.device = d;
+        }
+        dev = g_flagbuf.dev;
+        host = g_flagbuf.host;
         return MLAMG_OK;
-    }
-    ~Flags() {
-        if (dev) cudaFree(dev);
-        if (host) cudaFreeHost(host);
     }
     int clear(cudaStream_t s) { MLAMG_CUDA(cudaMemsetAsync(dev, 0, 4 * sizeof(int), s)); return MLAMG_OK; }
-    int fetch(cudaStream_t s) {
-        MLAMG_CUDA(cudaMemcpyAsync(host, dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        MLAMG_CUDA(cudaStreamSynchronize(s));
-        return MLAMG_OK;
-    }
+    int fetch(cudaStream_t s);
 };
+
+int Flags::fetch(cudaStream_t s) {
+    const long long t0 = now_ns();
+    MLAMG_CUDA(cudaMemcpyAsync(host, dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    g_stats[7] += now_ns() - t0;          // host time spent waiting for the device in the flag round trips
+    return MLAMG_OK;
+}
+
 
 // Work arrays of one Bellman-Ford run
 template <typename T>
@@ -263,6 +364,7 @@ struct BfWork {
     T *xa, *xb;
     int *za, *zb, *la, *lb;
     unsigned char *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;   // frontier flags (all zero between runs); null = full passes
+    int *list = nullptr;                                          // frontier: active rows of the current pass
 };
 
 // Emulates the sequential sweeps to their fixed point.  On entry x/z hold the initial state; on exit
@@ -284,6 +386,7 @@ static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, cons
     int nsweeps = 0;
     for (;;) {
         nsweeps++;
+        g_stats[2]++;
         MLAMG_CUDA(cudaMemcpyAsync(xcur, xprev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
         if (frontier) {      // rows whose higher neighbours changed during the previous sweep; fin and fout are all zero here
             unsigned char *t = fin; fin = fnext; fnext = t;
@@ -291,21 +394,27 @@ static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, cons
         bool any = false;
         for (;;) {   // fixed point of sweep `nsweeps`
             MLAMG_TRY(fl.clear(s));
-            if (frontier)
-                bf_relax_frontier_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fin, fout, fnext,
-                                                                             fl.dev);
-            else
+            if (frontier) {
+                frontier_compact_kernel<<<cdiv(cdiv(n, 16), AGG_THREADS), AGG_THREADS, 0, s>>>(n, fin, wk.list, fl.dev + 1);
+                MLAMG_LAUNCHED();
+                bf_relax_frontier_kernel<T, true><<<frontier_grid(n), AGG_THREADS, 0, s>>>(wk.list, fl.dev + 1, rowptr, col, w, xprev,
+                                                                                          xcur, fout, fnext, fl.dev);
+            } else
                 bf_relax_kernel<T, true><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, fl.dev);
             MLAMG_LAUNCHED();
             MLAMG_TRY(fl.fetch(s));
+            g_stats[0]++;
+            g_stats[4] += frontier ? fl.host[1] : n;
             if (frontier) { unsigned char *t = fin; fin = fout; fout = t; }
             if (!fl.host[0]) break;
             any = true;
         }
         if (!any) break;   // this sweep changed nothing: the sequential loop stops here
         MLAMG_TRY(fl.clear(s));
-        bf_label_kernel<T><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, xprev, xcur, zprev, zcur, wk.la, fl.dev + 1,
-                                                      fl.dev + 2);
+        bf_label_scan_kernel<T><<<eb, AGG_THREADS, 0, s>>>(n, xprev, xcur, zprev, zcur, wk.la, wk.list, fl.dev + 3);
+        MLAMG_LAUNCHED();
+        bf_label_kernel<T><<<frontier_grid(n), AGG_THREADS, 0, s>>>(wk.list, fl.dev + 3, rowptr, col, w, xprev, xcur, zprev, zcur,
+                                                                    wk.la, fl.dev + 1, fl.dev + 2);
         MLAMG_LAUNCHED();
         MLAMG_TRY(fl.fetch(s));
         if (fl.host[2]) return set_error(MLAMG_EINVAL, "bellman_ford: inconsistent relaxation (NaN or negative weight?)");
@@ -315,6 +424,7 @@ static int bf_ordered_fixed_point(int n, const int *rowptr, const int *col, cons
             bf_chain_kernel<<<eb, AGG_THREADS, 0, s>>>(n, lin, lout, zcur, fl.dev + 1);
             MLAMG_LAUNCHED();
             MLAMG_TRY(fl.fetch(s));
+            g_stats[3]++;
             int *t = lin; lin = lout; lout = t;
         }
         { T *t = xprev; xprev = xcur; xcur = t; }
@@ -334,12 +444,17 @@ static int bf_free_fixed_point(int n, const int *rowptr, const int *col, const T
     unsigned char *fin = wk.f0, *fout = wk.f1;
     for (;;) {
         MLAMG_TRY(fl.clear(s));
-        if (fin)
-            bf_relax_frontier_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fin, fout, fout, fl.dev);
-        else
+        if (fin) {
+            frontier_compact_kernel<<<cdiv(cdiv(n, 16), AGG_THREADS), AGG_THREADS, 0, s>>>(n, fin, wk.list, fl.dev + 1);
+            MLAMG_LAUNCHED();
+            bf_relax_frontier_kernel<T, false><<<frontier_grid(n), AGG_THREADS, 0, s>>>(wk.list, fl.dev + 1, rowptr, col, w, x, x, fout,
+                                                                                       fout, fl.dev);
+        } else
             bf_relax_kernel<T, false><<<gb, AGG_THREADS, 0, s>>>(n, rowptr, col, w, x, x, fl.dev);
         MLAMG_LAUNCHED();
         MLAMG_TRY(fl.fetch(s));
+        g_stats[1]++;
+        g_stats[5] += fin ? fl.host[1] : n;
         if (fin) { unsigned char *t = fin; fin = fout; fout = t; }
         if (!fl.host[0]) break;
     }
@@ -361,14 +476,15 @@ static int alloc_work(int n, cudaStream_t s, Scratch &buf, BfWork<T> *wk) {
     wk->lb = (int *)p; p += ni;
     wk->f0 = p; p += nf;
     wk->f1 = p; p += nf;
-    wk->f2 = p;
+    wk->f2 = p; p += nf;
+    wk->list = (int *)p;
     MLAMG_CUDA(cudaMemsetAsync(wk->f0, 0, 3 * nf, s));
     return MLAMG_OK;
 }
 static size_t work_bytes(int n, size_t tsize) {
     const size_t nx = ((size_t)n * tsize + 255) & ~(size_t)255, ni = ((size_t)n * sizeof(int) + 255) & ~(size_t)255;
     const size_t nf = ((size_t)n + 255) & ~(size_t)255;
-    return 2 * nx + 4 * ni + 3 * nf + 256;
+    return 2 * nx + 5 * ni + 3 * nf + 256;
 }
 
 // frontier passes need a symmetric pattern (a row's neighbours are its readers); MLAMG_AGG_FRONTIER=0 forces full passes
@@ -529,6 +645,7 @@ static int lloyd_cluster_t(int n, const int *rowptr, const int *col, const T *w,
         MLAMG_LAUNCHED();
         MLAMG_TRY(fl.fetch(s));
         it++;
+        g_stats[6]++;
         if (!fl.host[0]) break;   // seeds unchanged
     }
     if (iters_host) *iters_host = it;
@@ -628,6 +745,17 @@ __global__ void __launch_bounds__(AGG_THREADS) mbf_seed_kernel(int k, const int 
 using namespace mlamg;
 
 extern "C" {
+
+/* profiling aid: counters accumulated by the aggregation calls of this process since the last reset
+ * [0] ordered relaxation passes [1] order-free passes [2] sequential sweeps emulated [3] pointer-jumping passes
+ * [4] rows evaluated by ordered passes [5] rows evaluated by order-free passes [6] Lloyd iterations [7] unused */
+int mlamg_agg_stats(long long *out8, int reset) {
+    for (int i = 0; i < 8; i++) {
+        if (out8) out8[i] = g_stats[i];
+        if (reset) g_stats[i] = 0;
+    }
+    return MLAMG_OK;
+}
 
 int mlamg_bellman_ford(int dtype, int n, const int *rowptr, const int *col, const void *w, int nseeds,
                        const int *seeds, void *dist, int *nearest, int *sweeps_host, mlamg_stream_t stream) {

@@ -120,65 +120,118 @@ csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ 
     }
 }
 
-// Staged thread-per-row kernel for short rows (mean <= 12 entries: the fine-level operator, P).  A CTA owns 256
-// consecutive rows, i.e. ONE contiguous span of col/val: the span is copied to shared memory with fully
-// coalesced loads (8 + 8 independent loads per thread in flight, every sector requested once), then each
-// thread walks its own row out of shared memory (stride = row length: conflict-free for odd lengths).  The
-// plain thread-per-row kernel asks L1 for every 128-byte line of the span once per entry of a row (7x for
-// the 7-point operator, ncu: 4.3x the DRAM bytes through L1); here L1 only serves the gathers of x.
-constexpr int STAGE_CAP = 2048;      // entries per chunk: 24 KB of shared memory per CTA, 8 CTAs per SM
+// TMA-staged thread-per-row kernel for short rows (the fine-level Q, A: mean <= 12 entries).  A CTA owns 256 consecutive
+// rows, i.e. ONE contiguous span of col and of val.  An elected thread arms an mbarrier with the span's byte count and
+// issues two 1-D bulk copies (cp.async.bulk global -> shared, completion signalled on the mbarrier: SASS UBLKCP); the
+// copies go through the TMA path, not through the LSU/L1, so L1 is left to the gathers of x and the per-row vectors —
+// the plain thread-per-row kernel asks L1 for every 128-byte line of the span once per entry of a row and is bound by
+// that request rate (ncu: 83 % L1 request rate on OP_PSMOOTH0, DRAM traffic already algorithmic).  While the copy is in
+// flight the threads load their row bounds and per-row operands; with 8 CTAs per SM other CTAs compute meanwhile.
+// The previous staged variant (plain coalesced loads + two CTA barriers) lost to the plain kernel, 436 vs 290 us: its
+// barriers serialised load and gather phases; here there is no CTA barrier after the mbarrier initialisation.
+// Bulk copies need 16-byte aligned addresses and sizes: the span start is aligned down (at most 3 ints / 1 value of the
+// previous rows), only whole 16-byte units are copied and the elected thread loads the < 16-byte tail itself, so nothing
+// is read outside [0, end); spans larger than the shared-memory capacity take the plain loads.
+constexpr int STAGE_CAP = 2048;      // entries per CTA: 8 KB + 16 KB of shared memory (f64), 8 CTAs per SM
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <typename T, int OP, bool NORM>
 __global__ void __launch_bounds__(ROW_THREADS, 8)
-csr_staged_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ val,
-                  const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *y,
-                  double *__restrict__ partial, int row0, T *y2) {
-    __shared__ int s_col[STAGE_CAP];
-    __shared__ T s_val[STAGE_CAP];
-    __shared__ int s_ptr[ROW_THREADS + 1];
+csr_tma_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                     const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
+                     const T *__restrict__ dw, T *y, double *__restrict__ partial, int row0, T *y2) {
+    __shared__ __align__(16) int s_col[STAGE_CAP + 8];
+    __shared__ __align__(16) T s_val[STAGE_CAP + 4];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_span[2];
     const int t = threadIdx.x;
     const long long first = (long long)blockIdx.x * ROW_THREADS;        // first row of this CTA, relative to row0
     const int nr = (int)min((long long)ROW_THREADS, (long long)n - first);
     const long long row = first + t + row0;
-    if (t <= nr) s_ptr[t] = rowptr[first + row0 + t];
-    if (t == 0) s_ptr[nr] = rowptr[first + row0 + nr];
-    __syncthreads();
-    const int beg = s_ptr[0], end = s_ptr[nr];
     const bool valid = t < nr;
-    const int my_s = valid ? s_ptr[t] : 0, my_e = valid ? s_ptr[t + 1] : 0;
+    if (t == 0) {
+        const int beg = rowptr[first + row0], end = rowptr[first + row0 + nr];
+        s_span[0] = beg;
+        s_span[1] = end;
+        constexpr int CA = 16 / sizeof(int), VA = 16 / sizeof(T);
+        const int cb = beg & ~(CA - 1), vb = beg & ~(VA - 1);              // aligned starts (inside the arrays)
+        // whole 16-byte units only: the copies never read past `end`; the < 16-byte tails are loaded below
+        const unsigned cbytes = ((unsigned)(end - cb) * (unsigned)sizeof(int)) & ~15u;
+        const unsigned vbytes = ((unsigned)(end - vb) * (unsigned)sizeof(T)) & ~15u;
+        const bool staged = end > beg && end - cb <= STAGE_CAP + 8 && end - vb <= STAGE_CAP + 4 && cbytes > 0 && vbytes > 0 &&
+                            (reinterpret_cast<unsigned long long>(col) & 15ull) == 0 && (reinterpret_cast<unsigned long long>(val) & 15ull) == 0;
+        if (staged) {
+            const unsigned bar = smem_u32(&s_bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cbytes + vbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_col)),
+                         "l"(col + cb), "r"(cbytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_val)),
+                         "l"(val + vb), "r"(vbytes), "r"(bar)
+                         : "memory");
+            for (int j = cb + (int)(cbytes / sizeof(int)); j < end; j++) s_col[j - cb] = col[j];
+            for (int j = vb + (int)(vbytes / sizeof(T)); j < end; j++) s_val[j - vb] = val[j];
+        } else {
+            s_span[0] = -1 - beg;       // negative: not staged
+        }
+    }
+    // per-row operands while the bulk copies are in flight
+    int my_s = 0, my_e = 0;
+    if (valid) {
+        my_s = rowptr[row];
+        my_e = rowptr[row + 1];
+    }
+    __syncthreads();                    // s_span and the initialised barrier are visible
+    const bool staged = s_span[0] >= 0;
     T sum = (T)0;
-    for (int base = beg; base < end; base += STAGE_CAP) {
-        const int cnt = min(STAGE_CAP, end - base);
-#pragma unroll
-        for (int k = 0; k < STAGE_CAP / ROW_THREADS; k++) {
-            const int e = t + k * ROW_THREADS;
-            if (e < cnt) s_col[e] = col[base + e];
-        }
-#pragma unroll
-        for (int k = 0; k < STAGE_CAP / ROW_THREADS; k++) {
-            const int e = t + k * ROW_THREADS;
-            if (e < cnt) s_val[e] = val[base + e];
-        }
-        __syncthreads();
-        const int js = max(my_s, base) - base, je = min(my_e, base + cnt) - base;
-        constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
+    constexpr int NB = (OP == OP_RESZERO) ? 2 : 4;
 #define XOWN(c) (OP == OP_RESZERO ? dw[(c)] * b[(c)] : (OP == OP_RESZERO_S ? b[(c)] : x[(c)]))
-        for (int j = js; j < je; j += NB) {
+    if (staged) {
+        const int beg = s_span[0];
+        constexpr int CA = 16 / sizeof(int), VA = 16 / sizeof(T);
+        const int coff = beg & ~(CA - 1), voff = beg & ~(VA - 1);
+        const unsigned bar = smem_u32(&s_bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(bar), "r"(0u)
+                         : "memory");
+        }
+        for (int j = my_s; j < my_e; j += NB) {
             bool p[NB];
             int c[NB];
             T xv[NB];
 #pragma unroll
-            for (int k = 0; k < NB; k++) p[k] = (k == 0) || (j + k < je);
+            for (int k = 0; k < NB; k++) p[k] = (k == 0) || (j + k < my_e);
 #pragma unroll
-            for (int k = 0; k < NB; k++) c[k] = p[k] ? s_col[j + k] : 0;
+            for (int k = 0; k < NB; k++) c[k] = p[k] ? s_col[j + k - coff] : 0;
 #pragma unroll
             for (int k = 0; k < NB; k++) xv[k] = p[k] ? XOWN(c[k]) : (T)0;
 #pragma unroll
-            for (int k = 0; k < NB; k++) sum += (p[k] ? s_val[j + k] : (T)0) * xv[k];
+            for (int k = 0; k < NB; k++) sum += (p[k] ? s_val[j + k - voff] : (T)0) * xv[k];
         }
-#undef XOWN
-        if (base + STAGE_CAP < end) __syncthreads();
+    } else {
+        for (int j = my_s; j < my_e; j += NB) {
+            bool p[NB];
+            int c[NB];
+            T v[NB], xv[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) p[k] = (k == 0) || (j + k < my_e);
+#pragma unroll
+            for (int k = 0; k < NB; k++) c[k] = p[k] ? col[j + k] : 0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) v[k] = p[k] ? val[j + k] : (T)0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) xv[k] = p[k] ? XOWN(c[k]) : (T)0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) sum += v[k] * xv[k];
+        }
     }
+#undef XOWN
     double rr = 0.0;
     if (valid) rr = row_epilogue<T, OP, NORM>(row, sum, x, b, dw, y, y2);
     if (NORM) {
@@ -235,7 +288,7 @@ sell_rowop_kernel(int n, const int *__restrict__ slice_ptr, const int *__restric
     }
 }
 
-static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic, 0 = staged kernel
+static int g_force_lanes = -1;   // test / tuning hook (mlamg_set_csr_lanes), -1 = heuristic, 0 = TMA-staged kernel
 static int g_force_batch = 0;    // tuning hook (mlamg_set_csr_batch): entries per lane and loop trip (2, 4, 8), 0 = default
 // the heuristic never picks the staged kernel: measured at 256^3 it is slower than the plain thread-per-row
 // kernel (fine Jacobi sweep 436 vs 290 us, prolongation 252 vs 181 us — the two CTA barriers serialise the load
@@ -294,7 +347,7 @@ static int launch_rowop(int n, long long nnz_hint, const int *rowptr, const int 
     } while (0)
     switch (lanes) {
         case 0:
-            csr_staged_kernel<T, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row0, y2);
+            csr_tma_rowop_kernel<T, OP, NORM><<<blocks, ROW_THREADS, 0, s>>>(n, rowptr, col, val, x, b, dw, y, partial, row0, y2);
             break;
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;

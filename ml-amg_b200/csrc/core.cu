@@ -172,12 +172,21 @@ __global__ void __launch_bounds__(256) bin_count_kernel(int m, const int *__rest
     if (threadIdx.x < NB && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
 
+// one global atomic per (CTA, bin) instead of one per row: with 16.7 M rows falling into one or two bins the per-row
+// atomics serialised on five addresses (ncu: 2.4 ms per call, 25 % of the whole setup's kernel time)
 __global__ void __launch_bounds__(256) bin_fill_kernel(int m, const int *__restrict__ binid,
                                                        int *__restrict__ cursors, int *__restrict__ rows) {
+    __shared__ int sc[NB], sbase[NB];
+    if (threadIdx.x < NB) sc[threadIdx.x] = 0;
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int b = binid[i];
-    if (b >= 0) rows[atomicAdd(&cursors[b], 1)] = (int)i;
+    const int b = i < m ? binid[i] : -1;
+    int local = 0;
+    if (b >= 0) local = atomicAdd(&sc[b], 1);          // shared-memory atomic: rank inside the CTA (order is arbitrary)
+    __syncthreads();
+    if (threadIdx.x < NB && sc[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], sc[threadIdx.x]);
+    __syncthreads();
+    if (b >= 0) rows[sbase[b] + local] = (int)i;
 }
 
 int partition_rows_by_bin(int m, const int *binid, int *rows, Bins *bins, cudaStream_t s) {

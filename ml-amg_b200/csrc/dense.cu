@@ -19,8 +19,17 @@ using namespace mlamg;
 extern "C" int mlamg_dense_inverse_f64(int n, double *a, double *work, mlamg_stream_t stream) {
     cudaStream_t s = as_stream(stream);
     if (n <= 0) return set_error(MLAMG_EINVAL, "dense_inverse: n <= 0");
-    cusolverDnHandle_t hd = nullptr;
-    if (cusolverDnCreate(&hd) != CUSOLVER_STATUS_SUCCESS) return set_error(MLAMG_ECUDA, "cusolverDnCreate failed");
+    // one cuSOLVER handle per (thread, device), created on first use: cusolverDnCreate/Destroy cost 30-300 ms per call
+    static thread_local cusolverDnHandle_t g_hd = nullptr;
+    static thread_local int g_hd_device = -1;
+    int dev_now = 0;
+    MLAMG_CUDA(cudaGetDevice(&dev_now));
+    if (g_hd == nullptr || g_hd_device != dev_now) {
+        g_hd = nullptr;
+        if (cusolverDnCreate(&g_hd) != CUSOLVER_STATUS_SUCCESS) return set_error(MLAMG_ECUDA, "cusolverDnCreate failed");
+        g_hd_device = dev_now;
+    }
+    cusolverDnHandle_t hd = g_hd;
     int rc = MLAMG_OK;
     int lwork = 0;
     double *buf = nullptr;
@@ -52,6 +61,5 @@ extern "C" int mlamg_dense_inverse_f64(int n, double *a, double *work, mlamg_str
     if (buf) cudaFree(buf);
     if (ipiv) cudaFree(ipiv);
     if (info) cudaFree(info);
-    cusolverDnDestroy(hd);
     return rc;
 }

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mlamg_hierarchy_set_operator_scaled": (I, [P, I, P]),
     "mlamg_gather": (I, [I, I, P, P, P, P]),
     "mlamg_legacy_permutation_head": (I, [ctypes.c_uint, LL, LL, P]),
+    "mlamg_agg_stats": (I, [P, I]),
     "mlamg_bellman_ford": (I, [I, I, P, P, P, I, P, P, P, P, P]),
     "mlamg_lloyd_cluster": (I, [I, I, P, P, P, I, P, I, P, P, P, P]),
     "mlamg_modified_bellman_ford": (I, [I, P, P, P, I, P, P, P, P, P]),

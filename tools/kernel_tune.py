@@ -58,6 +58,8 @@ def main():
         ops = {
             "reszero_scaled": (lambda: core.jacobi_zero_residual_scaled(Al, vs, dw, b, y, r), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
             "psmooth": (lambda: core.prolong_smooth(Q, e, x, r, dw, y), Q.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N),
+            "psmooth0": (lambda: core.prolong_smooth_zero(Q, e, b, r, dw, y), Q.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N),
+            "residual_scaled": (lambda: core.residual(Al.with_values(vs), b, b, r), nnz * (v + 4) + 4 * (N + 1) + 2 * v * N),
             "jacobi": (lambda: core.jacobi_sweep(Al, dw, b, x, y), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
             "residual": (lambda: core.residual(Al, x, b, r), nnz * (v + 4) + 4 * (N + 1) + 3 * v * N),
             "reszero_fused": (lambda: core.jacobi_zero_residual(Al, dw, b, y, r), nnz * (v + 4) + 4 * (N + 1) + 4 * v * N),
@@ -70,12 +72,16 @@ def main():
         for name, (fn, nbytes) in ops.items():
             out = {"level": l, "op": name, "rows": N if "restrict" not in name else Nc,
                    "mean_row": round((pn / Nc) if "restrict" in name else (pn / N if name == "prolong_add" else
-                                                                           (Q.nnz / N if name == "psmooth" else nnz / N)), 2),
+                                                                           (Q.nnz / N if name.startswith("psmooth") else nnz / N)), 2),
                    "MB": round(nbytes / 1e6, 1), "us": {}, "GBs": {}}
             mean = out["mean_row"]
             cand = [l for l in (1, 2, 4, 8, 16, 32) if l <= max(1, 2 * mean) and l * 16 >= mean]
             if os.environ.get("TUNE_ALL") == "1":
                 cand = [0, 1, 2, 4, 8, 16, 32]
+            if os.environ.get("TUNE_TMA") == "1":          # plain thread-per-row vs the TMA-staged kernel, short-row ops only
+                if mean > 12 or name in ("restrict", "restrict_ordered"):
+                    continue
+                cand = [0, 1]
             for lanes in [-2] + cand:
                 for nb in ((0,) if lanes == -2 else (2, 4, 8)):
                     if lanes == 0 and (name == "restrict_ordered" or nb != 4):

@@ -37,7 +37,7 @@ def main():
     for name in ("_permuted", "lloyd_seeds", "distance_transform"):
         wrap(hm, name)
     exact = 1.0 + np.cos(np.pi / (n + 1))
-    for rep in range(2):
+    for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
         acc.clear()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
