@@ -630,7 +630,9 @@ def main():
     ap.add_argument("--geometry", default="cube", choices=["cube", "slab"],
                     help="N > 1: 'cube' = z-slabs of (2n)x(2n)x(n/4) (512^3 global at n=256 on 8 GPUs, BASELINE config 5), "
                          "'slab' = n x n x n per rank (global n x n x nN)")
-    ap.add_argument("--replicate-below", type=int, default=500000, help="N > 1: global rows below which levels are replicated")
+    ap.add_argument("--replicate-below", type=int, default=40000,
+                    help="N > 1: levels with at most this many GLOBAL rows are replicated on every rank (measured at 256^3 per GPU: a 24 k-row "
+                         "level is cheaper replicated, a 98 k-row level cheaper distributed; profiles/r02_dist_scale_tune_n*.jsonl)")
     ap.add_argument("--parity-n", type=int, default=48, help="N > 1: per-GPU grid side of the pre-timing parity check (0 = skip)")
     ap.add_argument("--profile", action="store_true", help="wrap `steps` plain-launch cycles in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
