@@ -293,6 +293,12 @@ int mlamg_solve_ex(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2
 int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter,
               double *res_host, int *niter_host, mlamg_stream_t stream);
 int mlamg_solver_loop_mode(mlamg_hierarchy_t h);
+/* One Krylov step of the Arnoldi process of GMRES (the `accel='gmres'` of PyAMG.py:119) in ONE call and one host
+ * synchronisation: modified Gram-Schmidt of w against the j+1 basis vectors V[0..j] (contiguous, stride n):
+ * h[i] = w.V_i, w -= h[i] V_i in sequence; h[j+1] = ||w||_2; v_next (may be NULL) = w / h[j+1] unless the norm is 0.
+ * h_host receives the j+2 Hessenberg entries. */
+int mlamg_gmres_orthogonalize(int dtype, int n, int j, const void *V, void *w, void *v_next, double *h_host,
+                              mlamg_stream_t stream);
 
 /* Preconditioner apply with HOST buffers (PETSc PC apply shape: MLAMG.py:199-212, PyAMG.py:118-120):
  * H2D(b) -> `cycles` V-cycles from a zero guess -> D2H(x), all inside the call; returns after x_host

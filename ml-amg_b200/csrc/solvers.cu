@@ -452,6 +452,60 @@ static int run_loop(mlamg_hierarchy *h, LoopGraph &G, piece_fn prologue, piece_f
     return MLAMG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ GMRES helper
+// w -= h * v with h read from device memory (modified Gram-Schmidt step)
+template <typename T>
+__global__ void __launch_bounds__(SOL_THREADS) mgs_axpy_kernel(int n, const T *__restrict__ v, T *__restrict__ w,
+                                                                const double *__restrict__ h) {
+    const double a = *h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        w[i] = (T)((double)w[i] - a * (double)v[i]);
+}
+__global__ void __launch_bounds__(1024) mgs_reduce_kernel(const double *__restrict__ partial, int nb, double *__restrict__ out,
+                                                           int take_sqrt) {
+    __shared__ double sm[32];
+    const double a = sol_reduce(partial, nb, sm);
+    if (threadIdx.x == 0) *out = take_sqrt ? sqrt(a) : a;
+}
+template <typename T>
+__global__ void __launch_bounds__(SOL_THREADS) mgs_scale_kernel(int n, const T *__restrict__ w, T *__restrict__ out,
+                                                                 const double *__restrict__ nrm) {
+    const double a = *nrm;
+    if (a == 0.0) return;
+    const double inv = 1.0 / a;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (T)((double)w[i] * inv);
+}
+
+template <typename T>
+static int gmres_orthogonalize_t(int n, int j, const T *V, T *w, T *v_next, double *h_host, cudaStream_t s) {
+    const unsigned vb = vec_blocks(n);
+    Scratch part((size_t)vb * sizeof(double), s), dh((size_t)(j + 2) * sizeof(double), s);
+    MLAMG_SCRATCH_OK(part);
+    MLAMG_SCRATCH_OK(dh);
+    double *h = dh.as<double>();
+    for (int i = 0; i <= j; i++) {
+        const T *vi = V + (size_t)i * (size_t)n;
+        sol_dot_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, w, vi, nullptr, part.as<double>());
+        MLAMG_LAUNCHED();
+        mgs_reduce_kernel<<<1, 1024, 0, s>>>(part.as<double>(), (int)vb, h + i, 0);
+        MLAMG_LAUNCHED();
+        mgs_axpy_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, vi, w, h + i);
+        MLAMG_LAUNCHED();
+    }
+    sol_dot_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, w, w, nullptr, part.as<double>());
+    MLAMG_LAUNCHED();
+    mgs_reduce_kernel<<<1, 1024, 0, s>>>(part.as<double>(), (int)vb, h + j + 1, 1);
+    MLAMG_LAUNCHED();
+    if (v_next) {
+        mgs_scale_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, w, v_next, h + j + 1);
+        MLAMG_LAUNCHED();
+    }
+    MLAMG_CUDA(cudaMemcpyAsync(h_host, h, (size_t)(j + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MLAMG_CUDA(cudaStreamSynchronize(s));
+    return MLAMG_OK;
+}
+
 }  // namespace mlamg
 
 using namespace mlamg;
@@ -485,6 +539,13 @@ int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, dou
     MLAMG_TRY(ensure_state(h, maxiter));
     MLAMG_DISPATCH(h->dtype, return run_loop(h, h->solver->pcg, pcg_prologue<T>, pcg_body<T>, LOOKAHEAD, b, x, nu1, nu2, 0, rtol, maxiter,
                                              res_host, niter_host, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_gmres_orthogonalize(int dtype, int n, int j, const void *V, void *w, void *v_next, double *h_host,
+                              mlamg_stream_t stream) {
+    if (n <= 0 || j < 0 || !V || !w || !h_host) return set_error(MLAMG_EINVAL, "gmres_orthogonalize: bad arguments");
+    MLAMG_DISPATCH(dtype, return gmres_orthogonalize_t<T>(n, j, (const T *)V, (T *)w, (T *)v_next, h_host, as_stream(stream)));
     return MLAMG_OK;
 }
 

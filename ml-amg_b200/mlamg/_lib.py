@@ -84,6 +84,7 @@ SIGNATURES = {
     "mlamg_solve_ex": (I, [P, P, P, I, I, I, D, I, P, P, P]),
     "mlamg_pcg": (I, [P, P, P, I, I, D, I, P, P, P]),
     "mlamg_solver_loop_mode": (I, [P]),
+    "mlamg_gmres_orthogonalize": (I, [I, I, I, P, P, P, P, P]),
     "mlamg_vcycle_host": (I, [P, P, P, I, I, I, P]),
     "mlamg_peer_alloc": (I, [LL, P, P]),
     "mlamg_peer_open": (I, [P, P]),

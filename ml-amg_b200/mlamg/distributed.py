@@ -231,7 +231,9 @@ PEER_INPLACE = _os.environ.get("MLAMG_PEER_INPLACE", "1") == "1"
 # boundary rows (the HALO kernel, which spins on values that have not landed) on the forked high-priority stream right
 # behind the push, BESIDE the interior rows instead of after them: their few CTAs are scheduled ahead of the interior
 # kernel's queued CTAs and wait for the neighbours' stores while the interior rows keep the SMs busy
-PEER_BOUNDARY_SIDE = _os.environ.get("MLAMG_PEER_BOUNDARY_SIDE", "1") == "1"
+# 2: boundary rows on a second, normal-priority side stream enqueued behind the interior launch (they then run in the
+# interior kernel's tail wave, when the halo has long arrived, instead of spinning on SM slots at the start)
+PEER_BOUNDARY_SIDE = int(_os.environ.get("MLAMG_PEER_BOUNDARY_SIDE", "1"))
 _ALIGN = 256
 
 
@@ -482,6 +484,16 @@ def gather_csr(rowptr, col, val, comm):
 # =====================================================================================================
 # distributed level + hierarchy (GPU)
 # =====================================================================================================
+_LOW_STREAM = {}
+
+
+def _low_stream():
+    d = torch.cuda.current_device()
+    if d not in _LOW_STREAM:
+        _LOW_STREAM[d] = torch.cuda.Stream(priority=0)
+    return _LOW_STREAM[d]
+
+
 class DistOperator:
     """Local rows of a row-partitioned operator, columns in ext numbering, with its halo plan."""
 
@@ -581,13 +593,19 @@ class DistOperator:
             A = self._csr_for(op)
             xk = b if op == 8 else xin
             rows = self.boundary if split else None
-            side = fork and PEER_BOUNDARY_SIDE and (PEER_INPLACE or op in (4, 6, 8))
-            if side:                   # boundary rows right behind the push on the side stream, beside the interior rows
+            side = PEER_BOUNDARY_SIDE if (fork and (PEER_INPLACE or op in (4, 6, 8))) else 0
+            if side == 1:              # boundary rows right behind the push on the side stream, beside the interior rows
                 with torch.cuda.stream(comm_stream):
                     chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             if split:
                 core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
                            rows=None if self.interior_range is not None else self.interior)
+            if side == 2:              # boundary rows on a normal-priority stream, enqueued behind the interior launch
+                lo = _low_stream()
+                lo.wait_stream(comm_stream)
+                with torch.cuda.stream(lo):
+                    chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
+                main.wait_stream(lo)
             if fork:
                 main.wait_stream(comm_stream)
             if side:

@@ -322,8 +322,9 @@ class Hierarchy:
 
     def _gmres(self, b, x, tol, maxiter, nu1, nu2, restart):
         """Left-preconditioned GMRES(restart), modified Gram-Schmidt + Givens; x updated in place.  The operator
-        applications (A v, one V-cycle per Krylov vector) and the dot products / updates run in libmlamg_b200.so;
-        the (restart+1) x restart Hessenberg lives on the host.  Same algorithm as oracle.multilevel.gmres."""
+        applications (A v, one V-cycle per Krylov vector) run in libmlamg_b200.so and the whole Gram-Schmidt step of a
+        Krylov vector is ONE call with one host sync (mlamg_gmres_orthogonalize); the (restart+1) x restart Hessenberg
+        lives on the host.  Same algorithm as oracle.multilevel.gmres."""
         A = self.levels[0].A
         n = A.shape[0]
         t = torch.empty(n, dtype=self.dtype, device=b.device)
@@ -335,6 +336,7 @@ class Hierarchy:
         nmb = float(torch.linalg.vector_norm(self.vcycle(b, None, nu1, nu2)).item())
         stop = tol * (nmb if nmb != 0 else 1.0)
         res, it = [], 0
+        basis = None
         while True:
             r = precond_residual()
             beta = float(np.sqrt(core.dot(r, r)))
@@ -343,20 +345,24 @@ class Hierarchy:
             if beta <= stop or it >= maxiter:
                 break
             m = min(int(restart), maxiter - it)
-            V = [r.mul_(1.0 / beta)]
+            if basis is None or basis.shape[0] < m + 1:
+                basis = torch.empty(m + 1, n, dtype=self.dtype, device=b.device)      # Krylov basis, contiguous
+            torch.mul(r, 1.0 / beta, out=basis[0])
+            nvec = 1
             Hm = np.zeros((m + 1, m))
+            hcol = (ctypes.c_double * (m + 2))()
             cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
             g[0] = beta
             k = 0
             for j in range(m):
-                core.spmv(A, V[j], out=t)
+                core.spmv(A, basis[j], out=t)
                 w = self.vcycle(t, None, nu1, nu2)
-                for i in range(j + 1):
-                    Hm[i, j] = core.dot(w, V[i])
-                    core.axpby(-Hm[i, j], V[i], 1.0, w)
-                Hm[j + 1, j] = float(np.sqrt(core.dot(w, w)))
+                # modified Gram-Schmidt against V[0..j], the norm and the next basis vector: one C call, one host sync
+                check(lib.mlamg_gmres_orthogonalize(core.dt(self.dtype), n, j, ptr(basis), ptr(w), ptr(basis[j + 1]), hcol,
+                                                    stream()))
+                Hm[:j + 2, j] = hcol[:j + 2]
                 if Hm[j + 1, j] != 0.0:
-                    V.append(w.mul_(1.0 / Hm[j + 1, j]))
+                    nvec += 1
                 for i in range(j):
                     tmp = cs[i] * Hm[i, j] + sn[i] * Hm[i + 1, j]
                     Hm[i + 1, j] = -sn[i] * Hm[i, j] + cs[i] * Hm[i + 1, j]
@@ -370,11 +376,11 @@ class Hierarchy:
                 it += 1
                 k = j + 1
                 res.append(abs(g[j + 1]))
-                if res[-1] <= stop or len(V) <= j + 1:
+                if res[-1] <= stop or nvec <= j + 1:
                     break
             y = np.linalg.solve(np.triu(Hm[:k, :k]), g[:k]) if k else np.zeros(0)
             for i in range(k):
-                core.axpby(float(y[i]), V[i], 1.0, x)
+                core.axpby(float(y[i]), basis[i], 1.0, x)
             if res[-1] <= stop:
                 break
         return np.array(res)

@@ -194,3 +194,131 @@ def random_gnn_outputs(A, alpha=0.1, seed=0):
     bf = torch.relu(torch.randn(A.nnz, generator=g)).to(torch.float32)
     ph = torch.relu(torch.randn(A.nnz, generator=g)).to(torch.float32)
     return top_k.numpy().astype(np.int64), bf.numpy(), ph.numpy()
+
+
+# ------------------------------------------------------------------------------------------ distributed Delaunay (config 4)
+def _morton_key(pts, bits=16):
+    q = np.clip((pts * (1 << bits)).astype(np.uint64), 0, (1 << bits) - 1)
+
+    def spread(v):
+        v = (v | (v << 16)) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << 8)) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << 2)) & np.uint64(0x3333333333333333)
+        v = (v | (v << 1)) & np.uint64(0x5555555555555555)
+        return v
+    return spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+
+
+def hull_vertices(pts, directions=32):
+    """indices of the convex-hull vertices of a large planar point set: points strictly inside the polygon of the
+    extreme points in `directions` directions cannot be hull vertices (Akl-Toussaint), Qhull runs on the rest."""
+    from scipy.spatial import ConvexHull
+    th = np.linspace(0.0, 2.0 * np.pi, directions, endpoint=False)
+    ext = np.unique([int(np.argmax(pts[:, 0] * np.cos(t) + pts[:, 1] * np.sin(t))) for t in th])
+    poly = pts[ext]
+    c = poly.mean(axis=0)
+    poly = poly[np.argsort(np.arctan2(poly[:, 1] - c[1], poly[:, 0] - c[0]))]       # counter-clockwise
+    inside = np.ones(pts.shape[0], dtype=bool)
+    for a, b in zip(poly, np.roll(poly, -1, axis=0)):
+        cross = (b[0] - a[0]) * (pts[:, 1] - a[1]) - (b[1] - a[1]) * (pts[:, 0] - a[0])
+        inside &= cross > 1e-14
+    cand = np.nonzero(~inside)[0]
+    return cand[ConvexHull(pts[cand]).vertices]
+
+
+def strip_order(pts, world, keep=None):
+    """Global numbering of the row partition of config 4: strip r owns y in [r/world, (r+1)/world); inside a strip rows
+    follow the Z-curve.  keep: boolean mask of the points that become rows (the others, Dirichlet nodes, get -1).
+    -> (new_index int64[npts], offsets int64[world+1])"""
+    n = pts.shape[0]
+    strip = np.minimum((pts[:, 1] * world).astype(np.int64), world - 1)
+    key = _morton_key(pts)
+    sel = np.nonzero(keep)[0] if keep is not None else np.arange(n)
+    order = sel[np.lexsort((key[sel], strip[sel]))]
+    new = np.full(n, -1, dtype=np.int64)
+    new[order] = np.arange(order.size)
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(strip[sel], minlength=world))]).astype(np.int64)
+    return new, offsets
+
+
+def delaunay_laplacian_strips(npts, seed=0, world=1):
+    """GLOBAL reference of the distributed generator below: P1 Laplacian on the Delaunay mesh of npts uniform random
+    points, Dirichlet hull removed, rows in strip_order.  -> (A csr, offsets)"""
+    pts, tris, bnd = delaunay_triangles(npts, seed)
+    new, offsets = strip_order(pts, world, ~bnd)
+    A = p1_stiffness(pts, tris, None)
+    keep = np.nonzero(~bnd)[0]
+    perm = keep[np.argsort(new[keep])]
+    Ad = sp.csr_matrix(A[perm][:, perm])
+    Ad.eliminate_zeros()
+    Ad.sort_indices()
+    return Ad, offsets
+
+
+def delaunay_laplacian_distributed(npts, seed, world, rank, halo_factor=10.0, info=None):
+    """Rows of rank `rank` of delaunay_laplacian_strips(npts, seed, world) WITHOUT triangulating the whole point set:
+    every rank draws the same points (the RNG stream is cheap), triangulates only its own strip plus a halo band of
+    width delta, and keeps the triangles it can certify: a local Delaunay triangle is a triangle of the global mesh
+    when the part of its circumdisc that lies inside the domain is inside the band the rank holds all points of.  If a
+    triangle touching an owned node cannot be certified the band is doubled and the step repeated.
+    -> (rowptr int32, global col int64, val float64, offsets)   rows = owned non-Dirichlet nodes in strip_order"""
+    from scipy.spatial import Delaunay
+    rs = np.random.RandomState(seed)
+    pts = rs.uniform(0.0, 1.0, size=(int(npts), 2))
+    bnd = np.zeros(pts.shape[0], dtype=bool)
+    bnd[hull_vertices(pts)] = True
+    new, offsets = strip_order(pts, world, ~bnd)
+    lo, hi = rank / world, (rank + 1) / world
+    strip = np.minimum((pts[:, 1] * world).astype(np.int64), world - 1)
+    own_mask = strip == rank
+    delta = halo_factor / np.sqrt(float(npts))
+    while True:
+        blo = lo - delta if lo - delta > 0.0 else -np.inf
+        bhi = hi + delta if hi + delta < 1.0 else np.inf
+        eps = delta
+        # the band of the strip plus thin layers along the left / right edges over the full height: the hull has only
+        # O(log n) vertices, so the triangles along those edges are long slivers between far-apart hull vertices; their
+        # (empty) circumdiscs meet the domain in caps a few 1/(n L) wide that hug the edge
+        loc = np.nonzero(((pts[:, 1] >= blo) & (pts[:, 1] <= bhi)) | (pts[:, 0] <= eps) | (pts[:, 0] >= 1.0 - eps))[0]
+        p = pts[loc]
+        tris = Delaunay(p).simplices.astype(np.int64)
+        own_l = own_mask[loc]
+        touch = own_l[tris].any(axis=1)
+        t = tris[touch]
+        a, b, c = p[t[:, 0]], p[t[:, 1]], p[t[:, 2]]
+        # circumcentre / radius
+        d = 2.0 * (a[:, 0] * (b[:, 1] - c[:, 1]) + b[:, 0] * (c[:, 1] - a[:, 1]) + c[:, 0] * (a[:, 1] - b[:, 1]))
+        a2, b2, c2 = (a ** 2).sum(1), (b ** 2).sum(1), (c ** 2).sum(1)
+        ux = (a2 * (b[:, 1] - c[:, 1]) + b2 * (c[:, 1] - a[:, 1]) + c2 * (a[:, 1] - b[:, 1])) / d
+        uy = (a2 * (c[:, 0] - b[:, 0]) + b2 * (a[:, 0] - c[:, 0]) + c2 * (b[:, 0] - a[:, 0])) / d
+        rho = np.sqrt((a[:, 0] - ux) ** 2 + (a[:, 1] - uy) ** 2) * (1.0 + 1e-12)
+
+        def part_covered(limit, above):
+            """the part of the disc beyond y = limit (above / below) lies outside 0 <= x <= 1 or inside an edge layer"""
+            if not np.isfinite(limit):
+                return np.ones(ux.shape, dtype=bool)
+            dist = (limit - uy) if above else (uy - limit)             # signed distance from the centre to the line
+            empty = dist >= rho                                        # the disc does not reach beyond the line
+            wx = np.sqrt(np.maximum(rho ** 2 - np.maximum(dist, 0.0) ** 2, 0.0))
+            return empty | (ux + wx <= eps) | (ux - wx >= 1.0 - eps)
+        ok = part_covered(bhi, True) & part_covered(blo, False)
+        if ok.all() or (blo == -np.inf and bhi == np.inf):
+            break
+        delta *= 2.0
+    if info is not None:
+        info.update(local_points=int(loc.size), owned=int(own_mask.sum()), delta=float(delta), triangles=int(t.shape[0]))
+    # P1 stiffness of the kept triangles, rows of owned non-Dirichlet nodes, global columns
+    A = p1_stiffness(p, t, None)
+    g = new[loc]                                                        # local point -> global row id (-1 = Dirichlet)
+    rows_l = np.nonzero(own_l & (g >= 0))[0]
+    rows_l = rows_l[np.argsort(g[rows_l])]
+    Ar = sp.csr_matrix(A[rows_l])
+    coo = Ar.tocoo()
+    keepc = g[coo.col] >= 0
+    n_glob = int(offsets[-1])
+    Ag = sp.coo_matrix((coo.data[keepc], (coo.row[keepc], g[coo.col[keepc]])), shape=(rows_l.size, n_glob)).tocsr()
+    Ag.eliminate_zeros()
+    Ag.sort_indices()
+    assert rows_l.size == int(offsets[rank + 1] - offsets[rank])
+    return Ag.indptr.astype(np.int32), Ag.indices.astype(np.int64), Ag.data, offsets

@@ -1,6 +1,6 @@
 """Multi-rank parity check of the row-partitioned hierarchy against the partitioned CPU oracle.
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py [n] [--cube] [--delaunay]
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py [n] [--cube] [--delaunay | --delaunay-strips]
 
 Each rank owns a z-slab of the global n x n x (n_z*world) Poisson grid.  Checks (per rank, its rows):
 aggregates bit-exact, P and the Galerkin operator of every distributed level bit-identical to the global
@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 
 
-def run_check(n, comm, geometry="slab", delaunay=False, verbose=True, extras=True):
+def run_check(n, comm, geometry="slab", delaunay=False, verbose=True, extras=True, strips=False):
     """Build the row-partitioned hierarchy on this communicator and hold it to the partitioned CPU oracle.
     -> dict(ok, labels_equal, P_bitwise, A_bitwise, vcycle_rel_err, pcg_iters_equal, pcg_hist_err, ...) for THIS rank.
     extras: also the transport/graph self-consistency checks (skipped by bench.py's pre-timing parity leg)."""
@@ -32,13 +32,30 @@ def run_check(n, comm, geometry="slab", delaunay=False, verbose=True, extras=Tru
         # BASELINE config 4 shape: P1 Laplacian on a Delaunay mesh of n random points (Morton-ordered rows, ~7 entries
         # per row), contiguous row blocks.  Every rank generates the same global matrix and keeps its rows.
         from mlamg import problems
-        A, _ = problems.delaunay_laplacian(n, seed=0)
-        N = A.shape[0]
-        offsets = [int(round(r * N / world)) for r in range(world + 1)]
-        Al = A[offsets[rank]:offsets[rank + 1]]
-        rowptr = torch.from_numpy(Al.indptr.astype(np.int32)).cuda()
-        col = torch.from_numpy(Al.indices.astype(np.int32)).cuda()
-        val = torch.from_numpy(Al.data.copy()).cuda()
+        if strips:
+            # the distributed generator of config 4 (every rank triangulates its own strip + certified halo only); the
+            # global matrix built here is only the oracle's input
+            A, offs_np = problems.delaunay_laplacian_strips(n, 0, world)
+            N = A.shape[0]
+            offsets = [int(v) for v in offs_np]
+            rp_l, col_l, val_l, offs_l = problems.delaunay_laplacian_distributed(n, 0, world, rank)
+            assert list(offs_l) == offsets
+            rowptr = torch.from_numpy(rp_l).cuda()
+            col = torch.from_numpy(col_l.astype(np.int32)).cuda()
+            val = torch.from_numpy(val_l.copy()).cuda()
+            # the oracle is given exactly the rows the ranks hold (entry sums may differ in the last bit between the two
+            # assemblies), so that P / Galerkin can be compared bit for bit
+            parts = comm.all_gather_obj((rp_l, col_l, val_l))
+            A = sp.vstack([sp.csr_matrix((v, c, r), shape=(len(r) - 1, N)) for r, c, v in parts]).tocsr()
+            A.sort_indices()
+        else:
+            A, _ = problems.delaunay_laplacian(n, seed=0)
+            N = A.shape[0]
+            offsets = [int(round(r * N / world)) for r in range(world + 1)]
+            Al = A[offsets[rank]:offsets[rank + 1]]
+            rowptr = torch.from_numpy(Al.indptr.astype(np.int32)).cuda()
+            col = torch.from_numpy(Al.indices.astype(np.int32)).cuda()
+            val = torch.from_numpy(Al.data.copy()).cuda()
         lam = [2.0, 1.9, 1.8, 1.7, 1.6]
         kw = dict(ratio=0.08, distance="unit", maxiter=10, rand=0, lam_max=lam, max_levels=6, max_coarse=30,
                   replicate_below=max(60, N // 20))
@@ -157,7 +174,8 @@ def run_check(n, comm, geometry="slab", delaunay=False, verbose=True, extras=Tru
 
 def main():
     args = [a for a in sys.argv[1:]]
-    delaunay = "--delaunay" in args
+    strips = "--delaunay-strips" in args
+    delaunay = "--delaunay" in args or strips
     geometry = "cube" if "--cube" in args else "slab"
     nums = [a for a in args if not a.startswith("--")]
     n = int(nums[0]) if nums else (4000 if delaunay else 12)
@@ -168,7 +186,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from mlamg import distributed as md
-    out = run_check(n, md.Comm(), geometry=geometry, delaunay=delaunay)
+    out = run_check(n, md.Comm(), geometry=geometry, delaunay=delaunay, strips=strips)
     print(f"[rank {rank}] {'PASS' if out['ok'] else 'FAIL'}: {out['dist_levels']} distributed + {out['tail_levels']} replicated "
           f"levels, halo {out['halo_entries']} entries, {geometry if not delaunay else 'delaunay'}", flush=True)
     if world > 1:

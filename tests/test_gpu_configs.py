@@ -19,7 +19,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import ROOT, assert_csr_close, hist_err0
+from helpers import ROOT, assert_csr_close, assert_csr_bitwise, hist_err0
 from oracle import reference_path as rp, multilevel as oml, pyamg_restated as pr
 
 pytestmark = pytest.mark.gpu
@@ -115,7 +115,7 @@ def test_config3_voronoi_jump_gnn_tail_small_vs_oracle(mesh, size):
     assert abs(conv_g - conv_r) < 1e-9
 
 
-def test_config3_voronoi_jump_4m_dof_properties():
+def test_config3_voronoi_jump_4m_dof_vs_oracle_and_properties():
     import mlamg
     from mlamg import problems, core
     import ns.model.agg_interp as ai
@@ -126,6 +126,22 @@ def test_config3_voronoi_jump_4m_dof_properties():
     k = len(top_k)
     Ad = mlamg.DeviceCSR.from_scipy(A)
     agg_T, labels, dist, near = ai.bellman_ford_aggregates(Ad, top_k, bf)
+    # --- FULL-SIZE parity against the oracle (the C restatement needs about a second at 4 M nodes): Bellman-Ford
+    # distances and nearest centres incl. tie-breaking bit-exact in fp32, aggregates, the learned prolongator in the
+    # callers' fp32 (1e-5) and in fp64 (bit-identical), the Galerkin operator bit-identical
+    C = sp.csr_matrix((bf, A.indices, A.indptr), shape=A.shape)
+    d_ref, near_ref = pr.bellman_ford(C, top_k)
+    assert np.array_equal(near.cpu().numpy(), near_ref), "4M: nearest centres differ from the oracle"
+    assert np.array_equal(dist.cpu().numpy(), d_ref)
+    Agg_ref = rp.nearest_center_to_agg(top_k, near_ref)
+    lab_ref = np.full(n, -1, dtype=np.int64)
+    coo = sp.coo_matrix(Agg_ref)
+    lab_ref[coo.row] = coo.col
+    assert np.array_equal(labels.cpu().numpy(), lab_ref)
+    P32_ref = sp.csr_matrix(rp.learned_prolongator(sp.csr_matrix((ph, A.indices, A.indptr), shape=A.shape), Agg_ref))
+    _, P32 = ai.learned_prolongator(Ad, ph, labels, k)
+    assert_csr_close(mlamg.drop_zeros(P32).to_scipy().astype(np.float64), P32_ref.astype(np.float64), 1e-5)
+    del P32, P32_ref
     # --- multi-source shortest paths: labels valid, centres own themselves, no edge can still relax (fp32 sums)
     tk = torch.from_numpy(top_k).cuda()
     assert int(labels.min()) >= 0 and int(labels.max()) < k
@@ -160,6 +176,10 @@ def test_config3_voronoi_jump_4m_dof_properties():
     H = mlamg.build_hierarchy(Ad, aggregates=[(labels, k)], P_hat=[ph.astype(np.float64) + 0.1], fallback="lloyd", ratio=0.1,
                               distance="unit", rand=0, max_coarse=1000, max_levels=8)
     assert len(H.levels) >= 4 and H.levels[1].A.shape[0] == k
+    P64_ref = sp.csr_matrix(rp.learned_prolongator(sp.csr_matrix((ph.astype(np.float64) + 0.1, A.indices, A.indptr), shape=A.shape),
+                                                   sp.csr_matrix(Agg_ref).astype(np.float64)))
+    assert_csr_bitwise(H.levels[0].P.to_scipy(), rp.canonical_csr(P64_ref, drop_zeros=False))
+    assert_csr_bitwise(H.levels[1].A.to_scipy(), rp.canonical_csr(rp.galerkin(A, P64_ref)))
     A1, P0 = H.levels[1].A, H.levels[0].P
     A1t = core.transpose(A1)
     assert torch.equal(A1t.rowptr, A1.rowptr) and torch.equal(A1t.col, A1.col)
@@ -204,3 +224,21 @@ def test_config4_delaunay_row_partitioned_world1():
 def test_config4_delaunay_row_partitioned_world2():
     out = _run_dist(2, ["--delaunay", 6000])
     assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_config4_distributed_delaunay_generator_world2():
+    """every rank triangulates only its strip + certified halo (mlamg.problems.delaunay_laplacian_distributed)"""
+    out = _run_dist(2, ["--delaunay-strips", 8000])
+    assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+def test_config4_distributed_delaunay_generator_world4():
+    out = _run_dist(4, ["--delaunay-strips", 12000])
+    assert out.returncode == 0 and out.stdout.count("PASS") == 4, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_config4_distributed_delaunay_generator_world1():
+    out = _run_dist(1, ["--delaunay-strips", 5000])
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -98,3 +98,23 @@ def test_grid_container_roundtrip_and_reference_fixture(tmp_path):
     if os.path.exists(ref):
         r = Grid.load(ref)
         assert r.A.shape == (1331, 1331) and r.A.nnz == 17191 and r.x.shape == (1331, 3) and r.extra["dim"] == 3
+
+
+def test_distributed_delaunay_rows_equal_the_global_mesh():
+    """config 4's distributed generator: every rank triangulates its own strip plus a certified halo band (and the thin
+    layers along the left/right edges) and must produce exactly its rows of the global P1 Laplacian"""
+    import scipy.sparse as sp
+    from mlamg import problems
+    for seed, npts, world in [(0, 3000, 3), (1, 20000, 4), (2, 60000, 8)]:
+        A, offs = problems.delaunay_laplacian_strips(npts, seed, world)
+        assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+        for r in range(world):
+            info = {}
+            rp_, col, val, offs2 = problems.delaunay_laplacian_distributed(npts, seed, world, r, info=info)
+            assert np.array_equal(offs, offs2)
+            Al = sp.csr_matrix((val, col, rp_), shape=(len(rp_) - 1, A.shape[1]))
+            Ar = sp.csr_matrix(A[offs[r]:offs[r + 1]])
+            assert np.array_equal(Al.indptr, Ar.indptr) and np.array_equal(Al.indices, Ar.indices), (seed, npts, world, r)
+            assert np.abs(Al.data - Ar.data).max() <= 1e-13 * np.abs(Ar.data).max()
+            if world >= 4 and npts >= 20000:
+                assert info["local_points"] < 0.7 * npts            # nowhere near the whole point set

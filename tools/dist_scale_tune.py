@@ -54,12 +54,12 @@ def main():
                "dist_levels": [int(o[-1]) for o in H.offsets[:-1]], "tail": [l.A.shape[0] for l in H.tail.levels],
                "halo_fine": H.levels[0].A.plan.n_halo,
                "setup_stages_s": {k: round(v, 3) for k, v in H.setup_profile.acc.items()}}
-        for side in (True, False):
+        for side, key in ((1, "ms_boundary_side"), (0, "ms_boundary_after"), (2, "ms_boundary_tail_stream")):
             md.PEER_BOUNDARY_SIDE = side
             replay = H.capture(b, x, 1, 1)
-            res["ms_boundary_side" if side else "ms_boundary_after"] = timed(replay)
+            res[key] = timed(replay)
             H._graph = None
-        md.PEER_BOUNDARY_SIDE = True
+        md.PEER_BOUNDARY_SIDE = 1
         H.check_exchange()
         if rank == 0:
             print(json.dumps(res), flush=True)
