@@ -76,78 +76,47 @@ __global__ void __launch_bounds__(256) spgemm_binid_kernel(int m, const int *__r
     binid[i] = bin_of(ub[i], nnz, symbolic);
 }
 
-// ---------------------------------------------------------------- warp-per-row kernels (ub <= 128)
-// 4 sub-groups of 8 lanes: a sub-group takes one A entry, its lanes stride over that B row.
-template <typename T, bool NUMERIC>
+// ---------------------------------------------------------------- symbolic phase: warp-per-row kernel (ub <= 128)
+// 4 sub-groups of 8 lanes: a sub-group takes one A entry, its lanes stride over that B row; distinct columns are counted
+// through a shared-memory hash table (the numeric phase is the ORDERED kernels further down).
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
-spgemm_warp_kernel(int nrows, const int *__restrict__ rows, const int *__restrict__ a_rowptr,
-                   const int *__restrict__ a_col, const T *__restrict__ a_val, const int *__restrict__ b_rowptr,
-                   const int *__restrict__ b_col, const T *__restrict__ b_val, int *__restrict__ c_rowptr,
-                   int *__restrict__ c_col, T *__restrict__ c_val) {
+spgemm_symbolic_warp_kernel(int nrows, const int *__restrict__ rows, const int *__restrict__ a_rowptr,
+                            const int *__restrict__ a_col, const int *__restrict__ b_rowptr,
+                            const int *__restrict__ b_col, int *__restrict__ c_rowptr) {
     __shared__ int s_keys[WARPS_PER_CTA][WARP_TS];
-    __shared__ T s_vals[NUMERIC ? WARPS_PER_CTA : 1][NUMERIC ? WARP_TS : 1];
-    __shared__ int s_cnt[WARPS_PER_CTA];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * WARPS_PER_CTA + wid;
     if (r >= nrows) return;  // whole warp exits together
     const int row = rows[r];
     int *keys = s_keys[wid];
-    T *vals = NUMERIC ? s_vals[wid] : nullptr;
-    for (int t = lane; t < WARP_TS; t += 32) {
-        keys[t] = -1;
-        if (NUMERIC) vals[t] = (T)0;
-    }
-    if (lane == 0) s_cnt[wid] = 0;
+    for (int t = lane; t < WARP_TS; t += 32) keys[t] = -1;
     __syncwarp();
     const int sub = lane >> 3, sl = lane & 7;
     int fresh = 0;
     for (int ja = a_rowptr[row] + sub; ja < a_rowptr[row + 1]; ja += 4) {
         const int k = a_col[ja];
-        const T av = NUMERIC ? a_val[ja] : (T)0;
         for (int jb = b_rowptr[k] + sl; jb < b_rowptr[k + 1]; jb += 8) {
             unsigned slot;
-            const int ins = table_insert(keys, WARP_TS - 1, b_col[jb], &slot);
-            if (ins > 0) fresh++;
-            if (NUMERIC) atomicAdd(&vals[slot], av * b_val[jb]);
+            if (table_insert(keys, WARP_TS - 1, b_col[jb], &slot) > 0) fresh++;
         }
     }
     __syncwarp();
-    if (!NUMERIC) {
-        fresh = warp_sum(fresh);
-        if (lane == 0) c_rowptr[row] = fresh;  // counts; scanned by the caller
-    } else {
-        const int base = c_rowptr[row];
-        for (int t = lane; t < WARP_TS; t += 32) {
-            const int key = keys[t];
-            if (key != -1) {
-                const int pos = atomicAdd(&s_cnt[wid], 1);
-                c_col[base + pos] = key;
-                c_val[base + pos] = vals[t];
-            }
-        }
-    }
+    fresh = warp_sum(fresh);
+    if (lane == 0) c_rowptr[row] = fresh;  // counts; scanned by the caller
 }
 
-// ---------------------------------------------------------------- CTA-per-row kernels
-// dynamic shared memory: int keys[ts]; T vals[ts] (numeric only).  Warps take A entries, lanes
-// stride over the B row.
-template <typename T, bool NUMERIC>
-__global__ void spgemm_cta_kernel(int nrows, const int *__restrict__ rows, int ts,
-                                  const int *__restrict__ a_rowptr, const int *__restrict__ a_col,
-                                  const T *__restrict__ a_val, const int *__restrict__ b_rowptr,
-                                  const int *__restrict__ b_col, const T *__restrict__ b_val,
-                                  int *__restrict__ c_rowptr, int *__restrict__ c_col, T *__restrict__ c_val,
-                                  int *__restrict__ overflow) {
+// ---------------------------------------------------------------- symbolic phase: CTA-per-row kernel
+// dynamic shared memory: int keys[ts].  Warps take A entries, lanes stride over the B row.
+__global__ void spgemm_symbolic_cta_kernel(int nrows, const int *__restrict__ rows, int ts,
+                                           const int *__restrict__ a_rowptr, const int *__restrict__ a_col,
+                                           const int *__restrict__ b_rowptr, const int *__restrict__ b_col,
+                                           int *__restrict__ c_rowptr, int *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_cnt;
     __shared__ int s_full;
     int *keys = reinterpret_cast<int *>(smem_raw);
-    T *vals = reinterpret_cast<T *>(smem_raw + (size_t)ts * sizeof(int));
     const int row = rows[blockIdx.x];
-    for (int t = threadIdx.x; t < ts; t += blockDim.x) {
-        keys[t] = -1;
-        if (NUMERIC) vals[t] = (T)0;
-    }
+    for (int t = threadIdx.x; t < ts; t += blockDim.x) keys[t] = -1;
     if (threadIdx.x == 0) { s_cnt = 0; s_full = 0; }
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -155,35 +124,19 @@ __global__ void spgemm_cta_kernel(int nrows, const int *__restrict__ rows, int t
     int fresh = 0;
     for (int ja = a_rowptr[row] + wid; ja < a_rowptr[row + 1]; ja += nw) {
         const int k = a_col[ja];
-        const T av = NUMERIC ? a_val[ja] : (T)0;
         for (int jb = b_rowptr[k] + lane; jb < b_rowptr[k + 1]; jb += 32) {
             unsigned slot = 0;
             const int ins = table_insert(keys, mask, b_col[jb], &slot);
             if (ins < 0) { s_full = 1; break; }
             if (ins > 0) fresh++;
-            if (NUMERIC) atomicAdd(&vals[slot], av * b_val[jb]);
         }
     }
-    if (!NUMERIC) {
-        fresh = warp_sum(fresh);
-        if (lane == 0 && fresh) atomicAdd(&s_cnt, fresh);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            c_rowptr[row] = s_cnt;
-            if (s_full || s_cnt > MAX_ROW_NNZ) atomicExch(overflow, 1);
-        }
-    } else {
-        __syncthreads();
-        if (threadIdx.x == 0 && s_full) atomicExch(overflow, 1);
-        const int base = c_rowptr[row];
-        for (int t = threadIdx.x; t < ts; t += blockDim.x) {
-            const int key = keys[t];
-            if (key != -1) {
-                const int pos = atomicAdd(&s_cnt, 1);
-                c_col[base + pos] = key;
-                c_val[base + pos] = vals[t];
-            }
-        }
+    fresh = warp_sum(fresh);
+    if (lane == 0 && fresh) atomicAdd(&s_cnt, fresh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        c_rowptr[row] = s_cnt;
+        if (s_full || s_cnt > MAX_ROW_NNZ) atomicExch(overflow, 1);
     }
 }
 
@@ -196,16 +149,12 @@ static int build_bins(int m, const int *ub, const int *c_rowptr, int symbolic, i
     return partition_rows_by_bin(m, ids.as<int>(), rows, bins, s);
 }
 
-template <typename T, bool NUMERIC>
-static int launch_cta(int nrows, const int *rows, int ts, int threads, const int *a_rowptr, const int *a_col,
-                      const T *a_val, const int *b_rowptr, const int *b_col, const T *b_val, int *c_rowptr,
-                      int *c_col, T *c_val, int *overflow, cudaStream_t s) {
+static int launch_symbolic_cta(int nrows, const int *rows, int ts, int threads, const int *a_rowptr, const int *a_col,
+                               const int *b_rowptr, const int *b_col, int *c_rowptr, int *overflow, cudaStream_t s) {
     if (nrows <= 0) return MLAMG_OK;
-    const size_t smem = (size_t)ts * sizeof(int) + (NUMERIC ? (size_t)ts * sizeof(T) : 0);
-    auto kern = spgemm_cta_kernel<T, NUMERIC>;
-    MLAMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<nrows, threads, smem, s>>>(nrows, rows, ts, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val, c_rowptr,
-                                      c_col, c_val, overflow);
+    const size_t smem = (size_t)ts * sizeof(int);
+    MLAMG_CUDA(cudaFuncSetAttribute(spgemm_symbolic_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spgemm_symbolic_cta_kernel<<<nrows, threads, smem, s>>>(nrows, rows, ts, a_rowptr, a_col, b_rowptr, b_col, c_rowptr, overflow);
     MLAMG_LAUNCHED();
     return MLAMG_OK;
 }
@@ -230,16 +179,14 @@ static int spgemm_symbolic_impl(int m, int k, int n, const int *a_rowptr, const 
     MLAMG_TRY(build_bins(m, ubs.as<int>(), nullptr, 1, rows.as<int>(), &bins, s));
     const int *rl = rows.as<int>();
     if (bins.counts[0] > 0) {
-        spgemm_warp_kernel<float, false><<<cdiv(bins.counts[0], WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, s>>>(
-            bins.counts[0], rl + bins.offsets[0], a_rowptr, a_col, nullptr, b_rowptr, b_col, nullptr, c_rowptr,
-            nullptr, nullptr);
+        spgemm_symbolic_warp_kernel<<<cdiv(bins.counts[0], WARPS_PER_CTA), 32 * WARPS_PER_CTA, 0, s>>>(
+            bins.counts[0], rl + bins.offsets[0], a_rowptr, a_col, b_rowptr, b_col, c_rowptr);
         MLAMG_LAUNCHED();
     }
-    MLAMG_TRY((launch_cta<float, false>(bins.counts[1], rl + bins.offsets[1], 4096, 256, a_rowptr, a_col, nullptr,
-                                        b_rowptr, b_col, nullptr, c_rowptr, nullptr, nullptr, ovf.as<int>(), s)));
-    MLAMG_TRY((launch_cta<float, false>(bins.counts[2], rl + bins.offsets[2], SYM_BIG_TS, 512, a_rowptr, a_col,
-                                        nullptr, b_rowptr, b_col, nullptr, c_rowptr, nullptr, nullptr,
-                                        ovf.as<int>(), s)));
+    MLAMG_TRY(launch_symbolic_cta(bins.counts[1], rl + bins.offsets[1], 4096, 256, a_rowptr, a_col, b_rowptr, b_col, c_rowptr,
+                                  ovf.as<int>(), s));
+    MLAMG_TRY(launch_symbolic_cta(bins.counts[2], rl + bins.offsets[2], SYM_BIG_TS, 512, a_rowptr, a_col, b_rowptr, b_col,
+                                  c_rowptr, ovf.as<int>(), s));
     MLAMG_TRY(exclusive_scan_i32(c_rowptr, c_rowptr, m, s));
     int h_ovf = 0, h_nnz = 0;
     MLAMG_CUDA(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -63,7 +63,17 @@ def jacobi_torch(A, b, x, Dinv=None, omega=0.666, nu=2):
 
 
 def gauss_seidel(A, b, x, L=None, U=None, nu=2):
-    """x <- L^-1 (b - U x), nu times (forward Gauss-Seidel); returns the new iterate."""
+    """x <- L^-1 (b - U x), nu times (forward Gauss-Seidel); returns the new iterate (reference :58-90).
+    L (lower triangle incl. the diagonal) and U (strict upper triangle) default to the halves of A, as in the
+    reference; when the caller supplies them the sweep runs on L + U, which is the same update."""
+    if L is not None or U is not None:
+        A = sp.csr_matrix(A)
+        Lm = sp.tril(A).tocsr() if L is None else sp.csr_matrix(L)
+        Um = sp.triu(A, k=1).tocsr() if U is None else sp.csr_matrix(U)
+        if sp.triu(Lm, k=1).nnz or sp.tril(Um, k=0).nnz:
+            raise ValueError('gauss_seidel: L must be lower triangular and U strictly upper triangular')
+        A = (Lm + Um).tocsr()
+        A.sort_indices()
     Ad = core.DeviceCSR.wrap(A)
     sched = core.GaussSeidelSchedule(Ad)
     bd = core.as_vec(np.asarray(b), Ad.dtype)
@@ -163,8 +173,12 @@ def amg_2_v(A, P, b, x,
             error_tol=None,
             max_iter=500,
             singular=False,
-            smoother='gauss_seidel'):
+            smoother='gauss_seidel',
+            _state=None):
     """Two-level AMG solver -> (x, conv_factor, err, num_iterations)  (reference :111-210).
+
+    _state: optional dict owned by a caller that solves many times on the SAME A (the GA fitness loop, population x
+    grids): the device copy of A and the Gauss-Seidel schedule are built on the first call and reused afterwards.
 
     Tolerances are absolute; err[i] = ||b - A x||_2 if res_tol is set else ||x||_2; a singular
     coarse operator returns (x, 1.0, err, 0) without raising, as the reference does.
@@ -174,6 +188,10 @@ def amg_2_v(A, P, b, x,
         raise RuntimeError('One of res_tol or error_tol must be set!')
     tol = res_tol if res_tol is not None else error_tol
     err = np.zeros(max_iter)
+    if _state is not None:
+        if 'A' not in _state:
+            _state['A'] = core.DeviceCSR.wrap(A)
+        A = _state['A']
     try:
         tl = _TwoLevel(A, P, singular=singular)
     except SingularCoarseError:
@@ -195,7 +213,12 @@ def amg_2_v(A, P, b, x,
     else:
         tmp = torch.empty_like(xd)
         if smoother == 'gauss_seidel':
-            sched = core.GaussSeidelSchedule(Ad)
+            if _state is not None:
+                if 'gs' not in _state:
+                    _state['gs'] = core.GaussSeidelSchedule(Ad)
+                sched = _state['gs']
+            else:
+                sched = core.GaussSeidelSchedule(Ad)
         else:
             dw = core.smoother_diag(Ad, smoother, jacobi_weight)
 
@@ -262,5 +285,7 @@ def amg_2_v_torch(A, P, b, x,
         err[i] = float(np.sqrt(core.dot(xd, xd)))
         if err[i] < error_tol:
             break
+    # the reference's jacobi_torch / `x +=` update the caller's tensor in place (:48-55, :234): keep that side effect
+    x.copy_(xd.to(device=x.device, dtype=x.dtype))
     n_err = 3
     return ((err[i] / err[i - n_err]) ** (1 / (n_err - 1))).to(device)

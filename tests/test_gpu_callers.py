@@ -73,3 +73,40 @@ def test_evaluate_dataset_with_a_model_tail():
     conv = common.evaluate_dataset(None, grids, model=Model(), alpha=0.15)
     assert 0.0 < conv[0] <= 1.0
     assert common.evaluate_dataset(None, grids, model=Broken(), alpha=0.15)[0] == 1.0
+
+
+def _train_dataset():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "ml-amg_b200"))
+    spec = importlib.util.spec_from_file_location("mlamg_utils_train_dataset", os.path.join(ROOT, "ml-amg_b200", "utils", "train_dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_population_evaluation_reuses_grid_state_and_matches_per_call_results():
+    """utils/train_dataset.py:81-138: the GA fitness loop, population x grids.  The grid-major batched evaluation
+    (operator uploaded and Gauss-Seidel schedule built once per grid) gives the same convergence factors as
+    independent evaluate_dataset calls, and those match the oracle's two-grid solver on the same P."""
+    import ns.lib.sparse_tensor as nst
+    td = _train_dataset()
+    grids = [_G(sp.csr_matrix(oml.poisson((16, 14)))), _G(sp.csr_matrix(oml.poisson((9, 8, 7))))]
+    model = td.StandInModel()
+    population = [np.full(5, 0.1 * (i + 1)) for i in range(3)]
+    conv = td.evaluate_population(population, grids, model, alpha=0.2)
+    assert conv.shape == (3, 2) and np.all(conv > 0) and np.all(conv <= 1.0)
+    for i, w in enumerate(population):
+        single = td.evaluate_dataset(w, grids, model, alpha=0.2)
+        assert np.array_equal(single, conv[i])
+        # against the oracle: same P (the model is deterministic given the weights), reference two-grid loop
+        model.load_flat_weights(w)
+        for g, grid in enumerate(grids):
+            P = nst.to_scipy(model.forward(grid.A, 0.2)[1]).astype(np.float64)
+            x = np.random.RandomState(0).randn(grid.A.shape[1])
+            x /= la.norm(x, 2)
+            ref = rp.amg_2_v(grid.A, P, np.zeros(grid.A.shape[1]), x, error_tol=1e-6)[1]
+            assert abs(conv[i, g] - ref) < 1e-8, (i, g, conv[i, g], ref)
+    f = td.fitness(3, population[0], grids, model, alpha=0.2)
+    assert abs(f - 1.0 / conv[0].mean()) < 1e-12
+    f_rel = td.fitness(3, population[0], grids, model, benchmark=np.array([0.5, 0.25]), alpha=0.2)
+    assert abs(f_rel - 1.0 / np.mean(conv[0] / np.array([0.5, 0.25]))) < 1e-12

@@ -239,7 +239,9 @@ def test_amg_loss_forward_and_torch_twins():
     n = A.shape[0]
     x0 = np.random.RandomState(0).randn(n).astype(np.float32)
     x0 /= np.linalg.norm(x0)
-    cf = mg.amg_2_v_torch(A_T, P_T, torch.zeros(n), torch.from_numpy(x0), jacobi_weight=2 / 3)
+    xt = torch.from_numpy(x0.copy())
+    cf = mg.amg_2_v_torch(A_T, P_T, torch.zeros(n), xt, jacobi_weight=2 / 3)
+    assert not np.array_equal(xt.numpy(), x0)            # the caller's iterate is updated in place, as in the reference
     ref = rp.amg_2_v_torch_like(A.astype(np.float32), P.astype(np.float32), np.zeros(n, dtype=np.float32), x0, jacobi_weight=2 / 3)
     assert abs(float(cf) - float(ref)) <= 1e-3 * abs(float(ref))
     assert nsp.torch_to_scipy(A_T).shape == A.shape

@@ -415,3 +415,26 @@ def test_prolong_smooth_equals_prolong_then_sweep(dtype):
     xp = x0.astype(np.float64) + P64 @ e.astype(np.float64)
     ref0 = xp + dw.astype(np.float64) * (b64 - A64 @ xp)
     close(z, ref0, dtype, np.abs(ref0).max() * 10)
+
+
+def test_gauss_seidel_mirror_honours_L_and_U():
+    """ns.lib.multigrid.gauss_seidel with caller-supplied triangles (reference :83-90): x <- L^-1 (b - U x)"""
+    import scipy.sparse.linalg as spla
+    import ns.lib.multigrid as mg
+    A = sp.csr_matrix(oml.poisson((9, 7)))
+    rs = np.random.RandomState(0)
+    b, x = rs.randn(A.shape[0]), rs.randn(A.shape[0])
+    L = (sp.tril(A) * 1.5).tocsr()            # NOT the halves of A: the supplied matrices must be the ones used
+    U = (sp.triu(A, k=1) * 0.5).tocsr()
+    ref = x.copy()
+    for _ in range(2):
+        ref = spla.spsolve_triangular(L, b - U @ ref)
+    got = mg.gauss_seidel(A, b, x.copy(), L=L, U=U, nu=2)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    got0 = mg.gauss_seidel(A, b, x.copy(), nu=2)
+    ref0 = x.copy()
+    for _ in range(2):
+        ref0 = spla.spsolve_triangular(sp.tril(A).tocsr(), b - sp.triu(A, k=1) @ ref0)
+    assert np.abs(got0 - ref0).max() <= 1e-13 * np.abs(ref0).max()
+    with pytest.raises(ValueError):
+        mg.gauss_seidel(A, b, x.copy(), L=A, nu=1)
