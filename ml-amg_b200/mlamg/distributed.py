@@ -234,6 +234,9 @@ PEER_INPLACE = _os.environ.get("MLAMG_PEER_INPLACE", "1") == "1"
 # 2: boundary rows on a second, normal-priority side stream enqueued behind the interior launch (they then run in the
 # interior kernel's tail wave, when the halo has long arrived, instead of spinning on SM slots at the start)
 PEER_BOUNDARY_SIDE = int(_os.environ.get("MLAMG_PEER_BOUNDARY_SIDE", "1"))
+# 1: when everything an operator sends is written by the boundary rows of the operator before it (residual -> restriction),
+# its push is issued right behind that boundary kernel on the side stream instead of after the previous operator's join
+EARLY_PUSH = _os.environ.get("MLAMG_EARLY_PUSH", "1") == "1"
 _ALIGN = 256
 
 
@@ -557,7 +560,8 @@ class DistOperator:
         """(name, send list, per-rank counts, dtype) of the halo exchange of this operator's input"""
         return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype)
 
-    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None, aux=None):
+    def apply(self, op, x_ext, y, b=None, dw=None, overlap=True, comm_stream=None, chan=None, aux=None, after_boundary=None,
+              prepushed=False):
         """halo exchange of x_ext, then the row-op; with overlap the interior rows run during the exchange.
         chan: peer-memory channel (push -> interior rows -> boundary rows reading the halo in place from the
         receive region; one stream, no collective); None: NCCL all-to-all on a side stream.
@@ -565,7 +569,11 @@ class DistOperator:
         dw.*b (4) or b (6) directly.
         op 8 (y = b - (A D_w) b on the scaled copy, x never materialised): x_ext is ignored.
         op 5 (y = aux + dw.*b + A x_ext): aux = iterate before the correction, b = residual, x_ext = coarse correction.
-        op 7 (y = dw.*(aux + b) + A x_ext): aux = right-hand side, b = residual of dw.*rhs."""
+        op 7 (y = dw.*(aux + b) + A x_ext): aux = right-hand side, b = residual of dw.*rhs.
+        after_boundary: callable run on the side stream right behind the boundary-row kernel (the NEXT operator's push
+        when everything it sends is produced by these boundary rows: its halo then travels while the interior rows
+        of THIS operator are still running); returns True when it was run.  prepushed: this operator's push has
+        already been issued that way."""
         plan = self.plan
         xin = None if op in (4, 6) else x_ext      # gather vector (ops 4/6 gather b instead)
         if op in (4, 6):
@@ -583,20 +591,29 @@ class DistOperator:
             main = torch.cuda.current_stream()
             if fork:                   # the 4 us push kernel runs beside the interior rows instead of in front of them
                 comm_stream.wait_stream(main)
-            with torch.cuda.stream(comm_stream if fork else main):
-                if op == 4:
-                    chan.push(b, scale=dw)
-                elif op in (6, 8):
-                    chan.push(b)
-                else:
-                    chan.push(x_ext)
+            if not prepushed:
+                with torch.cuda.stream(comm_stream if fork else main):
+                    if op == 4:
+                        chan.push(b, scale=dw)
+                    elif op in (6, 8):
+                        chan.push(b)
+                    else:
+                        chan.push(x_ext)
+            elif not fork:             # pushed early on the side stream, but this operator runs unsplit on the main stream
+                main.wait_stream(comm_stream)
+            # (prepushed and fork: the wait above orders this operator's boundary kernel behind the whole previous
+            # operator — its rows gather values the previous interior kernel wrote — while the push itself left earlier)
             A = self._csr_for(op)
             xk = b if op == 8 else xin
             rows = self.boundary if split else None
             side = PEER_BOUNDARY_SIDE if (fork and (PEER_INPLACE or op in (4, 6, 8))) else 0
+            ran_after = False
             if side == 1:              # boundary rows right behind the push on the side stream, beside the interior rows
                 with torch.cuda.stream(comm_stream):
                     chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
+                    if after_boundary is not None:
+                        after_boundary()
+                        ran_after = True
             if split:
                 core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
                            rows=None if self.interior_range is not None else self.interior)
@@ -609,7 +626,7 @@ class DistOperator:
             if fork:
                 main.wait_stream(comm_stream)
             if side:
-                return
+                return ran_after
             if PEER_INPLACE or op in (4, 6, 8):
                 chan.rowop(A, kop, xk, n_own, y, b=b, dw=dw, rows=rows, aux=aux)
             else:
@@ -725,6 +742,9 @@ class DistHierarchy:
             for L in self.levels:
                 L.A.build_scaled(L.dw)
         T_.lap("scaled_copy")
+        for L in self.levels:      # restriction sends only entries of r that the boundary rows of the residual write?
+            si, bd = L.R.plan.send_idx.long(), L.A.boundary.long()
+            L.early_R = bool(si.numel() == 0 or (bd.numel() > 0 and bool(torch.isin(si, bd).all())))
         self._alloc()
         T_.lap("alloc")
 
@@ -976,10 +996,17 @@ class DistHierarchy:
             fused = nu1 == 1 and (chans is not None or comm.world == 1) and (scaled or L.A.csr.nnz <= 12 * n)
             # with Q on the way up x = dw.*b is never materialised: r = b - (A D_w) b, then x1 = dw.*(b + r) + Q e
             L.lazy = fused and scaled and L.Q is not None and nu2 > 0
+            # the restriction's halo (entries of r its neighbours gather) is produced by the boundary rows of the residual:
+            # its push is chained right behind that boundary kernel, one interior kernel earlier than the restriction
+            early = None
+            if chans is not None and EARLY_PUSH and getattr(L, "early_R", False):
+                early = (lambda _c=ch(l, "R"), _r=L.r: _c.push(_r))
+            r_pushed = False
             if L.lazy:
-                L.A.apply(8, None, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
+                r_pushed = L.A.apply(8, None, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"), after_boundary=early)
             elif fused:    # x = dw.*b and r = b - A x in one pass over A (x is never read back)
-                L.A.apply(6 if scaled else 4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))
+                r_pushed = L.A.apply(6 if scaled else 4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs,
+                                     chan=ch(l, "res"), after_boundary=early)
             elif nu1 > 0:
                 core.jacobi_zero(L.dw, rhs, c[:n])
             else:
@@ -989,11 +1016,12 @@ class DistHierarchy:
                 L.A.apply(3, c, o, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "pre", k))
                 c = o
             if not fused:
-                L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"))   # r[:n] = b - A x
+                r_pushed = L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"),
+                                     after_boundary=early)   # r[:n] = b - A x
             nxt_b = self.levels[l + 1].b if l + 1 < len(self.levels) else None
             if nxt_b is None:
                 nxt_b = self._tail_local_b()
-            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs, chan=ch(l, "R"))        # b_c = R r
+            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs, chan=ch(l, "R"), prepushed=bool(r_pushed))   # b_c = R r
             cur.append(c)
             rhs = nxt_b
         # replicated tail: gather the restricted residual, every rank solves, keep my slice

@@ -60,6 +60,12 @@ def main():
             res[key] = timed(replay)
             H._graph = None
         md.PEER_BOUNDARY_SIDE = 1
+        md.EARLY_PUSH = False
+        replay = H.capture(b, x, 1, 1)
+        res["ms_boundary_side_no_early_push"] = timed(replay)
+        H._graph = None
+        md.EARLY_PUSH = True
+        res["early_R_push_levels"] = [bool(getattr(L, "early_R", False)) for L in H.levels]
         H.check_exchange()
         if rank == 0:
             print(json.dumps(res), flush=True)
