@@ -742,9 +742,17 @@ class DistHierarchy:
             for L in self.levels:
                 L.A.build_scaled(L.dw)
         T_.lap("scaled_copy")
-        for L in self.levels:      # restriction sends only entries of r that the boundary rows of the residual write?
-            si, bd = L.R.plan.send_idx.long(), L.A.boundary.long()
-            L.early_R = bool(si.numel() == 0 or (bd.numel() > 0 and bool(torch.isin(si, bd).all())))
+        def _subset(send_idx, rows):      # is everything that is sent written by these (boundary) rows?
+            si, bd = send_idx.long(), rows.long()
+            return bool(si.numel() == 0 or (bd.numel() > 0 and bool(torch.isin(si, bd).all())))
+        for l, L in enumerate(self.levels):
+            L.early_R = _subset(L.R.plan.send_idx, L.A.boundary)                  # residual -> restriction
+            L.early_next_res = l + 1 < len(self.levels) and _subset(self.levels[l + 1].A.plan.send_idx, L.R.boundary)
+            if l > 0:                                                            # last pass of level l -> prolongation of l-1
+                Lf = self.levels[l - 1]
+                up = (Lf.Q if Lf.Q is not None else Lf.P).plan.send_idx
+                L.early_up_Q = L.Q is not None and _subset(up, L.Q.boundary)
+                L.early_up_A = _subset(up, L.A.boundary)
         self._alloc()
         T_.lap("alloc")
 
@@ -980,33 +988,45 @@ class DistHierarchy:
             cs.close()
         self._chansets = {}
 
+    def _first_op(self, l, nu1, nu2, chans):
+        """(fused, scaled, lazy) of level l's first pass — does it push the right-hand side itself?"""
+        L = self.levels[l]
+        scaled = self.fuse_pre and hasattr(L.A, "csr_scaled")
+        fused = nu1 == 1 and (chans is not None or self.comm.world == 1) and (scaled or L.A.csr.nnz <= 12 * L.n)
+        lazy = fused and scaled and L.Q is not None and nu2 > 0
+        return fused, scaled, lazy
+
     def vcycle(self, b, x_out, nu1=1, nu2=1):
-        """x_out = V(nu1,nu2)(b) from a zero guess (preconditioner apply).  b, x_out: local slices."""
+        """x_out = V(nu1,nu2)(b) from a zero guess (preconditioner apply).  b, x_out: local slices.
+
+        Early pushes (peer transport): when everything an operator sends to its neighbours is written by the BOUNDARY rows
+        of the operator before it (checked once at setup: residual -> restriction, restriction -> the next level's first
+        pass, a level's last pass -> the finer level's prolongation), its push is issued on the side stream right behind
+        that boundary kernel; the halo then travels while the previous operator's interior rows are still running."""
         comm = self.comm
         cs = self.comm_stream if self.overlap else None
         chans = self._channels(nu1, nu2)
         ch = (lambda *key: chans[key]) if chans is not None else (lambda *key: None)
+        early_ok = chans is not None and EARLY_PUSH
         rhs = b
         cur = []
+        nl = len(self.levels)
+        rhs_pushed = False
         for l, L in enumerate(self.levels):
             xa, xb = L.x
             n = L.n
             c = xa
-            scaled = self.fuse_pre and hasattr(L.A, "csr_scaled")
-            fused = nu1 == 1 and (chans is not None or comm.world == 1) and (scaled or L.A.csr.nnz <= 12 * n)
-            # with Q on the way up x = dw.*b is never materialised: r = b - (A D_w) b, then x1 = dw.*(b + r) + Q e
-            L.lazy = fused and scaled and L.Q is not None and nu2 > 0
-            # the restriction's halo (entries of r its neighbours gather) is produced by the boundary rows of the residual:
-            # its push is chained right behind that boundary kernel, one interior kernel earlier than the restriction
+            fused, scaled, L.lazy = self._first_op(l, nu1, nu2, chans)
             early = None
-            if chans is not None and EARLY_PUSH and getattr(L, "early_R", False):
+            if early_ok and getattr(L, "early_R", False):
                 early = (lambda _c=ch(l, "R"), _r=L.r: _c.push(_r))
             r_pushed = False
-            if L.lazy:
-                r_pushed = L.A.apply(8, None, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"), after_boundary=early)
+            if L.lazy:     # x = dw.*b is never materialised: r = b - (A D_w) b, then x1 = dw.*(b + r) + Q e on the way up
+                r_pushed = L.A.apply(8, None, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"),
+                                     after_boundary=early, prepushed=rhs_pushed)
             elif fused:    # x = dw.*b and r = b - A x in one pass over A (x is never read back)
                 r_pushed = L.A.apply(6 if scaled else 4, c, L.r, b=rhs, dw=L.dw, overlap=self.overlap, comm_stream=cs,
-                                     chan=ch(l, "res"), after_boundary=early)
+                                     chan=ch(l, "res"), after_boundary=early, prepushed=rhs_pushed)
             elif nu1 > 0:
                 core.jacobi_zero(L.dw, rhs, c[:n])
             else:
@@ -1018,15 +1038,22 @@ class DistHierarchy:
             if not fused:
                 r_pushed = L.A.apply(2, c, L.r, b=rhs, overlap=self.overlap, comm_stream=cs, chan=ch(l, "res"),
                                      after_boundary=early)   # r[:n] = b - A x
-            nxt_b = self.levels[l + 1].b if l + 1 < len(self.levels) else None
+            nxt_b = self.levels[l + 1].b if l + 1 < nl else None
+            early_b = None
             if nxt_b is None:
                 nxt_b = self._tail_local_b()
-            L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs, chan=ch(l, "R"), prepushed=bool(r_pushed))   # b_c = R r
+            elif early_ok and getattr(L, "early_next_res", False):
+                f_n, s_n, _ = self._first_op(l + 1, nu1, nu2, chans)
+                if f_n:        # the next level's first pass pushes its right-hand side (scaled by dw on the unscaled fused op)
+                    Ln = self.levels[l + 1]
+                    early_b = (lambda _c=ch(l + 1, "res"), _b=nxt_b, _s=(None if s_n else Ln.dw): _c.push(_b, scale=_s))
+            rhs_pushed = bool(L.R.apply(0, L.r, nxt_b, overlap=self.overlap, comm_stream=cs, chan=ch(l, "R"),
+                                        prepushed=bool(r_pushed), after_boundary=early_b))   # b_c = R r
             cur.append(c)
             rhs = nxt_b
         # replicated tail: gather the restricted residual, every rank solves, keep my slice
         xc = self._tail_solve(rhs, nu1, nu2, chans["tail"] if chans is not None else None)
-        nl = len(self.levels)
+        e_pushed = False
         for l in range(nl - 1, -1, -1):
             L = self.levels[l]
             xa, xb = L.x
@@ -1034,25 +1061,45 @@ class DistHierarchy:
             c = cur[l]
             if xc is not None:                       # coarse correction not yet in L.e (tail, or a level without post-smoothing)
                 L.e[:L.nc].copy_(xc)
+                e_pushed = False
             rhs_l = b if l == 0 else self.levels[l].b
             # the last sweep writes straight into its consumer: the caller's vector (level 0) or the finer level's
             # coarse-correction buffer — no copy on the way up
             target = x_out if l == 0 else self.levels[l - 1].e
+
+            def early_up(last_is_q):
+                """push of the finer level's prolongation channel, chained behind this level's last boundary kernel"""
+                if not early_ok or l == 0 or nu2 == 0:
+                    return None
+                Lf = self.levels[l - 1]
+                if not getattr(L, "early_up_Q" if last_is_q else "early_up_A", False):
+                    return None
+                return (lambda _c=ch(l - 1, "P"), _e=Lf.e: _c.push(_e))
             k0 = 0
+            this_pushed, e_pushed = e_pushed, False
             if L.Q is not None and nu2 > 0:
                 # x + P e followed by one sweep == x + dw.*r + Q e (r is still in L.r): one pass over Q
                 o = target if nu2 == 1 else (xb if c is xa else xa)
+                ab = early_up(True) if nu2 == 1 else None
                 if L.lazy:
-                    L.Q.apply(7, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=rhs_l)
+                    ran = L.Q.apply(7, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=rhs_l,
+                                    prepushed=this_pushed, after_boundary=ab)
                 else:
-                    L.Q.apply(5, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=c)
+                    ran = L.Q.apply(5, L.e, o, b=L.r, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), aux=c,
+                                    prepushed=this_pushed, after_boundary=ab)
+                if nu2 == 1:
+                    e_pushed = bool(ran)
                 c = o
                 k0 = 1
             else:
-                L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"))        # x += P e
+                L.P.apply(1, L.e, c, overlap=self.overlap, comm_stream=cs, chan=ch(l, "P"), prepushed=this_pushed)   # x += P e
             for k in range(k0, nu2):
-                o = target if k == nu2 - 1 else (xb if c is xa else xa)
-                L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "post", k))
+                last = k == nu2 - 1
+                o = target if last else (xb if c is xa else xa)
+                ran = L.A.apply(3, c, o, b=rhs_l, dw=L.dw, overlap=self.overlap, comm_stream=cs, chan=ch(l, "post", k),
+                                after_boundary=early_up(False) if last else None)
+                if last:
+                    e_pushed = bool(ran)
                 c = o
             xc = None if nu2 > 0 else c[:n]
         if xc is not None:

@@ -65,7 +65,8 @@ def main():
         res["ms_boundary_side_no_early_push"] = timed(replay)
         H._graph = None
         md.EARLY_PUSH = True
-        res["early_R_push_levels"] = [bool(getattr(L, "early_R", False)) for L in H.levels]
+        res["early_push_flags"] = [{k: bool(getattr(L, k, False)) for k in ("early_R", "early_next_res", "early_up_Q", "early_up_A")}
+                                   for L in H.levels]
         H.check_exchange()
         if rank == 0:
             print(json.dumps(res), flush=True)
