@@ -293,6 +293,20 @@ int mlamg_solve_ex(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2
 int mlamg_pcg(mlamg_hierarchy_t h, const void *b, void *x, int nu1, int nu2, double rtol, int maxiter,
               double *res_host, int *niter_host, mlamg_stream_t stream);
 int mlamg_solver_loop_mode(mlamg_hierarchy_t h);
+/* Device-resident PCG pieces for ROW-PARTITIONED operators (one process per GPU).  `state` is mlamg_dloop_state_bytes()
+ * of device memory laid out as 10 doubles (fields 0 rz, 1 pap, 2 rr, 3 bb, 4 stop, 5 alpha, 6 beta, 7 tol, 8 tmp0, 9 tmp1)
+ * followed by 4 ints (it, done, maxiter, first).  mlamg_dloop_dot leaves the LOCAL x.y in a field; the caller all-reduces
+ * that field in place (e.g. ncclAllReduce on the device tensor — no host synchronisation) and calls mlamg_dloop_scalar:
+ * which = 0 start (fields tmp0 = b.b and rr = r.r reduced): stop, res[0], done; 1 beta (tmp0 = r.z reduced);
+ * 2 alpha (pap reduced); 3 check (rr reduced): it, res[it], done.  direction: p = z + beta p; update: x += alpha p,
+ * r -= alpha Ap and the local r.r into field rr.  Every piece returns at once when `done` is set. */
+int mlamg_dloop_state_bytes(void);
+int mlamg_dloop_init(void *state, double tol, int maxiter, mlamg_stream_t stream);
+int mlamg_dloop_dot(int dtype, int n, const void *x, const void *y, void *state, int field, mlamg_stream_t stream);
+int mlamg_dloop_scalar(void *state, int which, double *res_dev, mlamg_stream_t stream);
+int mlamg_dloop_direction(int dtype, int n, const void *z, void *p, const void *state, mlamg_stream_t stream);
+int mlamg_dloop_update(int dtype, int n, const void *p, const void *ap, void *x, void *r, void *state,
+                       mlamg_stream_t stream);
 /* One Krylov step of the Arnoldi process of GMRES (the `accel='gmres'` of PyAMG.py:119) in ONE call and one host
  * synchronisation: modified Gram-Schmidt of w against the j+1 basis vectors V[0..j] (contiguous, stride n):
  * h[i] = w.V_i, w -= h[i] V_i in sequence; h[j+1] = ||w||_2; v_next (may be NULL) = w / h[j+1] unless the norm is 0.

@@ -22,9 +22,10 @@ constexpr int SOL_MAX_BLOCKS = 148 * 8;
 constexpr int LOOKAHEAD = 2;
 
 struct LoopState {
-    double rz, pap, rr, bb, stop, alpha, beta, tol;
+    double rz, pap, rr, bb, stop, alpha, beta, tol, tmp0, tmp1;      // fields 0..9 (the mlamg_dloop_* calls address them by index)
     int it, done, maxiter, first;
 };
+static_assert(sizeof(LoopState) == 96, "LoopState layout is part of the mlamg_dloop_* contract");
 
 struct LoopGraph {
     cudaGraphExec_t exec = nullptr;
@@ -477,6 +478,71 @@ __global__ void __launch_bounds__(SOL_THREADS) mgs_scale_kernel(int n, const T *
         out[i] = (T)((double)w[i] * inv);
 }
 
+// ------------------------------------------------------------------------------------------------ distributed loop pieces
+// The same device-resident PCG for ROW-PARTITIONED operators (mlamg/distributed.py): every rank keeps a LoopState in its
+// HBM; the local dot products land in a field of the state, the caller all-reduces that field in place (NCCL on the
+// device tensor, no host synchronisation) and the scalar kernels below advance the state identically on every rank.
+__global__ void dloop_init_kernel(LoopState *st, double tol, int maxiter) {
+    LoopState z = {};
+    z.tol = tol;
+    z.maxiter = maxiter;
+    z.first = 1;
+    *st = z;
+}
+
+// which: 0 start (tmp0 = b.b, rr = r.r all-reduced): stop, res[0], done | 1 beta (tmp0 = r.z all-reduced)
+//        2 alpha (pap all-reduced) | 3 check (rr all-reduced): it, res[it], done
+__global__ void dloop_scalar_kernel(LoopState *st, int which, double *__restrict__ res) {
+    if (which == 0) {
+        const double nb = sqrt(st->tmp0);
+        st->bb = st->tmp0;
+        st->stop = st->tol * (nb != 0.0 ? nb : 1.0);
+        st->it = 0;
+        st->first = 1;
+        res[0] = sqrt(st->rr);
+        st->done = (res[0] <= st->stop) || st->maxiter <= 0;
+        return;
+    }
+    if (st->done) return;
+    if (which == 1) {
+        st->beta = st->first ? 0.0 : st->tmp0 / st->rz;
+        st->rz = st->tmp0;
+        st->first = 0;
+    } else if (which == 2) {
+        st->alpha = st->rz / st->pap;
+    } else {
+        const int it = st->it + 1;
+        st->it = it;
+        res[it] = sqrt(st->rr);
+        st->done = (res[it] <= st->stop) || it >= st->maxiter;
+    }
+}
+
+template <typename T>
+static int dloop_dot_t(int n, const T *x, const T *y, LoopState *st, int field, cudaStream_t s) {
+    const unsigned vb = vec_blocks(n);
+    Scratch part((size_t)vb * sizeof(double), s);
+    MLAMG_SCRATCH_OK(part);
+    sol_dot_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, x, y, nullptr, part.as<double>());
+    MLAMG_LAUNCHED();
+    mgs_reduce_kernel<<<1, 1024, 0, s>>>(part.as<double>(), (int)vb, reinterpret_cast<double *>(st) + field, 0);
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+template <typename T>
+static int dloop_update_t(int n, const T *p, const T *ap, T *x, T *r, LoopState *st, cudaStream_t s) {
+    const unsigned vb = vec_blocks(n);
+    Scratch part((size_t)vb * sizeof(double), s);
+    MLAMG_SCRATCH_OK(part);
+    MLAMG_CUDA(cudaMemsetAsync(part.p, 0, (size_t)vb * sizeof(double), s));      // a finished loop leaves the partials untouched
+    pcg_update_kernel<T><<<vb, SOL_THREADS, 0, s>>>(n, p, ap, x, r, st, part.as<double>());
+    MLAMG_LAUNCHED();
+    mgs_reduce_kernel<<<1, 1024, 0, s>>>(part.as<double>(), (int)vb, &st->rr, 0);
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
 template <typename T>
 static int gmres_orthogonalize_t(int n, int j, const T *V, T *w, T *v_next, double *h_host, cudaStream_t s) {
     const unsigned vb = vec_blocks(n);
@@ -546,6 +612,42 @@ int mlamg_gmres_orthogonalize(int dtype, int n, int j, const void *V, void *w, v
                               mlamg_stream_t stream) {
     if (n <= 0 || j < 0 || !V || !w || !h_host) return set_error(MLAMG_EINVAL, "gmres_orthogonalize: bad arguments");
     MLAMG_DISPATCH(dtype, return gmres_orthogonalize_t<T>(n, j, (const T *)V, (T *)w, (T *)v_next, h_host, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_dloop_state_bytes(void) { return (int)sizeof(LoopState); }
+
+int mlamg_dloop_init(void *state, double tol, int maxiter, mlamg_stream_t stream) {
+    if (!state || maxiter < 0) return set_error(MLAMG_EINVAL, "dloop_init: bad arguments");
+    dloop_init_kernel<<<1, 1, 0, as_stream(stream)>>>((LoopState *)state, tol, maxiter);
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_dloop_dot(int dtype, int n, const void *x, const void *y, void *state, int field, mlamg_stream_t stream) {
+    if (!state || field < 0 || field > 9 || n < 0) return set_error(MLAMG_EINVAL, "dloop_dot: bad arguments");
+    MLAMG_DISPATCH(dtype, return dloop_dot_t<T>(n, (const T *)x, (const T *)y, (LoopState *)state, field, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_dloop_scalar(void *state, int which, double *res_dev, mlamg_stream_t stream) {
+    if (!state || which < 0 || which > 3 || !res_dev) return set_error(MLAMG_EINVAL, "dloop_scalar: bad arguments");
+    dloop_scalar_kernel<<<1, 1, 0, as_stream(stream)>>>((LoopState *)state, which, res_dev);
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_dloop_direction(int dtype, int n, const void *z, void *p, const void *state, mlamg_stream_t stream) {
+    if (!state || n < 0) return set_error(MLAMG_EINVAL, "dloop_direction: bad arguments");
+    MLAMG_DISPATCH(dtype, (pcg_direction_kernel<T><<<vec_blocks(n), SOL_THREADS, 0, as_stream(stream)>>>(n, (const T *)z, (T *)p,
+                                                                                                      (const LoopState *)state)));
+    MLAMG_LAUNCHED();
+    return MLAMG_OK;
+}
+
+int mlamg_dloop_update(int dtype, int n, const void *p, const void *ap, void *x, void *r, void *state, mlamg_stream_t stream) {
+    if (!state || n < 0) return set_error(MLAMG_EINVAL, "dloop_update: bad arguments");
+    MLAMG_DISPATCH(dtype, return dloop_update_t<T>(n, (const T *)p, (const T *)ap, (T *)x, (T *)r, (LoopState *)state, as_stream(stream)));
     return MLAMG_OK;
 }
 

@@ -84,6 +84,12 @@ SIGNATURES = {
     "mlamg_solve_ex": (I, [P, P, P, I, I, I, D, I, P, P, P]),
     "mlamg_pcg": (I, [P, P, P, I, I, D, I, P, P, P]),
     "mlamg_solver_loop_mode": (I, [P]),
+    "mlamg_dloop_state_bytes": (I, []),
+    "mlamg_dloop_init": (I, [P, D, I, P]),
+    "mlamg_dloop_dot": (I, [I, I, P, P, P, I, P]),
+    "mlamg_dloop_scalar": (I, [P, I, P, P]),
+    "mlamg_dloop_direction": (I, [I, I, P, P, P, P]),
+    "mlamg_dloop_update": (I, [I, I, P, P, P, P, P, P]),
     "mlamg_gmres_orthogonalize": (I, [I, I, I, P, P, P, P, P]),
     "mlamg_vcycle_host": (I, [P, P, P, I, I, I, P]),
     "mlamg_peer_alloc": (I, [LL, P, P]),

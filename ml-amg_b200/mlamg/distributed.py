@@ -1159,39 +1159,71 @@ class DistHierarchy:
     def gdot(self, x, y):
         return self.comm.allreduce_sum(core.dot(x, y))
 
-    def pcg(self, b, x0=None, tol=1e-8, maxiter=200, nu1=1, nu2=1):
-        """V-cycle preconditioned CG on the local slices; returns (x, residual history, iterations)."""
+    def pcg(self, b, x0=None, tol=1e-8, maxiter=200, nu1=1, nu2=1, lookahead=2):
+        """V-cycle preconditioned CG on the local slices; returns (x, residual history, iterations).
+
+        Device resident: alpha, beta, the dot products, the iteration counter, the convergence flag and the residual
+        history live in a small state tensor on every rank (csrc/solvers.cu, mlamg_dloop_*).  A local dot product lands
+        in a field of the state, `all_reduce` sums that field in place on the device, one-thread kernels advance the
+        state identically on all ranks — no `.item()` anywhere in the iteration.  The host only polls a pinned copy of
+        the flag `lookahead` iterations behind what it has enqueued (every piece of an iteration that starts after
+        convergence returns at once, so x, r and the history are those of the converged iteration)."""
+        comm = self.comm
         n = b.numel()
+        dtc = core.dt(b)
+        s = core.stream
         x = torch.zeros_like(b) if x0 is None else x0.clone()
-        r = torch.empty_like(b)
-        ap = torch.empty_like(b)
-        z = torch.empty_like(b)
+        r, ap, z, p = torch.empty_like(b), torch.empty_like(b), torch.empty_like(b), torch.zeros_like(b)
+        state = torch.zeros(int(lib.mlamg_dloop_state_bytes()) // 8, dtype=torch.float64, device=b.device)
+        flags = state.view(torch.int32)[20:24]                        # it, done, maxiter, first
+        res_d = torch.zeros(maxiter + 1, dtype=torch.float64, device=b.device)
+        sp, rp = core.ptr(state), core.ptr(res_d)
+
+        def allred(field):
+            if comm.world > 1:
+                dist.all_reduce(state[field:field + 1], group=comm.group)
+
+        def dot_into(u, v, field):
+            check(lib.mlamg_dloop_dot(dtc, n, core.ptr(u), core.ptr(v), sp, field, s()))
+            allred(field)
+
+        check(lib.mlamg_dloop_init(sp, float(tol), int(maxiter), s()))
         self.matvec(x, ap)
         r.copy_(b)
         core.axpby(-1.0, ap, 1.0, r)
-        res = [np.sqrt(self.gdot(r, r))]
-        nb = np.sqrt(self.gdot(b, b))
-        stop = tol * (nb if nb != 0 else 1.0)
-        if res[0] <= stop:
-            return x, np.array(res), 0
-        self.vcycle(r, z, nu1, nu2)
-        p = z.clone()
-        rz = self.gdot(r, z)
-        it = 0
-        for it in range(1, maxiter + 1):
-            self.matvec(p, ap)
-            alpha = rz / self.gdot(p, ap)
-            core.axpby(alpha, p, 1.0, x)
-            core.axpby(-alpha, ap, 1.0, r)
-            res.append(np.sqrt(self.gdot(r, r)))
-            if res[-1] <= stop:
-                break
+        dot_into(b, b, 8)
+        dot_into(r, r, 2)
+        check(lib.mlamg_dloop_scalar(sp, 0, rp, s()))
+        M = lookahead + 1
+        pins = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(M)]
+        evs = [torch.cuda.Event() for _ in range(M)]
+        pins[0].copy_(flags, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        stop = bool(pins[0][1] != 0)
+        k = 0
+        while not stop and k < maxiter:
             self.vcycle(r, z, nu1, nu2)
-            rz_new = self.gdot(r, z)
-            core.axpby(1.0, z, rz_new / rz, p)
-            rz = rz_new
+            dot_into(r, z, 8)
+            check(lib.mlamg_dloop_scalar(sp, 1, rp, s()))
+            check(lib.mlamg_dloop_direction(dtc, n, core.ptr(z), core.ptr(p), sp, s()))
+            self.matvec(p, ap)
+            dot_into(p, ap, 1)
+            check(lib.mlamg_dloop_scalar(sp, 2, rp, s()))
+            check(lib.mlamg_dloop_update(dtc, n, core.ptr(p), core.ptr(ap), core.ptr(x), core.ptr(r), sp, s()))
+            allred(2)
+            check(lib.mlamg_dloop_scalar(sp, 3, rp, s()))
+            pins[k % M].copy_(flags, non_blocking=True)
+            evs[k % M].record()
+            if k >= lookahead:
+                j = (k - lookahead) % M
+                evs[j].synchronize()
+                stop = bool(pins[j][1] != 0)
+            k += 1
+        torch.cuda.current_stream().synchronize()
+        it = int(flags[0].item())
+        res = res_d[:it + 1].cpu().numpy()
         self.check_exchange()          # a halo wait that timed out returned stale values: never hand such a result out
-        return x, np.array(res), it
+        return x, res, it
 
     def cycle_bytes(self, nu1=1, nu2=1):
         """algorithmic bytes one rank moves per cycle on its distributed levels (+ the replicated tail)"""
