@@ -984,6 +984,8 @@ class DistHierarchy:
 
     def close(self):
         """collective: release the peer windows"""
+        self._pcg_ws = None
+        self._graph = None
         for cs in self._chansets.values():
             cs.close()
         self._chansets = {}
@@ -1173,7 +1175,17 @@ class DistHierarchy:
         dtc = core.dt(b)
         s = core.stream
         x = torch.zeros_like(b) if x0 is None else x0.clone()
-        r, ap, z, p = torch.empty_like(b), torch.empty_like(b), torch.empty_like(b), torch.zeros_like(b)
+        ap, p = torch.empty_like(b), torch.zeros_like(b)
+        # r and z are kept between calls so that the preconditioner apply z = V(r) is ONE captured CUDA graph that is
+        # replayed every iteration (peer transport / single rank; the NCCL transport launches the cycle eagerly)
+        key = (n, b.dtype, nu1, nu2, bool(self.overlap), self.halo)
+        ws = getattr(self, "_pcg_ws", None)
+        if ws is None or ws["key"] != key:
+            ws = self._pcg_ws = {"key": key, "r": torch.empty_like(b), "z": torch.empty_like(b), "replay": None}
+            if self.halo == "peer" or comm.world == 1:
+                ws["replay"] = self.capture(ws["r"], ws["z"], nu1, nu2)
+        r, z = ws["r"], ws["z"]
+        precond = ws["replay"] if ws["replay"] is not None else (lambda: self.vcycle(r, z, nu1, nu2))
         state = torch.zeros(int(lib.mlamg_dloop_state_bytes()) // 8, dtype=torch.float64, device=b.device)
         flags = state.view(torch.int32)[20:24]                        # it, done, maxiter, first
         res_d = torch.zeros(maxiter + 1, dtype=torch.float64, device=b.device)
@@ -1202,7 +1214,7 @@ class DistHierarchy:
         stop = bool(pins[0][1] != 0)
         k = 0
         while not stop and k < maxiter:
-            self.vcycle(r, z, nu1, nu2)
+            precond()
             dot_into(r, z, 8)
             check(lib.mlamg_dloop_scalar(sp, 1, rp, s()))
             check(lib.mlamg_dloop_direction(dtc, n, core.ptr(z), core.ptr(p), sp, s()))
