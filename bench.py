@@ -221,8 +221,14 @@ def run_ours(args):
             lambda: core.spmv(R0, r_, bc), P0.nnz * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc)]
     if lazy:
         Q0 = H._Q[0]
-        ops.append(("csr_rowop_kernel<double,LANES=1,OP_PSMOOTH0> (fine level: x = dw.*(b + r) + Q e, prolongation + post sweep fused)",
-                    lambda: core.prolong_smooth_zero(Q0, ec, b, r_, dw0, x), Q0.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N))
+        q32 = H._w32.get(0, (None, None))[1] if hasattr(H, "_w32") else None
+        if q32 is not None:      # the cycle's kernel: thread-per-row on the W32 (warp-interleaved) copy of Q
+            ops.append(("csr_w32_rowop_kernel<double,OP_PSMOOTH0> (fine level: x = dw.*(b + r) + Q e, prolongation + post sweep fused, "
+                        "W32 copy of Q)",
+                        lambda: core.prolong_smooth_zero_w32(Q0, q32, ec, b, r_, dw0, x), Q0.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N))
+        else:
+            ops.append(("csr_rowop_kernel<double,LANES=1,OP_PSMOOTH0> (fine level: x = dw.*(b + r) + Q e, prolongation + post sweep fused)",
+                        lambda: core.prolong_smooth_zero(Q0, ec, b, r_, dw0, x), Q0.nnz * (v + 4) + 4 * (N + 1) + v * Nc + 4 * v * N))
     elif H._Q:
         Q0 = H._Q[0]
         ops.append(("csr_rowop_kernel<double,LANES=1,OP_PSMOOTH> (fine level: x += dw.*r + Q e, prolongation + post sweep fused)",

@@ -86,6 +86,20 @@ int mlamg_jacobi_zero_residual_scaled_csr(int dtype, int n, int nnz, const int *
 int mlamg_prolong_smooth_csr(int dtype, int n, int nnz, const int *rowptr, const int *col, const void *val,
                              const void *e, const void *x_in, const void *r, const void *dw, void *x_out,
                              mlamg_stream_t stream);
+/* W32 layout of a short-row CSR operator (the fine-level Q): rowptr is shared with the CSR matrix, inside every window
+ * of 32 consecutive rows the entries are stored slot-major (all 0-th entries of the window in row order, then all 1-st
+ * entries, ...): no padding, no row permutation, and the k-th entries of a warp's rows are contiguous, so the thread-per-row
+ * kernel's col / val requests are coalesced (position = one ballot + popc per slot).  mlamg_csr_to_w32 writes the
+ * reordered col / val copies; mlamg_prolong_smooth_zero_w32 is mlamg_prolong_smooth_zero_csr on them (same sums, same
+ * order per row: bit-identical results). */
+int mlamg_csr_to_w32(int dtype, int n, const int *rowptr, const int *col, const void *val, int *col_out, void *val_out,
+                     mlamg_stream_t stream);
+int mlamg_prolong_smooth_zero_w32(int dtype, int n, const int *rowptr, const int *col_w32, const void *val_w32,
+                                  const void *e, const void *rhs, const void *r, const void *dw, void *x_out,
+                                  mlamg_stream_t stream);
+/* r = b - A x on the W32 copies */
+int mlamg_residual_w32(int dtype, int n, const int *rowptr, const int *col_w32, const void *val_w32, const void *x,
+                       const void *b, void *r, mlamg_stream_t stream);
 /* x_out = dw .* (rhs + r) + Q e: mlamg_prolong_smooth_csr when x_in is the zero-guess sweep dw.*rhs itself and
  * r = rhs - A x_in (e.g. from mlamg_residual_csr on the column-scaled values with x = b = rhs): x_in is never
  * materialised. */
@@ -259,6 +273,12 @@ int mlamg_hierarchy_set_operator_scaled(mlamg_hierarchy_t h, int level, const vo
  * q_rowptr == NULL removes it. */
 int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz, const int *q_rowptr,
                                       const int *q_col, const void *q_val);
+/* optional W32 copies (mlamg_csr_to_w32) of the column-scaled operator (values a_ij*dw_j) and of the post operator Q of a
+ * level: the zero-guess V(1,*) cycle then runs its residual and its prolongation + post sweep with the thread-per-row W32
+ * kernels.  Either pair may be NULL.  Pays on levels with >~ 100 k rows (measured at 256^3: level 1, 453 k rows of 17-30
+ * entries: 47.6 -> 37.8 us and 31.1 -> 22.7 us; level 0: 288.9 -> 285.3 us for Q, no change for A). */
+int mlamg_hierarchy_set_w32(mlamg_hierarchy_t h, int level, const int *a_col, const void *a_val_scaled, const int *q_col,
+                            const void *q_val);
 /* dense inverse of the coarsest operator (n x n row-major, in the hierarchy dtype) */
 int mlamg_hierarchy_set_coarse_inverse(mlamg_hierarchy_t h, const void *inv);
 /* allocate per-level work vectors (and the pinned staging buffers of the *_host entry points) */

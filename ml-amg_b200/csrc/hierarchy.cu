@@ -73,9 +73,16 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                 for (int k = 0; k < pipe->nchunks; k++) {      // rows of chunk k as soon as their columns have arrived
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
                     MLAMG_CUDA(cudaStreamWaitEvent(s, pipe->in_ev[pipe->need[k]], 0));
+                    if (lev.w32_a_col)
+                        MLAMG_TRY(w32_residual_range_t<T>(cnt, lo, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
+                                                          (T *)lev.r, s));
+                    else
                     MLAMG_TRY(residual_range_t<T>(cnt, lo, (long long)((double)A.nnz * cnt / A.n) + 1, A.rowptr, A.col,
                                                   (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r, s));
                 }
+            } else if (lazy[l] && lev.w32_a_col) {
+                MLAMG_TRY(w32_residual_range_t<T>(A.n, 0, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
+                                                  (T *)lev.r, s));
             } else if (lazy[l]) {
                 MLAMG_TRY(residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r,
                                         nullptr, s));
@@ -131,7 +138,10 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                 for (int k = 0; k < pipe->nchunks; k++) {      // every finished chunk of the result goes to the D2H copy
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
                     const long long hint = (long long)((double)Q.nnz * cnt / Q.n) + 1;
-                    if (lazy[l])
+                    if (lazy[l] && lev.w32_q_col)
+                        MLAMG_TRY(w32_psmooth0_range_t<T>(cnt, lo, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
+                                                          (const T *)lev.r, (const T *)lev.dw, o, s));
+                    else if (lazy[l])
                         MLAMG_TRY(psmooth0_range_t<T>(cnt, lo, hint, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l],
                                                       (const T *)lev.r, (const T *)lev.dw, o, s));
                     else
@@ -143,7 +153,10 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                                                cudaMemcpyDeviceToHost, pipe->cs));
                 }
                 x_host = nullptr;      // delivered
-            } else if (lazy[l])
+            } else if (lazy[l] && lev.w32_q_col)
+                MLAMG_TRY(w32_psmooth0_range_t<T>(Q.n, 0, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
+                                                  (const T *)lev.r, (const T *)lev.dw, o, s));
+            else if (lazy[l])
                 MLAMG_TRY(psmooth0_range_t<T>(Q.n, 0, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l], (const T *)lev.r,
                                               (const T *)lev.dw, o, s));
             else
@@ -335,6 +348,20 @@ int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz,
     if (!lev.has_A) return set_error(MLAMG_EINVAL, "set_post_operator: set the level operator first");
     lev.Q.n = lev.A.n; lev.Q.nnz = q_nnz; lev.Q.rowptr = q_rowptr; lev.Q.col = q_col; lev.Q.val = q_val;
     lev.has_Q = q_rowptr != nullptr;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return MLAMG_OK;
+}
+
+int mlamg_hierarchy_set_w32(mlamg_hierarchy_t h, int level, const int *a_col, const void *a_val_scaled, const int *q_col,
+                            const void *q_val) {
+    MLAMG_TRY(check_handle(h));
+    if (level < 0 || level + 1 >= (int)h->lv.size()) return set_error(MLAMG_EINVAL, "set_w32: bad level");
+    LevelData &lev = h->lv[level];
+    if (!lev.has_A) return set_error(MLAMG_EINVAL, "set_w32: set the level operator first");
+    if ((a_col == nullptr) != (a_val_scaled == nullptr) || (q_col == nullptr) != (q_val == nullptr))
+        return set_error(MLAMG_EINVAL, "set_w32: col and val copies come in pairs");
+    lev.w32_a_col = a_col; lev.w32_a_val = a_val_scaled;
+    lev.w32_q_col = q_col; lev.w32_q_val = q_val;
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     return MLAMG_OK;
 }

@@ -35,6 +35,10 @@ template <typename T>
 int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, T *, double *,
                  cudaStream_t);
 template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
+template <typename T>
+int w32_psmooth0_range_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
+template <typename T>
+int w32_residual_range_t(int, int, const int *, const int *, const T *, const T *, const T *, T *, cudaStream_t);
 
 struct Csr {
     int n = 0;          // rows
@@ -49,6 +53,10 @@ struct LevelData {
     Csr Q;                                                  // optional (I - D_w A) P: prolongation fused with the first post sweep
     bool has_Q = false;
     const void *val_scaled = nullptr;                       // optional values of A D_w (a_ij * dw_j) on A's pattern
+    // optional W32 copies (slot-major inside 32-row windows, apply.cu) of the scaled operator and of Q: thread-per-row
+    // kernels with a coalesced operator stream — used on levels with enough rows to fill the GPU with one thread per row
+    const int *w32_a_col = nullptr, *w32_q_col = nullptr;
+    const void *w32_a_val = nullptr, *w32_q_val = nullptr;
     const void *dw = nullptr;
     const int *r_order = nullptr;                           // optional processing order of the rows of R
     const int *sell_ptr = nullptr, *sell_col = nullptr;   // optional SELL-32 copy of A

@@ -61,6 +61,9 @@ SIGNATURES = {
     "mlamg_poisson_csr_slab": (I, [I, I, I, I, I, I, P, P, P, P, P]),
     "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P]),
     "mlamg_prolong_smooth_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
+    "mlamg_csr_to_w32": (I, [I, I, P, P, P, P, P, P]),
+    "mlamg_residual_w32": (I, [I, I, P, P, P, P, P, P, P]),
+    "mlamg_prolong_smooth_zero_w32": (I, [I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_prolong_smooth_zero_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_jacobi_zero_residual_scaled_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_hierarchy_set_operator_scaled": (I, [P, I, P]),
@@ -74,6 +77,7 @@ SIGNATURES = {
     "mlamg_hierarchy_set_operator": (I, [P, I, I, I, P, P, P, P]),
     "mlamg_hierarchy_set_transfer": (I, [P, I, I, P, P, P, P, P, P]),
     "mlamg_hierarchy_set_post_operator": (I, [P, I, I, P, P, P]),
+    "mlamg_hierarchy_set_w32": (I, [P, I, P, P, P, P]),
     "mlamg_hierarchy_set_coarse_inverse": (I, [P, P]),
     "mlamg_hierarchy_finalize": (I, [P, P]),
     "mlamg_hierarchy_destroy": (I, [P]),

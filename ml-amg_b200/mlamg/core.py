@@ -255,6 +255,33 @@ def prolong_smooth_zero(Q, e, rhs, r, dw, x_out=None):
     return x_out
 
 
+def csr_to_w32(A):
+    """W32 copies of A's col / val (slot-major inside every window of 32 rows; rowptr is shared).  -> (col_w32, val_w32)"""
+    col = torch.empty_like(A.col)
+    val = torch.empty_like(A.val)
+    if A.nnz == 0:
+        return col, val
+    check(lib.mlamg_csr_to_w32(dt(A.val), A.shape[0], ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(col), ptr(val), stream()))
+    return col, val
+
+
+def residual_w32(A, w32, x, b, out=None):
+    """r = b - A x on the W32 copies of A"""
+    if out is None:
+        out = torch.empty(A.shape[0], dtype=A.dtype, device=x.device)
+    check(lib.mlamg_residual_w32(dt(A.val), A.shape[0], ptr(A.rowptr), ptr(w32[0]), ptr(w32[1]), ptr(x), ptr(b), ptr(out), stream()))
+    return out
+
+
+def prolong_smooth_zero_w32(Q, w32, e, rhs, r, dw, x_out=None):
+    """prolong_smooth_zero on the W32 copies of Q (w32 = csr_to_w32(Q)): coalesced operator stream, bit-identical result"""
+    if x_out is None:
+        x_out = torch.empty_like(rhs)
+    check(lib.mlamg_prolong_smooth_zero_w32(dt(Q.val), Q.shape[0], ptr(Q.rowptr), ptr(w32[0]), ptr(w32[1]), ptr(e), ptr(rhs), ptr(r),
+                                            ptr(dw), ptr(x_out), stream()))
+    return x_out
+
+
 def prolong_smooth(Q, e, x_in, r, dw, x_out=None):
     """x_out = x_in + dw .* r + Q e (prolongation fused with the first post-smoothing sweep; x_out may be x_in)."""
     n = Q.shape[0]

@@ -134,7 +134,8 @@ class Hierarchy:
     """Owns the device arrays of every level and the C handle that runs the cycles."""
 
     def __init__(self, levels, smoother="jacobi", jacobi_weight=2.0 / 3.0, use_graph=False, sell="never",
-                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True, fuse_pre=True, coarse_inv=None):
+                 sell_max_padding=1.5, restrict_order=True, renumber=True, fuse_post=True, fuse_pre=True, coarse_inv=None,
+                 w32_min_rows=100000, w32_fine_operator=False):
         """levels: list[Level] in the REFERENCE numbering (what setup produced and what parity is checked on).
 
         renumber (default on): the cycle runs on apply copies whose coarse levels are renumbered spatially
@@ -189,6 +190,21 @@ class Hierarchy:
                 Q = post_operator(A, P, dw)
                 self._Q.append(Q)
                 check(lib.mlamg_hierarchy_set_post_operator(self._h, l, Q.nnz, ptr(Q.rowptr), ptr(Q.col), ptr(Q.val)))
+        # W32 copies (slot-major inside 32-row windows): thread-per-row kernels with a coalesced operator stream for the
+        # residual on the scaled copy and for x = dw.*(b + r) + Q e.  Levels with >= w32_min_rows rows (below that one
+        # thread per row does not fill the GPU; measured at 256^3: level 1 -18 us per cycle, level 2 slower).  The
+        # 7-entry fine operator is DRAM-bound in plain CSR already (w32_fine_operator=False: no second copy of A).
+        self._w32 = {}
+        for l, (A, P, R, dw) in enumerate(self._apply[:-1]):
+            if A.shape[0] < w32_min_rows or not (self._scaled and self._Q):
+                continue
+            a32 = None
+            if A.nnz > 12 * A.shape[0] or w32_fine_operator:
+                a32 = core.csr_to_w32(A.with_values(self._scaled[l]))
+            q32 = core.csr_to_w32(self._Q[l])
+            self._w32[l] = (a32, q32)
+            check(lib.mlamg_hierarchy_set_w32(self._h, l, ptr(a32[0]) if a32 else None, ptr(a32[1]) if a32 else None,
+                                              ptr(q32[0]), ptr(q32[1])))
         # Without renumbering the restriction rows keep the reference's random seed numbering; then at least
         # VISIT them in the order of their first fine node so neighbouring aggregates share sectors of r.
         self._r_order = []

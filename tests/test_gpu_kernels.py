@@ -438,3 +438,36 @@ def test_gauss_seidel_mirror_honours_L_and_U():
     assert np.abs(got0 - ref0).max() <= 1e-13 * np.abs(ref0).max()
     with pytest.raises(ValueError):
         mg.gauss_seidel(A, b, x.copy(), L=A, nu=1)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_w32_layout_is_bit_identical_to_csr(dtype):
+    """the warp-interleaved copy of a short-row operator: same per-row sums in the same order as the CSR kernel"""
+    import mlamg
+    from mlamg import core
+    rs = np.random.RandomState(7)
+    for A in (random_csr(1000, 300, 0.02, 3, dtype=dtype), oml.poisson((37, 29)).astype(dtype), random_csr(70, 50, 0.3, 5, dtype=dtype),
+              random_csr(33, 40, 0.0, 6, dtype=dtype)):
+        n, m = A.shape
+        Ad = mlamg.DeviceCSR.from_scipy(A)
+        w32 = core.csr_to_w32(Ad)
+        # the copy is a permutation of the entries inside every 32-row window
+        rp = A.indptr
+        for w0 in range(0, n, 32):
+            a, b_ = rp[w0], rp[min(w0 + 32, n)]
+            got = sorted(zip(w32[0][a:b_].cpu().numpy().tolist(), w32[1][a:b_].cpu().numpy().tolist()))
+            assert got == sorted(zip(A.indices[a:b_].tolist(), A.data[a:b_].tolist()))
+        e, rhs, r, dw = (dev(rs.randn(k), dtype) for k in (m, n, n, n))
+        try:
+            mlamg.set_csr_lanes(1)                 # thread-per-row CSR kernel: the same summation order per row
+            ref = core.prolong_smooth_zero(Ad, e, rhs, r, dw)
+            if n == m:
+                ref_r = core.residual(Ad, e, rhs)
+        finally:
+            mlamg.set_csr_lanes(-1)
+        got = core.prolong_smooth_zero_w32(Ad, w32, e, rhs, r, dw)
+        assert torch.equal(ref, got)
+        want = dw.cpu().numpy() * (rhs.cpu().numpy() + r.cpu().numpy()) + A @ e.cpu().numpy()
+        close(got, want, dtype, np.abs(want).max() + 1.0)
+        if n == m:
+            assert torch.equal(core.residual_w32(Ad, w32, e, rhs), ref_r)

@@ -42,7 +42,9 @@ def main():
         return e0.elapsed_time(e1) / 5 / reps * 1e3       # us
 
     v = 8
-    for l in (0, 1):
+    for l in ((0, 1, 2) if os.environ.get("TUNE_W32") == "1" else (0, 1)):
+        if l >= len(H._apply) - 1:
+            continue
         Al, P, R, dw = H._apply[l]
         N, nnz, Nc, pn = Al.shape[0], Al.nnz, P.shape[1], P.nnz
         rs = torch.Generator(device="cuda").manual_seed(l)
@@ -69,6 +71,14 @@ def main():
             "restrict": (lambda: core.spmv(R, r, bc), pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc),
             "restrict_ordered": (lambda: core.spmv_perm(R, r, order, bc), pn * (v + 4) + 4 * (Nc + 1) + v * N + v * Nc),
         }
+        if os.environ.get("TUNE_W32") == "1":
+            w32 = core.csr_to_w32(Q)
+            As = Al.with_values(vs)
+            aw32 = core.csr_to_w32(As)
+            ops = {"psmooth0_csr": ops["psmooth0"],
+                   "psmooth0_w32": (lambda: core.prolong_smooth_zero_w32(Q, w32, e, b, r, dw, y), ops["psmooth0"][1]),
+                   "residual_scaled_csr": ops["residual_scaled"],
+                   "residual_scaled_w32": (lambda: core.residual_w32(As, aw32, b, b, r), ops["residual_scaled"][1])}
         for name, (fn, nbytes) in ops.items():
             out = {"level": l, "op": name, "rows": N if "restrict" not in name else Nc,
                    "mean_row": round((pn / Nc) if "restrict" in name else (pn / N if name == "prolong_add" else
@@ -78,6 +88,8 @@ def main():
             cand = [l for l in (1, 2, 4, 8, 16, 32) if l <= max(1, 2 * mean) and l * 16 >= mean]
             if os.environ.get("TUNE_ALL") == "1":
                 cand = [0, 1, 2, 4, 8, 16, 32]
+            if os.environ.get("TUNE_W32") == "1":
+                cand = []
             if os.environ.get("TUNE_TMA") == "1":          # plain thread-per-row vs the TMA-staged kernel, short-row ops only
                 if mean > 12 or name in ("restrict", "restrict_ordered"):
                     continue

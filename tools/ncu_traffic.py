@@ -35,9 +35,13 @@ def main():
     best = {}
     for d in launches.values():
         m = re.search(r"csr_rowop_kernel<double, (\d+), (\d+)", d["name"])
-        if not m:
+        mw = re.search(r"csr_w32_rowop_kernel<double, (\d+)", d["name"])
+        if mw:
+            key = f"csr_w32_rowop_kernel<double,{OPS.get(int(mw.group(1)), mw.group(1))}>"
+        elif m:
+            key = f"LANES={int(m.group(1))},{OPS.get(int(m.group(2)), m.group(2))}>"
+        else:
             continue
-        key = f"LANES={int(m.group(1))},{OPS.get(int(m.group(2)), m.group(2))}>"
         if key not in best or d["bytes"] > best[key]["bytes"]:
             best[key] = d
     sha = hashlib.sha256(open(os.path.join(ROOT, "ml-amg_b200", "csrc", "apply.cu"), "rb").read()).hexdigest()
