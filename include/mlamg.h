@@ -97,6 +97,12 @@ int mlamg_csr_to_w32(int dtype, int n, const int *rowptr, const int *col, const 
 int mlamg_prolong_smooth_zero_w32(int dtype, int n, const int *rowptr, const int *col_w32, const void *val_w32,
                                   const void *e, const void *rhs, const void *r, const void *dw, void *x_out,
                                   mlamg_stream_t stream);
+/* generic row-op on the W32 copies over rows [row0, row0 + nrows) of an operator with n_total rows — op codes of
+ * mlamg_rowop_csr: 0 y = A x | 2 y = b - A x | 5 y = aux + dw.*b + A x | 7 y = dw.*(aux + b) + A x (any row range: windows are
+ * aligned to absolute row numbers and the rows of the first / last window outside the range only take part in the ballots) */
+int mlamg_rowop_w32(int dtype, int op, int nrows, int row0, int n_total, const int *rowptr, const int *col_w32,
+                    const void *val_w32, const void *x, const void *b, const void *dw, void *y, void *aux,
+                    mlamg_stream_t stream);
 /* r = b - A x on the W32 copies */
 int mlamg_residual_w32(int dtype, int n, const int *rowptr, const int *col_w32, const void *val_w32, const void *x,
                        const void *b, void *r, mlamg_stream_t stream);

@@ -250,21 +250,27 @@ csr_tma_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restric
 // both computed with one ballot + popc per slot — nothing but the row lengths is read.  With plain CSR a warp's k-th
 // entries lie 5.5 entries apart (Q) and every col / val request touches 22 / 32 sectors (ncu source counters:
 // 160 M of the kernel's 225 M L1 sectors, 37 M ideal); here they are 4 / 8.
+// Rows [row_begin, row_end) of an operator with n_total rows; windows are aligned to absolute row numbers, so the launch
+// starts at the window containing row_begin and rows of the first / last window outside the range only take part in the
+// ballots (their entries occupy positions of the window too).
 template <typename T, int OP>
 __global__ void __launch_bounds__(ROW_THREADS, 8)
-csr_w32_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const T *__restrict__ val,
-                     const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *y, int row0, T *y2) {
-    const long long gtid = (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
-    const bool valid = gtid < n;
-    const long long row = gtid + row0;                       // row0 is a multiple of 32: lane = row % 32
+csr_w32_rowop_kernel(int row_begin, int row_end, int n_total, const int *__restrict__ rowptr, const int *__restrict__ col,
+                     const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ dw, T *y,
+                     T *y2) {
+    const long long row = (long long)(row_begin & ~31) + (long long)blockIdx.x * ROW_THREADS + threadIdx.x;
+    const int last_window_end = min(n_total, (row_end + 31) & ~31);
+    const bool present = row < last_window_end;              // a row of a window this launch touches
+    const bool active = row >= row_begin && row < row_end;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     int start = 0, len = 0;
-    if (valid) {
+    if (present) {
         start = rowptr[row];
         len = rowptr[row + 1] - start;
     }
     int off = __shfl_sync(0xffffffffu, start, 0);            // first entry of the window
+    const int mylen = active ? len : 0;                      // rows outside the range load nothing
     T sum = (T)0;
     constexpr int NB = 4;
     for (int k = 0;; k += NB) {
@@ -283,15 +289,15 @@ csr_w32_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restric
         }
         off = o;
 #pragma unroll
-        for (int j = 0; j < NB; j++) c[j] = (k + j < len) ? col[idx[j]] : 0;
+        for (int j = 0; j < NB; j++) c[j] = (k + j < mylen) ? col[idx[j]] : 0;
 #pragma unroll
-        for (int j = 0; j < NB; j++) v[j] = (k + j < len) ? val[idx[j]] : (T)0;
+        for (int j = 0; j < NB; j++) v[j] = (k + j < mylen) ? val[idx[j]] : (T)0;
 #pragma unroll
-        for (int j = 0; j < NB; j++) xv[j] = (k + j < len) ? x[c[j]] : (T)0;
+        for (int j = 0; j < NB; j++) xv[j] = (k + j < mylen) ? x[c[j]] : (T)0;
 #pragma unroll
         for (int j = 0; j < NB; j++) sum += v[j] * xv[j];
     }
-    if (valid) row_epilogue<T, OP, false>(row, sum, x, b, dw, y, y2);
+    if (active) row_epilogue<T, OP, false>(row, sum, x, b, dw, y, y2);
 }
 
 // CSR -> W32: same index arithmetic, entries scattered to their slot-major position
@@ -321,43 +327,51 @@ csr_to_w32_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__
     }
 }
 
+static inline unsigned w32_blocks(int row_begin, int row_end, int n_total) {
+    const int first = row_begin & ~31;
+    int last = (row_end + 31) & ~31;
+    if (last > n_total) last = n_total;
+    return cdiv(last - first, ROW_THREADS);
+}
+
+// generic W32 row-op over rows [row0, row0 + nrows) of an operator with n_total rows (ops: residual, psmooth, psmooth0, spmv)
 template <typename T>
-int w32_psmooth0_range_t(int nrows, int row0, const int *rowptr, const int *col_w32, const T *val_w32, const T *e,
-                         const T *rhs, const T *r, const T *dw, T *x_out, cudaStream_t s) {
+int w32_rowop_t(int op, int nrows, int row0, int n_total, const int *rowptr, const int *col_w32, const T *val_w32, const T *x,
+                const T *b, const T *dw, T *y, T *aux, cudaStream_t s) {
     if (nrows <= 0) return MLAMG_OK;
-    if (row0 & 31) return set_error(MLAMG_EINVAL, "w32 row-op: the first row must be a multiple of 32");
-    csr_w32_rowop_kernel<T, OP_PSMOOTH0><<<cdiv(nrows, ROW_THREADS), ROW_THREADS, 0, s>>>(nrows, rowptr, col_w32, val_w32, e, r, dw,
-                                                                                        x_out, row0, const_cast<T *>(rhs));
+    if (row0 < 0 || row0 + nrows > n_total) return set_error(MLAMG_EINVAL, "w32 row-op: row range outside the operator");
+    const unsigned blocks = w32_blocks(row0, row0 + nrows, n_total);
+#define W32_LAUNCH(OPC) \
+    csr_w32_rowop_kernel<T, OPC><<<blocks, ROW_THREADS, 0, s>>>(row0, row0 + nrows, n_total, rowptr, col_w32, val_w32, x, b, dw, y, aux)
+    switch (op) {
+        case OP_SPMV: W32_LAUNCH(OP_SPMV); break;
+        case OP_RESIDUAL: W32_LAUNCH(OP_RESIDUAL); break;
+        case OP_PSMOOTH: W32_LAUNCH(OP_PSMOOTH); break;
+        case OP_PSMOOTH0: W32_LAUNCH(OP_PSMOOTH0); break;
+        default: return set_error(MLAMG_EINVAL, "w32 row-op: op %d is not built for this layout", op);
+    }
+#undef W32_LAUNCH
     MLAMG_LAUNCHED();
     return MLAMG_OK;
 }
+template int w32_rowop_t<float>(int, int, int, int, const int *, const int *, const float *, const float *, const float *, const float *, float *, float *, cudaStream_t);
+template int w32_rowop_t<double>(int, int, int, int, const int *, const int *, const double *, const double *, const double *, const double *, double *, double *, cudaStream_t);
+
 template <typename T>
-int w32_psmooth_range_t(int nrows, int row0, const int *rowptr, const int *col_w32, const T *val_w32, const T *e,
-                        const T *x_in, const T *r, const T *dw, T *x_out, cudaStream_t s) {
-    if (nrows <= 0) return MLAMG_OK;
-    if (row0 & 31) return set_error(MLAMG_EINVAL, "w32 row-op: the first row must be a multiple of 32");
-    csr_w32_rowop_kernel<T, OP_PSMOOTH><<<cdiv(nrows, ROW_THREADS), ROW_THREADS, 0, s>>>(nrows, rowptr, col_w32, val_w32, e, r, dw,
-                                                                                       x_out, row0, const_cast<T *>(x_in));
-    MLAMG_LAUNCHED();
-    return MLAMG_OK;
+int w32_psmooth0_range_t(int nrows, int row0, int n_total, const int *rowptr, const int *col_w32, const T *val_w32, const T *e,
+                         const T *rhs, const T *r, const T *dw, T *x_out, cudaStream_t s) {
+    return w32_rowop_t<T>(OP_PSMOOTH0, nrows, row0, n_total, rowptr, col_w32, val_w32, e, r, dw, x_out, const_cast<T *>(rhs), s);
 }
 // r = b - A x on the W32 copies (the scaled-copy residual of the cycle: x = b)
 template <typename T>
-int w32_residual_range_t(int nrows, int row0, const int *rowptr, const int *col_w32, const T *val_w32, const T *x, const T *b,
-                         T *r, cudaStream_t s) {
-    if (nrows <= 0) return MLAMG_OK;
-    if (row0 & 31) return set_error(MLAMG_EINVAL, "w32 row-op: the first row must be a multiple of 32");
-    csr_w32_rowop_kernel<T, OP_RESIDUAL><<<cdiv(nrows, ROW_THREADS), ROW_THREADS, 0, s>>>(nrows, rowptr, col_w32, val_w32, x, b, nullptr,
-                                                                                        r, row0, nullptr);
-    MLAMG_LAUNCHED();
-    return MLAMG_OK;
+int w32_residual_range_t(int nrows, int row0, int n_total, const int *rowptr, const int *col_w32, const T *val_w32, const T *x,
+                         const T *b, T *r, cudaStream_t s) {
+    return w32_rowop_t<T>(OP_RESIDUAL, nrows, row0, n_total, rowptr, col_w32, val_w32, x, b, nullptr, r, nullptr, s);
 }
-template int w32_residual_range_t<float>(int, int, const int *, const int *, const float *, const float *, const float *, float *, cudaStream_t);
-template int w32_residual_range_t<double>(int, int, const int *, const int *, const double *, const double *, const double *, double *, cudaStream_t);
-template int w32_psmooth0_range_t<float>(int, int, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
-template int w32_psmooth0_range_t<double>(int, int, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
-template int w32_psmooth_range_t<float>(int, int, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
-template int w32_psmooth_range_t<double>(int, int, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
+template int w32_residual_range_t<float>(int, int, int, const int *, const int *, const float *, const float *, const float *, float *, cudaStream_t);
+template int w32_residual_range_t<double>(int, int, int, const int *, const int *, const double *, const double *, const double *, double *, cudaStream_t);
+template int w32_psmooth0_range_t<float>(int, int, int, const int *, const int *, const float *, const float *, const float *, const float *, const float *, float *, cudaStream_t);
+template int w32_psmooth0_range_t<double>(int, int, int, const int *, const int *, const double *, const double *, const double *, const double *, const double *, double *, cudaStream_t);
 
 // SELL-32: rows are grouped in slices of 32; a slice stores width = max row length columns, column-
 // major inside the slice (entry k of lane l at slice_ptr[s] + 32 k + l), padded with col = -1.  One
@@ -854,8 +868,15 @@ int mlamg_prolong_smooth_zero_w32(int dtype, int n, const int *rowptr, const int
                                   const void *rhs, const void *r, const void *dw, void *x_out, mlamg_stream_t stream) {
     if (n < 0) return set_error(MLAMG_EINVAL, "prolong_smooth_zero_w32: n < 0");
     if (e == x_out || r == x_out || rhs == x_out) return set_error(MLAMG_EINVAL, "prolong_smooth_zero_w32: aliased arguments");
-    MLAMG_DISPATCH(dtype, return w32_psmooth0_range_t<T>(n, 0, rowptr, col_w32, (const T *)val_w32, (const T *)e, (const T *)rhs,
+    MLAMG_DISPATCH(dtype, return w32_psmooth0_range_t<T>(n, 0, n, rowptr, col_w32, (const T *)val_w32, (const T *)e, (const T *)rhs,
                                                          (const T *)r, (const T *)dw, (T *)x_out, as_stream(stream)));
+    return MLAMG_OK;
+}
+
+int mlamg_rowop_w32(int dtype, int op, int nrows, int row0, int n_total, const int *rowptr, const int *col_w32, const void *val_w32,
+                    const void *x, const void *b, const void *dw, void *y, void *aux, mlamg_stream_t stream) {
+    MLAMG_DISPATCH(dtype, return w32_rowop_t<T>(op, nrows, row0, n_total, rowptr, col_w32, (const T *)val_w32, (const T *)x,
+                                                (const T *)b, (const T *)dw, (T *)y, (T *)aux, as_stream(stream)));
     return MLAMG_OK;
 }
 
@@ -863,7 +884,7 @@ int mlamg_residual_w32(int dtype, int n, const int *rowptr, const int *col_w32, 
                        void *r, mlamg_stream_t stream) {
     if (n < 0) return set_error(MLAMG_EINVAL, "residual_w32: n < 0");
     if (x == r || b == r) return set_error(MLAMG_EINVAL, "residual_w32: aliased arguments");
-    MLAMG_DISPATCH(dtype, return w32_residual_range_t<T>(n, 0, rowptr, col_w32, (const T *)val_w32, (const T *)x, (const T *)b,
+    MLAMG_DISPATCH(dtype, return w32_residual_range_t<T>(n, 0, n, rowptr, col_w32, (const T *)val_w32, (const T *)x, (const T *)b,
                                                          (T *)r, as_stream(stream)));
     return MLAMG_OK;
 }

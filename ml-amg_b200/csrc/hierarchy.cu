@@ -74,14 +74,14 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
                     MLAMG_CUDA(cudaStreamWaitEvent(s, pipe->in_ev[pipe->need[k]], 0));
                     if (lev.w32_a_col)
-                        MLAMG_TRY(w32_residual_range_t<T>(cnt, lo, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
+                        MLAMG_TRY(w32_residual_range_t<T>(cnt, lo, A.n, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
                                                           (T *)lev.r, s));
                     else
                     MLAMG_TRY(residual_range_t<T>(cnt, lo, (long long)((double)A.nnz * cnt / A.n) + 1, A.rowptr, A.col,
                                                   (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r, s));
                 }
             } else if (lazy[l] && lev.w32_a_col) {
-                MLAMG_TRY(w32_residual_range_t<T>(A.n, 0, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
+                MLAMG_TRY(w32_residual_range_t<T>(A.n, 0, A.n, A.rowptr, lev.w32_a_col, (const T *)lev.w32_a_val, rhs[l], rhs[l],
                                                   (T *)lev.r, s));
             } else if (lazy[l]) {
                 MLAMG_TRY(residual_t<T>(A.n, A.nnz, A.rowptr, A.col, (const T *)lev.val_scaled, rhs[l], rhs[l], (T *)lev.r,
@@ -139,7 +139,7 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                     const int lo = pipe->row_lo[k], cnt = pipe->row_lo[k + 1] - lo;
                     const long long hint = (long long)((double)Q.nnz * cnt / Q.n) + 1;
                     if (lazy[l] && lev.w32_q_col)
-                        MLAMG_TRY(w32_psmooth0_range_t<T>(cnt, lo, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
+                        MLAMG_TRY(w32_psmooth0_range_t<T>(cnt, lo, Q.n, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
                                                           (const T *)lev.r, (const T *)lev.dw, o, s));
                     else if (lazy[l])
                         MLAMG_TRY(psmooth0_range_t<T>(cnt, lo, hint, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l],
@@ -154,7 +154,7 @@ static int vcycle_enqueue(mlamg_hierarchy *h, const T *b, T *x, int nu1, int nu2
                 }
                 x_host = nullptr;      // delivered
             } else if (lazy[l] && lev.w32_q_col)
-                MLAMG_TRY(w32_psmooth0_range_t<T>(Q.n, 0, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
+                MLAMG_TRY(w32_psmooth0_range_t<T>(Q.n, 0, Q.n, Q.rowptr, lev.w32_q_col, (const T *)lev.w32_q_val, cur[l + 1], rhs[l],
                                                   (const T *)lev.r, (const T *)lev.dw, o, s));
             else if (lazy[l])
                 MLAMG_TRY(psmooth0_range_t<T>(Q.n, 0, Q.nnz, Q.rowptr, Q.col, (const T *)Q.val, cur[l + 1], rhs[l], (const T *)lev.r,

@@ -36,9 +36,9 @@ int sell_rowop_t(int, int, const int *, const int *, const T *, const T *, const
                  cudaStream_t);
 template <typename T> int gemv_t(int, const T *, const T *, T *, cudaStream_t);
 template <typename T>
-int w32_psmooth0_range_t(int, int, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
+int w32_psmooth0_range_t(int, int, int, const int *, const int *, const T *, const T *, const T *, const T *, const T *, T *, cudaStream_t);
 template <typename T>
-int w32_residual_range_t(int, int, const int *, const int *, const T *, const T *, const T *, T *, cudaStream_t);
+int w32_residual_range_t(int, int, int, const int *, const int *, const T *, const T *, const T *, T *, cudaStream_t);
 
 struct Csr {
     int n = 0;          // rows

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mlamg_rowop_csr": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P]),
     "mlamg_prolong_smooth_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_csr_to_w32": (I, [I, I, P, P, P, P, P, P]),
+    "mlamg_rowop_w32": (I, [I, I, I, I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_residual_w32": (I, [I, I, P, P, P, P, P, P, P]),
     "mlamg_prolong_smooth_zero_w32": (I, [I, I, P, P, P, P, P, P, P, P, P]),
     "mlamg_prolong_smooth_zero_csr": (I, [I, I, I, P, P, P, P, P, P, P, P, P]),

@@ -265,6 +265,17 @@ def csr_to_w32(A):
     return col, val
 
 
+def rowop_w32(A, w32, op, x, y, b=None, dw=None, row_range=None, aux=None):
+    """rowop() on the W32 copies of A (ops 0, 2, 5, 7) over all rows or the contiguous range row_range=(begin, end)"""
+    n_total = A.shape[0]
+    begin, end = (0, n_total) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    if end <= begin:
+        return y
+    check(lib.mlamg_rowop_w32(dt(A.val), op, end - begin, begin, n_total, ptr(A.rowptr), ptr(w32[0]), ptr(w32[1]), ptr(x), ptr(b),
+                              ptr(dw), ptr(y), ptr(aux), stream()))
+    return y
+
+
 def residual_w32(A, w32, x, b, out=None):
     """r = b - A x on the W32 copies of A"""
     if out is None:

@@ -237,6 +237,8 @@ PEER_BOUNDARY_SIDE = int(_os.environ.get("MLAMG_PEER_BOUNDARY_SIDE", "1"))
 # 1: when everything an operator sends is written by the boundary rows of the operator before it (residual -> restriction),
 # its push is issued right behind that boundary kernel on the side stream instead of after the previous operator's join
 EARLY_PUSH = _os.environ.get("MLAMG_EARLY_PUSH", "1") == "1"
+# rows per rank from which the interior rows of the residual / prolongation+post-sweep run on W32 copies (0 = never)
+W32_MIN_ROWS = int(_os.environ.get("MLAMG_W32_MIN_ROWS", "100000"))
 _ALIGN = 256
 
 
@@ -556,6 +558,14 @@ class DistOperator:
         self.plan.exchange(dw_ext, self.n_cols_own)
         self.csr_scaled = self.csr.with_values(core.scaled_values(self.csr, dw_ext))
 
+    def build_w32(self, scaled_only=False):
+        """W32 copies (core.csr_to_w32) of the local rows for the interior-row kernels of the cycle"""
+        self.w32 = getattr(self, "w32", {})
+        if not scaled_only:
+            self.w32["csr"] = core.csr_to_w32(self.csr)
+        if hasattr(self, "csr_scaled"):
+            self.w32["scaled"] = core.csr_to_w32(self.csr_scaled)
+
     def channel_spec(self, name, dtype):
         """(name, send list, per-rank counts, dtype) of the halo exchange of this operator's input"""
         return (name, self.plan.send_idx, self.plan.send_counts, self.plan.recv_counts, dtype)
@@ -615,8 +625,13 @@ class DistOperator:
                         after_boundary()
                         ran_after = True
             if split:
-                core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
-                           rows=None if self.interior_range is not None else self.interior)
+                w32 = getattr(self, "w32", {}).get("scaled" if op in (6, 8) else "csr")
+                if w32 is not None and self.interior_range is not None and kop in (0, 2, 5, 7):
+                    # thread-per-row kernel on the W32 (warp-interleaved) copy: coalesced operator stream
+                    core.rowop_w32(A, w32, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range)
+                else:
+                    core.rowop(A, kop, xk, y, b=b, dw=dw, aux=aux, row_range=self.interior_range,
+                               rows=None if self.interior_range is not None else self.interior)
             if side == 2:              # boundary rows on a normal-priority stream, enqueued behind the interior launch
                 lo = _low_stream()
                 lo.wait_stream(comm_stream)
@@ -742,6 +757,16 @@ class DistHierarchy:
             for L in self.levels:
                 L.A.build_scaled(L.dw)
         T_.lap("scaled_copy")
+        # W32 copies for the thread-per-row interior kernels (levels with enough rows per rank; the 7-entry fine operator is
+        # DRAM-bound in plain CSR already): Q always, the scaled operator when its rows are long
+        if W32_MIN_ROWS > 0:
+            for L in self.levels:
+                if L.n < W32_MIN_ROWS or not (self.fuse_pre and self.fuse_post and L.Q is not None):
+                    continue
+                L.Q.build_w32()
+                if L.A.csr.nnz > 12 * L.n:
+                    L.A.build_w32(scaled_only=True)
+
         def _subset(send_idx, rows):      # is everything that is sent written by these (boundary) rows?
             si, bd = send_idx.long(), rows.long()
             return bool(si.numel() == 0 or (bd.numel() > 0 and bool(torch.isin(si, bd).all())))

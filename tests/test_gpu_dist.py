@@ -58,3 +58,10 @@ def test_dist_hierarchy_world4_interior_ranks(extra):
 def test_dist_hierarchy_world8():
     out = _run(8, 12, extra=["--cube"])
     assert out.returncode == 0 and out.stdout.count("PASS") == 8, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dist_hierarchy_world2_w32_interior_kernels():
+    """the interior rows of the residual / prolongation passes on the W32 (warp-interleaved) copies, forced on at this size"""
+    out = _run(2, 16, env={"MLAMG_W32_MIN_ROWS": "1"}, extra=["--cube"])
+    assert out.returncode == 0 and out.stdout.count("PASS") == 2, out.stdout[-3000:] + out.stderr[-3000:]

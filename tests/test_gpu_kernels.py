@@ -471,3 +471,25 @@ def test_w32_layout_is_bit_identical_to_csr(dtype):
         close(got, want, dtype, np.abs(want).max() + 1.0)
         if n == m:
             assert torch.equal(core.residual_w32(Ad, w32, e, rhs), ref_r)
+
+
+def test_w32_rowop_on_unaligned_row_ranges():
+    """mlamg_rowop_w32 over arbitrary [begin, end): rows of the first / last window outside the range only vote"""
+    import mlamg
+    from mlamg import core
+    rs = np.random.RandomState(11)
+    A = random_csr(777, 777, 0.02, 9)
+    n = A.shape[0]
+    Ad = mlamg.DeviceCSR.from_scipy(A)
+    w32 = core.csr_to_w32(Ad)
+    x, b, dw, aux = (dev(rs.randn(n), np.float64) for _ in range(4))
+    xn, bn, dwn, auxn = (t.cpu().numpy() for t in (x, b, dw, aux))
+    full = {0: A @ xn, 2: bn - A @ xn, 5: auxn + dwn * bn + A @ xn, 7: dwn * (auxn + bn) + A @ xn}
+    for op in (0, 2, 5, 7):
+        for lo, hi in ((0, n), (5, 40), (31, 33), (64, 64), (100, 777), (770, 777), (33, 500)):
+            y = torch.full((n,), 123.0, dtype=torch.float64, device="cuda")
+            core.rowop_w32(Ad, w32, op, x, y, b=b, dw=dw, row_range=(lo, hi), aux=aux)
+            got = y.cpu().numpy()
+            assert np.all(got[:lo] == 123.0) and np.all(got[hi:] == 123.0), (op, lo, hi)
+            scale = np.abs(full[op]).max() + 1.0
+            assert np.abs(got[lo:hi] - full[op][lo:hi]).max() <= 1e-13 * scale, (op, lo, hi)

@@ -65,6 +65,7 @@ def main():
         res["ms_boundary_side_no_early_push"] = timed(replay)
         H._graph = None
         md.EARLY_PUSH = True
+        res["w32_levels"] = [sorted(getattr(L.Q, "w32", {})) + sorted("A:" + k for k in getattr(L.A, "w32", {})) for L in H.levels]
         res["early_push_flags"] = [{k: bool(getattr(L, k, False)) for k in ("early_R", "early_next_res", "early_up_Q", "early_up_A")}
                                    for L in H.levels]
         H.check_exchange()
