@@ -61,6 +61,11 @@ static __device__ __noinline__ uint4 ll_spin16(const uint4 *p, unsigned tag, uns
     for (unsigned spins = 0;; spins++) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
         if (v.y == tag && v.w == tag) break;
+#ifndef MLAMG_LL_TIGHT_SPIN
+        // back off: a warp that polls in a tight loop takes issue slots, LSU bandwidth and power from the interior-row
+        // kernel running beside it (the boundary rows are launched before their halo can have arrived)
+        if (spins >= 4u) __nanosleep(spins < 64u ? 100u : 400u);
+#endif
         if ((spins & 1023u) == 0u) {
             if (*(volatile unsigned long long *)(state + 3) != 0ull) break;      // the channel already timed out
             if (spins == 0u) t0 = ll_global_ns();
@@ -78,6 +83,9 @@ static __device__ __noinline__ uint2 ll_spin8(const uint2 *p, unsigned tag, unsi
     for (unsigned spins = 0;; spins++) {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
         if (v.y == tag) break;
+#ifndef MLAMG_LL_TIGHT_SPIN
+        if (spins >= 4u) __nanosleep(spins < 64u ? 100u : 400u);
+#endif
         if ((spins & 1023u) == 0u) {
             if (*(volatile unsigned long long *)(state + 3) != 0ull) break;
             if (spins == 0u) t0 = ll_global_ns();

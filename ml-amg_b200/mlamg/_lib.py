@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmlamg_b200.so")
+# MLAMG_LIB_PATH: development aid (A/B of two builds of the extension); the default is the in-tree library
+LIB_PATH = os.environ.get("MLAMG_LIB_PATH") or os.path.join(HERE, "libmlamg_b200.so")
 
 F32, F64 = 0, 1
 OK, EINVAL, ECUDA, ELIMIT, ESINGULAR, EKEY = 0, 1, 2, 3, 4, 5
