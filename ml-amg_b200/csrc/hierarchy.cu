@@ -12,6 +12,12 @@
 
 namespace mlamg {
 
+// a setter changed what the cycle runs: drop the cached cycle graph and the solver-loop graphs built on it
+static void invalidate_graphs(mlamg_hierarchy *h) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    solver_graphs_reset(h);
+}
+
 int check_handle(mlamg_hierarchy_t h) {
     if (!h) return set_error(MLAMG_EINVAL, "null hierarchy handle");
     return MLAMG_OK;
@@ -302,7 +308,7 @@ int mlamg_hierarchy_set_restrict_order(mlamg_hierarchy_t h, int level, const int
     MLAMG_TRY(check_handle(h));
     if (level < 0 || level + 1 >= (int)h->lv.size()) return set_error(MLAMG_EINVAL, "set_restrict_order: bad level");
     h->lv[level].r_order = row_order;
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    invalidate_graphs(h);
     return MLAMG_OK;
 }
 
@@ -313,7 +319,7 @@ int mlamg_hierarchy_set_operator_sell(mlamg_hierarchy_t h, int level, const int 
         return set_error(MLAMG_EINVAL, "set_operator_sell: set the CSR operator of the level first");
     LevelData &lev = h->lv[level];
     lev.sell_ptr = slice_ptr; lev.sell_col = scol; lev.sell_val = sval;
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    invalidate_graphs(h);
     return MLAMG_OK;
 }
 
@@ -336,7 +342,7 @@ int mlamg_hierarchy_set_operator_scaled(mlamg_hierarchy_t h, int level, const vo
     if (level < 0 || level >= (int)h->lv.size() || !h->lv[level].has_A)
         return set_error(MLAMG_EINVAL, "set_operator_scaled: set the CSR operator of the level first");
     h->lv[level].val_scaled = val_scaled;
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    invalidate_graphs(h);
     return MLAMG_OK;
 }
 
@@ -348,7 +354,7 @@ int mlamg_hierarchy_set_post_operator(mlamg_hierarchy_t h, int level, int q_nnz,
     if (!lev.has_A) return set_error(MLAMG_EINVAL, "set_post_operator: set the level operator first");
     lev.Q.n = lev.A.n; lev.Q.nnz = q_nnz; lev.Q.rowptr = q_rowptr; lev.Q.col = q_col; lev.Q.val = q_val;
     lev.has_Q = q_rowptr != nullptr;
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    invalidate_graphs(h);
     return MLAMG_OK;
 }
 
@@ -362,7 +368,7 @@ int mlamg_hierarchy_set_w32(mlamg_hierarchy_t h, int level, const int *a_col, co
         return set_error(MLAMG_EINVAL, "set_w32: col and val copies come in pairs");
     lev.w32_a_col = a_col; lev.w32_a_val = a_val_scaled;
     lev.w32_q_col = q_col; lev.w32_q_val = q_val;
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    invalidate_graphs(h);
     return MLAMG_OK;
 }
 

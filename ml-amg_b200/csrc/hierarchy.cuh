@@ -110,4 +110,5 @@ int vcycle_dispatch(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2
 // the same through the handle's CUDA-graph cache when use_graph is set
 int vcycle_run(mlamg_hierarchy *h, const void *b, void *x, int nu1, int nu2, int zero_guess, cudaStream_t s);
 void solver_state_free(mlamg_hierarchy *h);
+void solver_graphs_reset(mlamg_hierarchy *h);      // drop the cached PCG / stationary loop graphs (operators changed)
 }  // namespace mlamg

@@ -66,6 +66,12 @@ void solver_state_free(mlamg_hierarchy *h) {
     h->solver = nullptr;
 }
 
+void solver_graphs_reset(mlamg_hierarchy *h) {
+    if (!h->solver) return;
+    h->solver->pcg.reset();
+    h->solver->sol.reset();
+}
+
 static int ensure_state(mlamg_hierarchy *h, int maxiter) {
     if (!h->solver) {
         SolverState *S = new SolverState();
