@@ -452,7 +452,7 @@ def build_hierarchy(A, *, aggregates="lloyd", ratio=0.1, distance="unit", maxite
     fallback    : None -> stop coarsening when the list of external aggregates is exhausted;
                   'lloyd' -> continue with Lloyd + smoothed aggregation below the learned levels
     P_hat       : optional list of per-level weights on A_l's pattern (learned P = P_hat Agg)
-    lam_max     : |lambda_max(D^-1 A)| per level: None -> on-device power iteration; float, list or
+    lam_max     : |lambda_max(D^-1 A)| per level: None -> on the device (Lanczos, core.lambda_max); float, list or
                   callable(DeviceCSR) -> supplied (parity runs pass the oracle's value)
     """
     core.require_cuda()
