@@ -60,9 +60,12 @@ __device__ __forceinline__ double row_epilogue(long long row, T sum, const T *__
 // HALO: columns >= halo.n_own are read in place from a peer channel's receive region (values written by the
 // neighbouring GPUs over NVLink, each carrying a sequence tag; the load spins on the few that have not landed).
 template <typename T, int LANES, int OP, bool NORM, bool HALO, int NBT>
-// 32 registers / 8 CTAs per SM for every variant with <= 4 entries in flight per lane (none spills): the row ops are
-// latency-bound gathers, occupancy is what hides them (restriction 136 -> 126 us with 8 instead of 6 CTAs per SM)
-__global__ void __launch_bounds__(ROW_THREADS, NBT <= 4 ? 8 : 4)
+// 32 registers / 8 CTAs per SM for every non-halo variant with <= 4 entries in flight per lane (none spills): the row ops
+// are latency-bound gathers, occupancy is what hides them (restriction 136 -> 126 us with 8 instead of 6 CTAs per SM).  The
+// halo-gathering variants stay at 6 CTAs per SM: at 32 registers they spill inside the entry loop (ptxas: 12-76 bytes), and the
+// boundary rows they process run beside the interior kernel, where every wasted instruction is taken from it (2 GPUs,
+// sustained: 0.908 vs 0.918-0.928 ms per cycle)
+__global__ void __launch_bounds__(ROW_THREADS, (!HALO && NBT <= 4) ? 8 : (NBT <= 4 ? 6 : 4))
 csr_rowop_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
                  const T *__restrict__ val, const T *__restrict__ x, const T *__restrict__ b,
                  const T *__restrict__ dw, T *y, double *__restrict__ partial,
