@@ -411,14 +411,9 @@ def run_ours_distributed(args, rank, world, local, cpus=None):
     from mlamg import core, distributed as md
     n = args.n
     comm = md.Comm()
-    parity = None
-    if args.parity_n > 0:
-        try:
-            parity = dist_parity(args, comm)
-        except Exception as exc:        # noqa: BLE001  an infrastructure failure of the checker is reported, not hidden;
-            # every rank reaches this point or none does (the check is collective), so the run can go on to the timing
-            parity = {"ok": None, "error": f"{type(exc).__name__}: {exc}"[:300]}
-    if parity is not None and parity["ok"] is False:
+    parity = dist_parity(args, comm) if args.parity_n > 0 else None      # an exception here ends the run at once (a rank
+    # that swallowed it would leave its peers waiting in the checker's collectives)
+    if parity is not None and not parity["ok"]:
         if rank == 0:
             print(json.dumps({"error": "multi-GPU parity check failed; nothing was timed", "parity": parity}), flush=True)
         dist.barrier()
