@@ -260,9 +260,10 @@ def mlamg_amg_2_v(A, P, A_H_lu_solve, Dinv_w, b, x, amg_rtol=1e-8, pre_smoothing
     return x, it + 1
 
 
-def amg_loss_forward(P, A, test_vecs, tot_num_loop=5, no_prerelax=1, no_postrelax=1):
-    """ns/model/loss.py:32-96, forward value only (no autograd, no neumann fix):
-    fp32 iterates, fp64 coarse solve, softmax-weighted per-column convergence factor."""
+def amg_loss_forward(P, A, test_vecs, tot_num_loop=5, no_prerelax=1, no_postrelax=1, neumann_solve_fix=False):
+    """ns/model/loss.py:32-96, forward value only (no autograd): fp32 iterates, fp64 coarse solve, softmax-weighted
+    per-column convergence factor.  neumann_solve_fix: the coarse operator is bordered with a Lagrange row / column of
+    ones (`add_lagrange_rowcols` :11-27, `add_lagrange_vec` :29-30) so that the constant null space is handled."""
     A = sp.csr_matrix(A).astype(np.float32)
     P = sp.csr_matrix(P).astype(np.float32)
     omega = 2.0 / 3.0
@@ -276,12 +277,20 @@ def amg_loss_forward(P, A, test_vecs, tot_num_loop=5, no_prerelax=1, no_postrela
     else:
         x = test_vecs.astype(np.float32)
     errs = np.zeros((tot_num_loop + 1, x.shape[1]), dtype=np.float32)
+    if neumann_solve_fix:
+        k = A_H.shape[0]
+        ones = np.ones((k, 1))
+        A_H = sp.bmat([[A_H, sp.csr_matrix(ones)], [sp.csr_matrix(ones.T), None]], format="csc")      # (k+1) x (k+1)
     solve = spla.factorized(sp.csc_matrix(A_H))
     for it in range(tot_num_loop + 1):
         for _ in range(no_prerelax):
             x = x - Dinv_v[:, None] * (A @ x)
         r_H = P.T @ (A @ x)
+        if neumann_solve_fix:
+            r_H = np.vstack([r_H, np.zeros((1, r_H.shape[1]), dtype=r_H.dtype)])
         e_H = np.stack([solve(-r_H[:, c].astype(np.float64)) for c in range(x.shape[1])], axis=1).astype(np.float32)
+        if neumann_solve_fix:
+            e_H = e_H[:-1]
         x = x + P @ e_H
         for _ in range(no_postrelax):
             x = x - Dinv_v[:, None] * (A @ x)

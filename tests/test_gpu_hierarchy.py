@@ -245,6 +245,15 @@ def test_amg_loss_forward_and_torch_twins():
     ref = rp.amg_2_v_torch_like(A.astype(np.float32), P.astype(np.float32), np.zeros(n, dtype=np.float32), x0, jacobi_weight=2 / 3)
     assert abs(float(cf) - float(ref)) <= 1e-3 * abs(float(ref))
     assert nsp.torch_to_scipy(A_T).shape == A.shape
+    # neumann_solve_fix: singular operator (graph Laplacian, constant null space), Lagrange-bordered coarse solve (:11-30, :66-82)
+    G = sp.csr_matrix(oml.poisson((12, 11)))
+    G = G - sp.diags(G.diagonal())
+    L = (sp.diags(-np.asarray(G.sum(axis=1)).ravel()) + G).tocsr()
+    Agg, _, _ = rp.lloyd_aggregation(L, ratio=0.15, distance="unit", rand=0)
+    Pn = sp.csr_matrix(rp.smoothed_aggregation_jacobi(L, Agg, omega=2.0 / 3.0))
+    val_n = float(loss.amg_loss(nsp.to_torch_sparse(Pn), nsp.to_torch_sparse(L), 6, tot_num_loop=5, neumann_solve_fix=True))
+    ref_n, _ = rp.amg_loss_forward(Pn, L, 6, tot_num_loop=5, neumann_solve_fix=True)
+    assert abs(val_n - ref_n) <= 5e-4 * abs(ref_n), (val_n, ref_n)
 
 
 class _FakeVec:
