@@ -143,3 +143,17 @@ def test_gmres_restatement_converges_and_matches_a_direct_solve():
     one = [lv[0]]                                                  # single level = exact coarse solve as the preconditioner
     x, res, it = oml.gmres(one, b, tol=1e-10, maxiter=10)
     assert it <= 1 and np.abs(x - xd).max() <= 1e-9 * np.abs(xd).max()
+
+
+def test_amg_loss_oracle_neumann_fix_handles_the_constant_null_space():
+    """ns/model/loss.py:11-30,66-82 restated: on a singular operator (graph Laplacian) the bordered coarse solve gives a
+    finite convergence estimate below 1, and on a regular operator it agrees with the plain solve up to the mean removal"""
+    from oracle import multilevel as oml
+    G = sp.csr_matrix(oml.poisson((12, 11)))
+    G = G - sp.diags(G.diagonal())
+    L = (sp.diags(-np.asarray(G.sum(axis=1)).ravel()) + G).tocsr()
+    Agg, _, _ = rp.lloyd_aggregation(L, ratio=0.15, distance="unit", rand=0)
+    P = sp.csr_matrix(rp.smoothed_aggregation_jacobi(L, Agg, omega=2.0 / 3.0))
+    assert np.abs(P @ np.ones(P.shape[1]) - 1.0).max() < 1e-12          # the coarse space reproduces the null space
+    val, errs = rp.amg_loss_forward(P, L, 6, tot_num_loop=5, neumann_solve_fix=True)
+    assert np.isfinite(val) and 0.0 < val < 1.0 and np.all(np.diff(errs, axis=0) < 0)
