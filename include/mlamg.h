@@ -146,6 +146,21 @@ int mlamg_set_csr_batch(int nb);
 /* multi-vector forms (N x k row-major block), loss.py:72,75,85,88 */
 int mlamg_spmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *val,
                    const void *X, void *Y, double alpha, double beta, mlamg_stream_t stream);
+/* Backward pass of the multi-vector loss (loss.py:95-96 `loss` -> `.backward()`, demos/1d_poisson.py:91-95;
+ * the reference gets these from torch_sparse's autograd).  All blocks row-major.
+ * SDDMM on a CSR pattern: out[j] = <U[row(j), 0..k), V[col(j), 0..k)>.  Gradient of the stored values of S in
+ * Y = S X (U = dL/dY, V = X) and in Y = S^T X (U = X, V = dL/dY). */
+int mlamg_sddmm_csr(int dtype, int n, int k, const int *rowptr, const int *col, const void *U, const void *V,
+                    void *out, mlamg_stream_t stream);
+/* out[j] = dense[row(j) * ncols + col(j)]: gradient of P's stored values in A_H = P^T A P from the dense
+ * N x k block A P G^T + A^T P G (loss.py:53-54 backward). */
+int mlamg_csr_sample_dense(int dtype, int n, int ncols, const int *rowptr, const int *col, const void *dense,
+                           void *out, mlamg_stream_t stream);
+/* gradient of P_hat (values on A's pattern) in P = P_hat Agg (agg_interp.py:481-484 backward):
+ * g_phat[j] = g_p[entry (row(j), labels[col(j)]) of P], 0 when labels[col(j)] < 0. */
+int mlamg_agg_product_backward(int dtype, int n, const int *a_rowptr, const int *a_col, const int *labels,
+                               const int *p_rowptr, const int *p_col, const void *g_p, void *g_phat,
+                               mlamg_stream_t stream);
 
 /* small BLAS-1 helpers used by the cycle / PCG drivers (deterministic reductions) */
 int mlamg_axpby(int dtype, int n, double alpha, const void *x, double beta, void *y, mlamg_stream_t stream);

@@ -39,6 +39,9 @@ SIGNATURES = {
     "mlamg_set_csr_batch": (I, [I]),
     "mlamg_hierarchy_set_operator_sell": (I, [P, I, P, P, P]),
     "mlamg_spmm_csr": (I, [I, I, I, P, P, P, P, P, D, D, P]),
+    "mlamg_sddmm_csr": (I, [I, I, I, P, P, P, P, P, P]),
+    "mlamg_csr_sample_dense": (I, [I, I, I, P, P, P, P, P]),
+    "mlamg_agg_product_backward": (I, [I, I, P, P, P, P, P, P, P, P]),
     "mlamg_axpby": (I, [I, I, D, P, D, P, P]),
     "mlamg_dot": (I, [I, I, P, P, P, P]),
     "mlamg_gs_schedule": (I, [I, P, P, P, P, P, P, P]),

@@ -88,22 +88,23 @@ class DeviceCSR:
                    torch.from_numpy(data).to(device=device, dtype=dtype).contiguous(), shape)
 
     @classmethod
-    def from_torch(cls, A, dtype=None):
+    def from_torch(cls, A, dtype=None, device="cuda"):
         """torch sparse COO/CSR (any device) -> DeviceCSR.  Indices are integer tensors (the
-        reference's float-typed indices, ns/lib/sparse.py:26-30, are not reproduced)."""
+        reference's float-typed indices, ns/lib/sparse.py:26-30, are not reproduced).  The stored values keep
+        their autograd link to A (a coalesced COO tensor that requires grad: mlamg.autograd, ns/model/loss.py)."""
         require_cuda()
         if A.layout == torch.sparse_coo:
-            A = A.coalesce().to("cuda")
+            A = A.coalesce().to(device)
             idx = A.indices()
             n, m = A.shape
             counts = torch.bincount(idx[0], minlength=n)
-            rowptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+            rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
             rowptr[1:] = torch.cumsum(counts, 0)
             val = A.values()
             return cls(rowptr.to(torch.int32), idx[1].to(torch.int32).contiguous(),
                        val.to(dtype or val.dtype).contiguous(), (n, m))
         if A.layout == torch.sparse_csr:
-            A = A.to("cuda")
+            A = A.to(device)
             val = A.values()
             return cls(A.crow_indices().to(torch.int32).contiguous(), A.col_indices().to(torch.int32).contiguous(),
                        val.to(dtype or val.dtype).contiguous(), A.shape)
@@ -392,6 +393,53 @@ def spmm(A, X, alpha=1.0, beta=0.0, out=None):
         out = torch.zeros(n, k, dtype=A.dtype, device=X.device)
     check(lib.mlamg_spmm_csr(dt(A.val), n, k, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(X), ptr(out), float(alpha),
                              float(beta), stream()))
+    return out
+
+
+def sddmm(S, U, V):
+    """out[j] = <U[row(j), :], V[col(j), :]> on the pattern of S: the gradient of S's stored values in S X / S^T X
+    (backward pass of ns/model/loss.py's multi-vector cycle)."""
+    n, m = S.shape
+    assert U.dim() == 2 and V.dim() == 2 and U.shape == (n, V.shape[1]) and V.shape[0] == m
+    assert U.is_contiguous() and V.is_contiguous() and U.dtype == V.dtype
+    out = torch.empty(S.nnz, dtype=U.dtype, device=U.device)
+    check(lib.mlamg_sddmm_csr(dt(U), n, U.shape[1], ptr(S.rowptr), ptr(S.col), ptr(U), ptr(V), ptr(out), stream()))
+    return out
+
+
+def sample_dense(S, Dm):
+    """out[j] = Dm[row(j), col(j)] on the pattern of S (Dm: dense S.shape block, row-major)."""
+    n, m = S.shape
+    assert Dm.shape == (n, m) and Dm.is_contiguous()
+    out = torch.empty(S.nnz, dtype=Dm.dtype, device=Dm.device)
+    check(lib.mlamg_csr_sample_dense(dt(Dm), n, m, ptr(S.rowptr), ptr(S.col), ptr(Dm), ptr(out), stream()))
+    return out
+
+
+def agg_product_backward(A, labels, P, g_p):
+    """gradient of P_hat's values (on A's pattern) in P = P_hat Agg, given the gradient of P's stored values"""
+    assert g_p.is_contiguous() and g_p.numel() == P.nnz
+    out = torch.empty(A.nnz, dtype=g_p.dtype, device=g_p.device)
+    check(lib.mlamg_agg_product_backward(dt(g_p), A.shape[0], ptr(A.rowptr), ptr(A.col), ptr(labels), ptr(P.rowptr),
+                                         ptr(P.col), ptr(g_p), ptr(out), stream()))
+    return out
+
+
+def csr_to_dense(A):
+    """square DeviceCSR -> dense row-major block in A's dtype"""
+    n = A.shape[0]
+    assert A.shape[0] == A.shape[1]
+    dense = torch.empty(n, n, dtype=A.dtype, device=A.val.device)
+    check(lib.mlamg_csr_to_dense(dt(A.val), n, ptr(A.rowptr), ptr(A.col), ptr(A.val), ptr(dense), stream()))
+    return dense
+
+
+def dense_inverse_f64(dense):
+    """inverse of a dense fp64 block (LU with partial pivoting, cuSOLVER); the argument is left untouched"""
+    n = dense.shape[0]
+    out = dense.detach().clone().contiguous()
+    work = torch.empty_like(out)
+    check(lib.mlamg_dense_inverse_f64(n, ptr(out), ptr(work), stream()))
     return out
 
 

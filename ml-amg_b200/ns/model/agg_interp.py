@@ -45,13 +45,18 @@ def bellman_ford_aggregates(A, top_k, BF_edges):
 
 def learned_prolongator(A, P_hat_edges, labels, k):
     """:481-484.  P_hat = PNet edge weights on A's pattern; P = P_hat Agg (explicit zeros kept, as
-    `torch.sparse.mm(...).coalesce()` keeps them).  -> (P_T torch sparse COO on the device, P DeviceCSR)"""
+    `torch.sparse.mm(...).coalesce()` keeps them).  -> (P_T torch sparse COO on the device, P DeviceCSR).
+    Differentiable in P_hat_edges (a tensor that requires grad), like the reference's `torch.sparse.mm`."""
     core.require_cuda()
     Ad = _pattern(A)
     ph = core.as_vec(P_hat_edges, P_hat_edges.dtype if isinstance(P_hat_edges, torch.Tensor) else
                      {np.dtype(np.float32): torch.float32}.get(np.asarray(P_hat_edges).dtype, torch.float64))
+    labels = core.as_i32(labels, ph.device)
     Agg = core.agg_from_labels(labels, int(k), ph.dtype)
-    P = mlamg.learned_prolongator(Ad.with_values(ph), Agg)
+    P = mlamg.learned_prolongator(Ad.with_values(ph.detach()), Agg)
+    if ph.requires_grad:                       # training: the gradient of P's values flows back onto the PNet's edge outputs
+        from mlamg import autograd as ag
+        P = P.with_values(ag.agg_product_values(ph, P, Ad, labels))
     return P.to_torch_coo(), P
 
 

@@ -157,3 +157,20 @@ def test_amg_loss_oracle_neumann_fix_handles_the_constant_null_space():
     assert np.abs(P @ np.ones(P.shape[1]) - 1.0).max() < 1e-12          # the coarse space reproduces the null space
     val, errs = rp.amg_loss_forward(P, L, 6, tot_num_loop=5, neumann_solve_fix=True)
     assert np.isfinite(val) and 0.0 < val < 1.0 and np.all(np.diff(errs, axis=0) < 0)
+
+
+@pytest.mark.parametrize("name", ["poisson1d_9", "neumann1d_9", "poisson2d_14", "poisson3d_6x6x5_nu2"])
+def test_amg_loss_oracle_matches_the_unmodified_reference(name):
+    """ns/model/loss.py:32-96 restated vs the loss value the reference's own `amg_loss` returned
+    (tests/golden/make_golden_loss.py: the 9-node 1-D problem of demos/1d_poisson.py, its Neumann twin with the
+    Lagrange-bordered coarse solve, 2-D / 3-D Poisson with Lloyd aggregates, nu = 1 and 2)"""
+    import os
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"ref_amg_loss_{name}.npz"))
+    n, k = int(z["n"]), int(z["k"])
+    A = sp.csr_matrix((z["A_data"], z["A_indices"], z["A_indptr"]), shape=(n, n))
+    P = sp.csr_matrix((z["P_val"], (z["P_row"], z["P_col"])), shape=(n, k))
+    kw = {key[3:]: int(z[key]) for key in z.files if key.startswith("kw_")}
+    val, _ = rp.amg_loss_forward(P, A, z["test_vecs"], neumann_solve_fix=bool(z["neumann"]), **kw)
+    assert abs(val - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    assert abs(float(z["loss_alt"]) - float(z["loss"])) <= 1e-6 * float(z["loss"])      # the reference's own fp32 noise floor
