@@ -203,3 +203,29 @@ def test_gradient_reaches_the_edge_outputs_through_P_hat_times_Agg(cpu_kernels):
     print(f"P_hat gradient: max err {(ph.grad - ph2.grad).abs().max().item():.2e} of scale {scale:.2e}")
     assert (ph.grad - ph2.grad).abs().max().item() <= 1e-3 * scale
     assert P_T.shape == (n, k)
+
+
+def test_descent_on_the_edge_weights_lowers_the_loss(cpu_kernels):
+    """demos/1d_poisson.py:84-101 without the PNet (torch_geometric is absent): Adam on the P_hat edge values of the
+    9-node problem, starting from the smoothed-aggregation weights perturbed — the loss the optimiser sees must go down"""
+    import ns.model.loss as loss
+    import ns.model.agg_interp as ai
+    z, A, P, kw = load("poisson1d_9")
+    n, k = P.shape
+    labels = torch.from_numpy(np.repeat(np.arange(k), n // k).astype(np.int32))
+    S = sp.csr_matrix(sp.eye(n) - (2.0 / 3.0) * sp.diags(1.0 / A.diagonal()) @ A)        # I - omega D^-1 A on A's pattern
+    S.sort_indices()
+    assert np.array_equal(S.indices, A.indices)
+    ph = torch.from_numpy((S.data * (1.0 + 0.5 * np.random.RandomState(0).randn(S.nnz))).astype(np.float32)).requires_grad_(True)
+    Ad = _dev(A, torch.float32)
+    tv = torch.from_numpy(z["test_vecs"].copy())
+    opt = torch.optim.Adam([ph], lr=0.02)
+    hist = []
+    for _ in range(25):
+        opt.zero_grad()
+        _, Pd = ai.learned_prolongator(Ad, ph, labels, k)
+        val = loss.amg_loss(Pd, Ad, tv, tot_num_loop=10)
+        val.backward()
+        opt.step()
+        hist.append(float(val.detach()))
+    assert hist[-1] < 0.8 * hist[0], hist

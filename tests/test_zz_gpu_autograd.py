@@ -145,3 +145,30 @@ def test_forward_only_inputs_still_work_and_A_stays_constant():
     val = loss.amg_loss(P.astype(np.float32), A, torch.from_numpy(z["test_vecs"].copy()), **kw)        # scipy in, no gradient asked
     assert not val.requires_grad
     assert abs(float(val) - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+
+
+def test_descent_on_the_edge_weights_lowers_the_loss():
+    """demos/1d_poisson.py:84-101 without the PNet (torch_geometric is absent): Adam on the P_hat edge values of the
+    9-node problem, starting from the smoothed-aggregation weights perturbed — the loss the optimiser sees must go down"""
+    import ns.model.loss as loss
+    import ns.model.agg_interp as ai
+    import mlamg
+    z, A, P, kw = load("poisson1d_9")
+    n, k = P.shape
+    labels = torch.from_numpy(np.repeat(np.arange(k), n // k).astype(np.int32)).cuda()
+    S = sp.csr_matrix(sp.eye(n) - (2.0 / 3.0) * sp.diags(1.0 / A.diagonal()) @ A)        # I - omega D^-1 A on A's pattern
+    S.sort_indices()
+    assert np.array_equal(S.indices, A.indices)
+    ph = torch.from_numpy((S.data * (1.0 + 0.5 * np.random.RandomState(0).randn(S.nnz))).astype(np.float32)).cuda().requires_grad_(True)
+    Ad = mlamg.DeviceCSR.from_scipy(A, torch.float32)
+    tv = torch.from_numpy(z["test_vecs"].copy()).cuda()
+    opt = torch.optim.Adam([ph], lr=0.02)
+    hist = []
+    for _ in range(25):
+        opt.zero_grad()
+        _, Pd = ai.learned_prolongator(Ad, ph, labels, k)
+        val = loss.amg_loss(Pd, Ad, tv, tot_num_loop=10)
+        val.backward()
+        opt.step()
+        hist.append(float(val.detach()))
+    assert hist[-1] < 0.8 * hist[0], hist
