@@ -224,6 +224,36 @@ int mlamg_dense_inverse_f64(int n, double *a, double *work, mlamg_stream_t strea
 /* y = M x, M dense n x n row-major */
 int mlamg_gemv(int dtype, int n, const void *m, const void *x, void *y, mlamg_stream_t stream);
 
+/* ---- evolution strength of connection (pyamg.strength.evolution_strength_of_connection with its defaults; the
+ * reference's 'evolution' and DEFAULT 'olson' measures, utils/common.py:27,30,58).  One kernel per step of the pyamg
+ * evaluation, arithmetic non-fused and in pyamg's order (same bits as the CPU evaluation for the same rho).
+ * S = I - inv_rho * D^-1 A on A's pattern (A must store its diagonal: *flags |= 1 otherwise); dinv_a_val (may be
+ * NULL) receives the values of D^-1 A. */
+int mlamg_evolution_step(int dtype, int n, const int *rowptr, const int *col, const void *val, double inv_rho,
+                         void *s_val, void *dinv_a_val, int *flags, mlamg_stream_t stream);
+/* amg_core incomplete_mat_mult_csr: S(i,j) = <A(i,:), B(:,j)> for (i,j) in S's pattern; A in CSR, B in CSC (= the
+ * CSR arrays of B^T), indices sorted; products summed in increasing inner index. */
+int mlamg_incomplete_matmul_csr(int dtype, int n, const int *Ap, const int *Aj, const void *Ax, const int *Bp,
+                                const int *Bj, const void *Bx, const int *Sp, const int *Sj, void *Sx,
+                                mlamg_stream_t stream);
+/* in place: z_ij -> |1 - z_ii / z_ij|, 0 for weak ratios (< 1e-4), obtuse angles and stored zeros, 1e-4 for
+ * near-perfect connections (< sqrt(eps)) */
+int mlamg_evolution_measure(int dtype, int n, const int *rowptr, const int *col, void *val, mlamg_stream_t stream);
+/* amg_core apply_distance_filter, in place: off-diagonals >= epsilon * (smallest off-diagonal of the row) -> 0 */
+int mlamg_distance_filter(int dtype, int n, double epsilon, const int *rowptr, const int *col, void *val,
+                          mlamg_stream_t stream);
+/* out (on A's pattern-symmetric pattern) = 0.5 (M + M^T) [symmetrize != 0] or M, unit diagonal; 0 where neither
+ * M nor M^T stores the entry */
+int mlamg_evolution_symmetrize(int dtype, int n, const int *a_rowptr, const int *a_col, const int *m_rowptr,
+                               const int *m_col, const void *m_val, int symmetrize, void *out,
+                               mlamg_stream_t stream);
+/* in place: v -> 1/v, then every row times the reciprocal of its largest |entry| (scale_rows_by_largest_entry) */
+int mlamg_invert_scale_rows(int dtype, int n, const int *rowptr, void *val, mlamg_stream_t stream);
+/* out[j] = E(row(j), col(j)) + w[j] where E stores that entry, w[j] otherwise (E's pattern inside A's):
+ * `evolution(A) + W` of utils/common.py:27,30 */
+int mlamg_csr_pattern_add(int dtype, int n, const int *a_rowptr, const int *a_col, const void *w, const int *e_rowptr,
+                          const int *e_col, const void *e_val, void *out, mlamg_stream_t stream);
+
 /* |lambda_max(D^-1 A)| to a reported accuracy (replaces ARPACK `eigs(Dinv@A, k=1, which='LM')`, multigrid.py:105).
  * symmetric: 1 = A is symmetric, 0 = it is not, -1 = test it (two SpMVs).  Symmetric A with a positive diagonal:
  * Lanczos on D^-1/2 A D^-1/2, stopped when the eigenvalue error estimate min(res, res^2/gap) <= tol*lambda (res = exact

@@ -42,6 +42,13 @@ SIGNATURES = {
     "mlamg_sddmm_csr": (I, [I, I, I, P, P, P, P, P, P]),
     "mlamg_csr_sample_dense": (I, [I, I, I, P, P, P, P, P]),
     "mlamg_agg_product_backward": (I, [I, I, P, P, P, P, P, P, P, P]),
+    "mlamg_evolution_step": (I, [I, I, P, P, P, D, P, P, P, P]),
+    "mlamg_incomplete_matmul_csr": (I, [I, I, P, P, P, P, P, P, P, P, P, P]),
+    "mlamg_evolution_measure": (I, [I, I, P, P, P, P]),
+    "mlamg_distance_filter": (I, [I, I, D, P, P, P, P]),
+    "mlamg_evolution_symmetrize": (I, [I, I, P, P, P, P, P, I, P, P]),
+    "mlamg_invert_scale_rows": (I, [I, I, P, P, P]),
+    "mlamg_csr_pattern_add": (I, [I, I, P, P, P, P, P, P, P, P]),
     "mlamg_axpby": (I, [I, I, D, P, D, P, P]),
     "mlamg_dot": (I, [I, I, P, P, P, P]),
     "mlamg_gs_schedule": (I, [I, P, P, P, P, P, P, P]),

@@ -1,15 +1,15 @@
 """Mirror of the reference's evaluation helpers (/root/reference/utils/common.py:24-111) — the canonical
 call sequences of the hot path — running on the B200 modules under `ml-amg_b200/ns`.
 
-  strength_measure_funcs   :24-30   'abs', 'invabs', 'unit' (host CSR in, host CSR out, as in the reference);
-                                    'evolution' / 'olson' need pyamg's evolution strength of connection, which is
-                                    not on the built path: they raise NotImplementedError
+  strength_measure_funcs   :24-30   'abs', 'invabs', 'unit', 'evolution', 'olson' (host CSR in, host CSR out, as in the
+                                    reference); the two pyamg-based measures run pyamg's evolution strength of connection
+                                    on the device (mlamg/strength.py, csrc/strength.cu), incl. its Arnoldi estimate of
+                                    rho(D^-1 A) from numpy's global stream — callers seed it exactly as the reference does
   evaluate_dataset         :40-82   Lloyd aggregates + SA prolongator (or a model's learned P) -> two-grid
                                     convergence factor per grid
   evaluate_ref_conv        :84-111  the same with the baseline strength measure
 
-Differences: without `S`, `evaluate_dataset` falls back to 'invabs' (the reference's default 'olson' adds pyamg's
-evolution measure to it); an optional trailing `lam_max` (callable A -> |lambda_max(D^-1 A)|) lets a parity run inject the
+Differences: an optional trailing `lam_max` (callable A -> |lambda_max(D^-1 A)|) lets a parity run inject the
 oracle's spectral radius (the reference calls ARPACK); plotting on failure is dropped.
 """
 import traceback
@@ -24,7 +24,15 @@ import ns.lib.sparse_tensor
 
 
 def _evolution(A):
-    raise NotImplementedError("pyamg.strength.evolution_strength_of_connection is not on the built path")
+    """:27  pyamg.strength.evolution_strength_of_connection(A) + 0.1 * pattern(A)"""
+    from mlamg import strength
+    return strength.evolution_measure_plus_pattern(sp.csr_matrix(A)).to_scipy()
+
+
+def _olson(A):
+    """:30  pyamg.strength.evolution_strength_of_connection(A) + 1/|A|  (the default of evaluate_dataset, :52)"""
+    from mlamg import strength
+    return strength.olson_measure(sp.csr_matrix(A)).to_scipy()
 
 
 strength_measure_funcs = {
@@ -32,7 +40,7 @@ strength_measure_funcs = {
     'evolution': _evolution,
     'invabs': lambda A: sp.csr_matrix((1.0 / np.abs(A.data), A.indices, A.indptr), A.shape),
     'unit': lambda A: sp.csr_matrix((np.ones_like(A.data), A.indices, A.indptr), A.shape),
-    'olson': _evolution,
+    'olson': _olson,
 }
 
 
@@ -57,7 +65,6 @@ def evaluate_dataset(weights, dataset, model=None, S=None, neumann_solve=False, 
     for i in range(len(dataset)):
         A = dataset[i].A
         np.random.seed(0)
-        C = strength_measure_funcs['invabs'](A) if S is None else S(A)
         if model is not None:
             try:
                 agg_T, P_T = model.forward(A, alpha)[:2]
@@ -67,6 +74,8 @@ def evaluate_dataset(weights, dataset, model=None, S=None, neumann_solve=False, 
                 conv[i] = 1.0
                 continue
         else:
+            # :51-58 (the reference also builds the Lloyd aggregates when a model is given, and never uses them)
+            C = strength_measure_funcs['olson'](A) if S is None else S(A)
             L_Agg, _, _ = ns.lib.graph.lloyd_aggregation(C, ratio=alpha, distance='same', rand=0)
             P = ns.lib.multigrid.smoothed_aggregation_jacobi(A, L_Agg, lam_max=None if lam_max is None else lam_max(A))
         x = np.random.RandomState(0).randn(A.shape[1])

@@ -186,3 +186,63 @@ int oracle_modified_bf_##SUF(int n, long long nnz, const long long *row,        
 }
 DEFINE_MBF(float, float, f32)
 DEFINE_MBF(double, double, f64)
+
+/*
+ * pyamg 4.x strength-of-connection helpers behind
+ * `pyamg.strength.evolution_strength_of_connection` — called by the reference at
+ * /root/reference/utils/common.py:27,30 (`'evolution'` and the default `'olson'` measure).
+ * Restated from the published amg_core (`linalg.h` / `smoothed_aggregation.h` / `evolution_strength.h`);
+ * PARITY UNPINNED like the loops above.
+ *
+ *   incomplete_mat_mult_csr : S(i,j) = <A(i,:), B(:,j)> for (i,j) in the pattern of S only; A in CSR, B in CSC,
+ *                             both with sorted indices: a merge of the two index lists, products summed in
+ *                             increasing inner index, starting from 0.0.
+ *   apply_distance_filter   : per row, threshold = epsilon * (smallest off-diagonal value); every OFF-diagonal
+ *                             entry >= threshold is set to 0.
+ *   maximum_row_value       : largest |entry| of every row.
+ */
+void oracle_incomplete_mat_mult_csr_f64(const int *Ap, const int *Aj, const double *Ax,
+                                        const int *Bp, const int *Bj, const double *Bx,
+                                        const int *Sp, const int *Sj, double *Sx, int num_rows)
+{
+    for (int row = 0; row < num_rows; row++) {
+        for (int k = Sp[row]; k < Sp[row + 1]; k++) {
+            const int col = Sj[k];
+            double sum = 0.0;
+            int a = Ap[row], a_end = Ap[row + 1];
+            int b = Bp[col], b_end = Bp[col + 1];
+            while (a < a_end && b < b_end) {
+                const int ac = Aj[a], br = Bj[b];
+                if (ac == br) { sum += Ax[a] * Bx[b]; a++; b++; }
+                else if (ac < br) a++;
+                else b++;
+            }
+            Sx[k] = sum;
+        }
+    }
+}
+
+void oracle_apply_distance_filter_f64(int n_row, double epsilon, const int *Sp, const int *Sj, double *Sx)
+{
+    for (int i = 0; i < n_row; i++) {
+        double min_offdiagonal = DBL_MAX;
+        for (int jj = Sp[i]; jj < Sp[i + 1]; jj++)
+            if (Sj[jj] != i && Sx[jj] < min_offdiagonal) min_offdiagonal = Sx[jj];
+        const double threshold = epsilon * min_offdiagonal;
+        for (int jj = Sp[i]; jj < Sp[i + 1]; jj++)
+            if (Sx[jj] >= threshold && Sj[jj] != i) Sx[jj] = 0.0;
+    }
+}
+
+void oracle_maximum_row_value_f64(int n_row, double *x, const int *Sp, const int *Sj, const double *Sx)
+{
+    (void)Sj;
+    for (int i = 0; i < n_row; i++) {
+        double m = DBL_MIN;          /* std::numeric_limits<double>::min() in the original */
+        for (int jj = Sp[i]; jj < Sp[i + 1]; jj++) {
+            const double v = fabs(Sx[jj]);
+            if (v > m) m = v;
+        }
+        x[i] = m;
+    }
+}

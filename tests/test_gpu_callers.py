@@ -49,8 +49,8 @@ def test_evaluate_ref_conv_and_dataset_match_the_oracle_sequence():
     got = common.evaluate_dataset(None, grids, S=common.strength_measure_funcs["invabs"], alpha=0.2, lam_max=lambda A: lam)
     ref = [_oracle_conv(g.A, common.strength_measure_funcs["invabs"](g.A), 0.2, lam, 0) for g in grids]
     assert np.allclose(got, ref, rtol=0, atol=1e-9)
-    with pytest.raises(NotImplementedError):
-        common.strength_measure_funcs["olson"](grids[0].A)
+    C = common.strength_measure_funcs["olson"](grids[0].A)               # parity: tests/test_zz_gpu_strength.py
+    assert sp.isspmatrix_csr(C) and C.shape == grids[0].A.shape and C.nnz == grids[0].A.nnz
 
 
 def test_evaluate_dataset_with_a_model_tail():
