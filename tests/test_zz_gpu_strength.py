@@ -89,7 +89,7 @@ def test_every_kernel_against_its_contract(name):
     hm = strength.evolution_measure_(H).val.cpu().numpy()
     assert np.array_equal(hm, sr.evolution_measure(np.concatenate([hp, np.full(4, 5, np.int32)]), hj, hx))
     assert hm[0] == 0 and hm[1] == 0 and hm[2] == 0 and hm[3] == 0 and hm[4] == 1e-4
-    M = sp.csr_matrix((m_ref, A.indices, A.indptr), shape=A.shape)
+    M = sp.csr_matrix((m_ref, A.indices.copy(), A.indptr.copy()), shape=A.shape)      # copies: eliminate_zeros works in place
     M.eliminate_zeros()
     Md = mlamg.DeviceCSR.from_scipy(M)
     f = strength.distance_filter_(Md, 4.0).val.cpu().numpy()
@@ -101,7 +101,8 @@ def test_every_kernel_against_its_contract(name):
     for symm in (True, False):
         o = strength.symmetrize_on(Ad, Md, symm).val.cpu().numpy()
         assert np.array_equal(o, sr.evolution_symmetrize(A.indptr, A.indices, M.indptr, M.indices, M.data, symm))
-    O = sp.csr_matrix((sr.evolution_symmetrize(A.indptr, A.indices, M.indptr, M.indices, M.data, True), A.indices, A.indptr), shape=A.shape)
+    O = sp.csr_matrix((sr.evolution_symmetrize(A.indptr, A.indices, M.indptr, M.indices, M.data, True), A.indices.copy(), A.indptr.copy()),
+                      shape=A.shape)
     O.eliminate_zeros()
     Od = mlamg.DeviceCSR.from_scipy(O)
     inv_ref = sr.invert_scale_rows(O.indptr, O.data)
