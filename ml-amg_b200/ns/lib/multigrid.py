@@ -82,6 +82,28 @@ def gauss_seidel(A, b, x, L=None, U=None, nu=2):
     return xd.cpu().numpy()
 
 
+def gauss_seidel_torch(A, b, x, L=None, U=None, nu=2):
+    """Torch twin (reference :93-99): x <- tril(A)^-1 (b - U x), nu times, A a dense (or sparse) torch matrix, U its
+    strict upper triangle unless given.  Returns a new tensor on x's device; the sweeps run in the level-scheduled
+    Gauss-Seidel kernel on tril(A) + U."""
+    def host(M):
+        M = M.detach().cpu()
+        return M.to_dense().numpy() if M.layout != torch.strided else M.numpy()
+    Ah = host(A)
+    Lm = sp.csr_matrix(np.tril(Ah))
+    Um = sp.csr_matrix(np.triu(Ah, 1)) if U is None else sp.csr_matrix(host(U))
+    if sp.tril(Um, k=0).nnz:
+        raise ValueError('gauss_seidel_torch: U must be strictly upper triangular')
+    M = (Lm + Um).tocsr()
+    M.sort_indices()
+    Ad = core.DeviceCSR.from_scipy(M)
+    sched = core.GaussSeidelSchedule(Ad)
+    bd = b.detach().to(device="cuda", dtype=Ad.dtype).contiguous()
+    xd = x.detach().to(device="cuda", dtype=Ad.dtype).contiguous().clone()
+    sched.sweep(bd, xd, iterations=nu)
+    return xd.to(device=x.device, dtype=x.dtype)
+
+
 def smoothed_aggregation_jacobi(A, Agg, omega=None, lam_max=None):
     """P = (I - omega D^-1 A) Agg with omega = (4/3)/|lambda_max(D^-1 A)|; scipy CSR out."""
     Ad = core.DeviceCSR.wrap(A)

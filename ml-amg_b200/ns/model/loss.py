@@ -13,6 +13,23 @@ from mlamg import core
 from mlamg import autograd as ag
 
 
+def add_lagrange_rowcols(A, device='cpu'):
+    """:11-27  sparse COO [[A, 1], [1^T, 0]] (integer index tensors; the reference's are float-typed)"""
+    A = A.coalesce()
+    n, m = A.size()
+    dev = A.device
+    extra = torch.cat([torch.stack([torch.arange(n, device=dev), torch.full((n,), m, device=dev)]),
+                       torch.stack([torch.full((m,), n, device=dev), torch.arange(m, device=dev)])], dim=1)
+    return torch.sparse_coo_tensor(torch.cat((A.indices(), extra), dim=1),
+                                   torch.cat((A.values(), torch.ones(n + m, dtype=A.dtype, device=dev))),
+                                   (n + 1, m + 1)).coalesce()
+
+
+def add_lagrange_vec(x, device='cpu'):
+    """:29-30  one zero row under the block of right-hand sides"""
+    return torch.cat((x, torch.zeros(1, x.shape[1], dtype=x.dtype, device=x.device)), dim=0)
+
+
 def _lagrange_border(A_H):
     """[[A_H, 1], [1^T, 0]] (add_lagrange_rowcols, :11-27), dense fp64"""
     k = A_H.shape[0]
