@@ -174,3 +174,47 @@ def test_amg_loss_oracle_matches_the_unmodified_reference(name):
     val, _ = rp.amg_loss_forward(P, A, z["test_vecs"], neumann_solve_fix=bool(z["neumann"]), **kw)
     assert abs(val - float(z["loss"])) <= 1e-6 * float(z["loss"])
     assert abs(float(z["loss_alt"]) - float(z["loss"])) <= 1e-6 * float(z["loss"])      # the reference's own fp32 noise floor
+
+
+def _modes():
+    import os
+    from helpers import GOLDEN
+    return np.load(os.path.join(GOLDEN, "ref_two_level_modes.npz"))
+
+
+def test_two_level_driver_modes_match_the_unmodified_reference():
+    """ns/lib/multigrid.py in the modes the per-problem goldens do not cover (tests/golden/make_golden_modes.py):
+    error_tol measure, singular=True (lsqr + mean removal), missing tolerance, singular coarse operator, the scipy
+    Gauss-Seidel form and the fp32 torch twins"""
+    z = _modes()
+    A, P = csr_from(z, "A"), csr_from(z, "P")
+    n = A.shape[0]
+    x0, b2 = z["x0"], z["b2"]
+    x, conv, err, nit = rp.amg_2_v(A, P, np.zeros(n), x0, error_tol=1e-9)
+    assert nit == int(z["errtol_nit"]) and rel_hist_err(err, z["errtol_err"]) < 1e-12
+    assert abs(conv - float(z["errtol_conv"])) < 1e-10 and np.abs(x - z["errtol_x"]).max() < 1e-12
+    with pytest.raises(RuntimeError) as ei:
+        rp.amg_2_v(A, P, np.zeros(n), x0)
+    assert str(ei.value) == str(z["no_tol_message"]) == "One of res_tol or error_tol must be set!"
+    Pz = csr_from(z, "Pz")
+    xs, convs, errs, nits = rp.amg_2_v(A, Pz, np.zeros(n), x0, res_tol=1e-10)
+    assert convs == float(z["singcoarse_conv"]) == 1.0 and nits == int(z["singcoarse_nit"]) == 0 and bool(z["singcoarse_x_is_x0"])
+    assert np.array_equal(xs, x0)
+    xg = x0.copy()
+    pr.gauss_seidel(A, xg, b2, iterations=3)                      # pyamg's sweep == the reference's own triangular-solve form
+    assert np.abs(xg - z["gs_scipy_x"]).max() < 1e-13
+    # fp32 twins
+    A32, P32 = A.astype(np.float32), P.astype(np.float32)
+    xj = rp.jacobi_torch_like(A32, z["jacobi_torch_b"], x0.astype(np.float32), (1.0 / A32.diagonal()).astype(np.float32), omega=0.666, nu=3)
+    assert np.abs(xj - z["jacobi_torch_x"]).max() <= 2e-6 * np.abs(z["jacobi_torch_x"]).max()
+    cf = rp.amg_2_v_torch_like(A32, P32, np.zeros(n, dtype=np.float32), x0.astype(np.float32), jacobi_weight=2.0 / 3.0)
+    assert abs(float(cf) - float(z["amg_2_v_torch_conv"])) <= 1e-3 * float(z["amg_2_v_torch_conv"])
+    cf2 = rp.amg_2_v_torch_like(A32, P32, np.zeros(n, dtype=np.float32), x0.astype(np.float32), pre_smoothing_steps=2,
+                                post_smoothing_steps=2, jacobi_weight=0.5, max_iter=12)
+    assert abs(float(cf2) - float(z["amg_2_v_torch_conv_nu2"])) <= 1e-3 * float(z["amg_2_v_torch_conv_nu2"])
+    # singular=True on the Neumann problem
+    L, PN = csr_from(z, "L"), csr_from(z, "PN")
+    x, conv, err, nit = rp.amg_2_v(L, PN, np.zeros(L.shape[0]), z["xn0"], res_tol=1e-8, singular=True)
+    # lsqr stops at its default 1e-6 tolerances: the history is reproducible to about that accuracy only (stored-order of P^T A P changes
+    # the last bits of its matvecs), measured 1e-7
+    assert nit == int(z["sing_nit"]) and rel_hist_err(err, z["sing_err"]) < 2e-6 and abs(conv - float(z["sing_conv"])) < 1e-5

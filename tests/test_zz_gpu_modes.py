@@ -1,0 +1,40 @@
+"""GPU: the mirrored two-level drivers in the modes of tests/golden/ref_two_level_modes.npz — written by the UNMODIFIED
+reference (tests/golden/make_golden_modes.py): error_tol measure, singular coarse operator, singular=True, the scipy
+Gauss-Seidel form and the fp32 torch twins.  Same bars as tests/test_gpu_hierarchy.py holds against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, csr_from, hist_err0, rel_hist_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_level_driver_modes_vs_reference_golden():
+    import ns.lib.multigrid as mg
+    import ns.lib.sparse as nsp
+    z = np.load(os.path.join(GOLDEN, "ref_two_level_modes.npz"))
+    A, P = csr_from(z, "A"), csr_from(z, "P")
+    n = A.shape[0]
+    x0, b2 = z["x0"], z["b2"]
+    x, conv, err, nit = mg.amg_2_v(A, P, np.zeros(n), x0, error_tol=1e-9)            # reference smoother: exact Gauss-Seidel
+    assert nit == int(z["errtol_nit"]) and hist_err0(err, z["errtol_err"]) < 1e-12
+    assert rel_hist_err(err[:10], z["errtol_err"][:10]) < 1e-11 and abs(conv - float(z["errtol_conv"])) < 1e-9
+    assert np.abs(x - z["errtol_x"]).max() < 1e-12
+    out = mg.amg_2_v(A, csr_from(z, "Pz"), np.zeros(n), x0, res_tol=1e-10)            # singular coarse operator (:166-170)
+    assert out[1] == 1.0 and out[3] == 0 and np.array_equal(np.asarray(out[0]), x0)
+    xg = mg.gauss_seidel(A, b2, x0.copy(), nu=3)
+    assert np.abs(xg - z["gs_scipy_x"]).max() <= 1e-12 * np.abs(z["gs_scipy_x"]).max()
+    A_T, P_T = nsp.to_torch_sparse(A), nsp.to_torch_sparse(P)
+    xt = torch.from_numpy(x0.astype(np.float32))
+    Dinv = 1.0 / nsp.get_diagonal(A_T)
+    xj = mg.jacobi_torch(A_T, torch.from_numpy(z["jacobi_torch_b"]), xt.clone(), Dinv, omega=0.666, nu=3).numpy()
+    assert np.abs(xj - z["jacobi_torch_x"]).max() <= 1e-5 * np.abs(z["jacobi_torch_x"]).max()
+    cf = mg.amg_2_v_torch(A_T, P_T, torch.zeros(n), xt.clone(), jacobi_weight=2.0 / 3.0)
+    assert abs(float(cf) - float(z["amg_2_v_torch_conv"])) <= 1e-3 * float(z["amg_2_v_torch_conv"])
+    # singular=True: the exact pseudo-inverse here, lsqr at its default 1e-6 tolerances in the reference
+    L, PN = csr_from(z, "L"), csr_from(z, "PN")
+    got = mg.amg_2_v(L, PN, np.zeros(L.shape[0]), z["xn0"], res_tol=1e-8, singular=True)
+    assert abs(got[3] - int(z["sing_nit"])) <= 1 and hist_err0(got[2][:8], z["sing_err"][:8]) < 1e-4
