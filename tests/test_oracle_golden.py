@@ -218,3 +218,25 @@ def test_two_level_driver_modes_match_the_unmodified_reference():
     # lsqr stops at its default 1e-6 tolerances: the history is reproducible to about that accuracy only (stored-order of P^T A P changes
     # the last bits of its matvecs), measured 1e-7
     assert nit == int(z["sing_nit"]) and rel_hist_err(err, z["sing_err"]) < 2e-6 and abs(conv - float(z["sing_conv"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["poisson2d_20", "poisson3d_8"])
+def test_mlamg_pc_loop_matches_the_unmodified_reference(name):
+    """ns/preconditioner/MLAMG.py:143-212 restated (`rp.mlamg_jacobi`, `rp.mlamg_amg_2_v`) vs what the reference class itself
+    returned from `apply` (tests/golden/make_golden_pc.py: seeded random guess, splu COLAMD coarse solve)"""
+    import os
+    import scipy.sparse.linalg as spla
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "ref_mlamg_pc.npz"))
+    A = sp.csr_matrix((z[f"{name}_A_data"], z[f"{name}_A_indices"], z[f"{name}_A_indptr"]))
+    P = sp.csr_matrix((z[f"{name}_P_data"], z[f"{name}_P_indices"], z[f"{name}_P_indptr"]), shape=tuple(z[f"{name}_P_shape"]))
+    n = A.shape[0]
+    w, rtol, b = float(z[f"{name}_jacobi_weight"]), float(z[f"{name}_amg_rtol"]), z[f"{name}_b"]
+    Dw = sp.diags(1.0 / A.diagonal()) * w
+    lu = spla.splu(sp.csc_matrix(P.T @ A @ P), permc_spec="COLAMD")
+    np.random.seed(0)
+    x0 = np.random.normal(size=n)                                       # MLAMG.py:209
+    x, it = rp.mlamg_amg_2_v(A, P, lu.solve, Dw, b, x0, amg_rtol=rtol)
+    assert np.abs(x - z[f"{name}_x"]).max() <= 1e-12 * np.abs(z[f"{name}_x"]).max() and 1 < it < 500
+    xj = rp.mlamg_jacobi(A, Dw, b, np.random.RandomState(4).randn(n), nu=3)
+    assert np.abs(xj - z[f"{name}_jacobi_x"]).max() <= 1e-13 * np.abs(z[f"{name}_jacobi_x"]).max()

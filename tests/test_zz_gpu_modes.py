@@ -38,3 +38,62 @@ def test_two_level_driver_modes_vs_reference_golden():
     L, PN = csr_from(z, "L"), csr_from(z, "PN")
     got = mg.amg_2_v(L, PN, np.zeros(L.shape[0]), z["xn0"], res_tol=1e-8, singular=True)
     assert abs(got[3] - int(z["sing_nit"])) <= 1 and hist_err0(got[2][:8], z["sing_err"][:8]) < 1e-4
+
+
+class _Mat:
+    def __init__(self, A):
+        self.A = A
+
+    def getValuesCSR(self):
+        return self.A.indptr, self.A.indices, self.A.data
+
+
+class _PC:
+    def __init__(self, A, P):
+        self.m = _Mat(A)
+        self.appctx = {"mlamg_P": P}
+
+    def getType(self):
+        return "python"
+
+    def getOptionsPrefix(self):
+        return ""
+
+    def getOperators(self):
+        return self.m, self.m
+
+
+class _Vec:
+    def __init__(self, a):
+        self.array_r = a
+        self.out = None
+
+    def setArray(self, a):
+        self.out = np.array(a, copy=True)
+
+
+@pytest.mark.parametrize("name", ["poisson2d_20", "poisson3d_8"])
+def test_mlamg_pc_apply_vs_the_reference_class(name):
+    """ns.preconditioner.MLAMG.apply against what the UNMODIFIED reference class returned from `apply` on the same A, P, b and
+    seeded random guess (tests/golden/make_golden_pc.py)"""
+    import scipy.sparse as sp
+    from ns.preconditioner import _petsc_shim
+    from ns.preconditioner.MLAMG import MLAMG
+    z = np.load(os.path.join(GOLDEN, "ref_mlamg_pc.npz"))
+    A = sp.csr_matrix((z[f"{name}_A_data"], z[f"{name}_A_indices"], z[f"{name}_A_indptr"]))
+    P = sp.csr_matrix((z[f"{name}_P_data"], z[f"{name}_P_indices"], z[f"{name}_P_indptr"]), shape=tuple(z[f"{name}_P_shape"]))
+    old = dict(_petsc_shim.OPTIONS)
+    _petsc_shim.OPTIONS.update({"mlamg_jacobi_weight": float(z[f"{name}_jacobi_weight"]), "mlamg_amg_rtol": float(z[f"{name}_amg_rtol"])})
+    try:
+        pc = _PC(A, P)
+        p = MLAMG()
+        p.initialize(pc)
+        X, Y = _Vec(z[f"{name}_b"]), _Vec(None)
+        np.random.seed(0)
+        p.apply(pc, X, Y)
+    finally:
+        _petsc_shim.OPTIONS.clear()
+        _petsc_shim.OPTIONS.update(old)
+    ref = z[f"{name}_x"]
+    assert np.linalg.norm(z[f"{name}_b"] - A @ Y.out) <= float(z[f"{name}_amg_rtol"]) * (1 + 1e-6)
+    assert np.abs(Y.out - ref).max() <= 1e-11 * np.abs(ref).max(), np.abs(Y.out - ref).max()
