@@ -101,3 +101,14 @@ def grid_graph(shape, weights="unit", seed=0, dtype=np.float64, symmetric=True):
     else:
         raise ValueError(weights)
     return sp.csr_matrix((data.astype(dtype), A.indices, A.indptr), shape=A.shape)
+
+
+def load_eval_golden():
+    """tests/golden/ref_evaluation_sequences.npz (written by the unmodified reference's utils/common.py drivers)
+    -> (npz, {grid name: csr})"""
+    z = np.load(os.path.join(GOLDEN, "ref_evaluation_sequences.npz"))
+    grids = {}
+    for name in z["grid_names"]:
+        name = str(name)
+        grids[name] = sp.csr_matrix((z[f"{name}_data"], z[f"{name}_indices"], z[f"{name}_indptr"]))
+    return z, grids

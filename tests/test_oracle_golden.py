@@ -240,3 +240,46 @@ def test_mlamg_pc_loop_matches_the_unmodified_reference(name):
     assert np.abs(x - z[f"{name}_x"]).max() <= 1e-12 * np.abs(z[f"{name}_x"]).max() and 1 < it < 500
     xj = rp.mlamg_jacobi(A, Dw, b, np.random.RandomState(4).randn(n), nu=3)
     assert np.abs(xj - z[f"{name}_jacobi_x"]).max() <= 1e-13 * np.abs(z[f"{name}_jacobi_x"]).max()
+
+
+def _oracle_measure(name, A):
+    A = sp.csr_matrix(A)
+    if name == "abs":
+        return abs(A)
+    if name == "invabs":
+        return sp.csr_matrix((1.0 / np.abs(A.data), A.indices, A.indptr), A.shape)
+    if name == "unit":
+        return sp.csr_matrix((np.ones_like(A.data), A.indices, A.indptr), A.shape)
+    E = pr.evolution_strength_of_connection(A)
+    if name == "evolution":
+        return E + sp.csr_matrix((np.ones_like(A.data), A.indices, A.indptr), A.shape) * 0.1
+    return E + sp.csr_matrix((1.0 / np.abs(A.data), A.indices, A.indptr), A.shape)
+
+
+def test_evaluation_sequences_match_the_unmodified_reference_drivers():
+    """The oracle's statement of utils/common.py:40-111 (seed -> strength measure -> Lloyd 'same' -> SA -> amg_2_v) against the
+    convergence factors the reference's own evaluate_ref_conv / evaluate_dataset returned (tests/golden/make_golden_eval.py);
+    ARPACK's lambda_max as recorded there is injected."""
+    from helpers import load_eval_golden
+    z, grids = load_eval_golden()
+    for measure in ("abs", "evolution", "invabs", "unit", "olson"):
+        for g, (name, A) in enumerate(grids.items()):
+            np.random.seed(0)
+            C = sp.csr_matrix(_oracle_measure(measure, A))
+            Agg, _, _ = rp.lloyd_aggregation(C, ratio=0.2, distance="same")             # rand=None: the global stream (common.py:91)
+            P = rp.smoothed_aggregation_jacobi(A, Agg, omega=(4.0 / 3.0) / float(z[f"ref_conv_{measure}_lam"][g]))
+            np.random.seed(0)
+            x = np.random.randn(A.shape[1])
+            x /= np.linalg.norm(x, 2)
+            conv = rp.amg_2_v(A, P, np.zeros(A.shape[1]), x, res_tol=1e-10, jacobi_weight=2. / 3.)[1]
+            assert abs(conv - float(z[f"ref_conv_{measure}"][g])) < 1e-10, (measure, name)
+    for key, S, alpha in (("dataset_conv_default", "olson", 0.2), ("dataset_conv_invabs", "invabs", 0.3)):
+        for g, (name, A) in enumerate(grids.items()):
+            np.random.seed(0)
+            C = sp.csr_matrix(_oracle_measure(S, A))
+            Agg, _, _ = rp.lloyd_aggregation(C, ratio=alpha, distance="same", rand=0)   # common.py:58
+            P = rp.smoothed_aggregation_jacobi(A, Agg, omega=(4.0 / 3.0) / float(z[f"{key}_lam"][g]))
+            x = np.random.RandomState(0).randn(A.shape[1])
+            x /= np.linalg.norm(x, 2)
+            conv = rp.amg_2_v(A, P, np.zeros(A.shape[1]), x, res_tol=1e-10)[1]
+            assert abs(conv - float(z[key][g])) < 1e-10, (key, name)

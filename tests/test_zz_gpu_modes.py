@@ -97,3 +97,38 @@ def test_mlamg_pc_apply_vs_the_reference_class(name):
     ref = z[f"{name}_x"]
     assert np.linalg.norm(z[f"{name}_b"] - A @ Y.out) <= float(z[f"{name}_amg_rtol"]) * (1 + 1e-6)
     assert np.abs(Y.out - ref).max() <= 1e-11 * np.abs(ref).max(), np.abs(Y.out - ref).max()
+
+
+class _G:
+    def __init__(self, A):
+        self.A = A
+
+
+def test_evaluation_drivers_vs_the_reference_drivers():
+    """utils/common.py evaluate_ref_conv / evaluate_dataset on the device against the convergence factors the UNMODIFIED reference
+    drivers returned (tests/golden/make_golden_eval.py), ARPACK's recorded lambda_max injected.  The two measures built on the
+    Arnoldi estimate of rho are compared on the unstructured grids only: on a structured grid every distance is tied with
+    others to the last bit, and the last bits of rho (dot products summed in another order) may legitimately move them."""
+    import importlib.util
+    from helpers import ROOT, load_eval_golden
+    spec = importlib.util.spec_from_file_location("mlamg_utils_common", os.path.join(ROOT, "ml-amg_b200", "utils", "common.py"))
+    common = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(common)
+    z, grids = load_eval_golden()
+    data = [_G(A) for A in grids.values()]
+
+    def lam_of(key):
+        table = {A.shape[0]: float(v) for A, v in zip(grids.values(), z[key])}
+        return lambda A: table[A.shape[0]]
+
+    for measure in ("abs", "invabs", "unit"):
+        got = common.evaluate_ref_conv(data, common.strength_measure_funcs[measure], alpha=0.2, lam_max=lam_of(f"ref_conv_{measure}_lam"))
+        assert np.allclose(got, z[f"ref_conv_{measure}"], rtol=0, atol=1e-8), (measure, got, z[f"ref_conv_{measure}"])
+    for measure in ("evolution", "olson"):
+        got = common.evaluate_ref_conv(data[1:], common.strength_measure_funcs[measure], alpha=0.2, lam_max=lam_of(f"ref_conv_{measure}_lam"))
+        assert np.allclose(got, z[f"ref_conv_{measure}"][1:], rtol=0, atol=1e-8), (measure, got, z[f"ref_conv_{measure}"][1:])
+    got = common.evaluate_dataset(None, data[1:], alpha=0.2, lam_max=lam_of("dataset_conv_default_lam"))          # 'olson' default
+    assert np.allclose(got, z["dataset_conv_default"][1:], rtol=0, atol=1e-8), (got, z["dataset_conv_default"][1:])
+    got = common.evaluate_dataset(None, data, S=common.strength_measure_funcs["invabs"], alpha=0.3, omega=0.5,
+                                  lam_max=lam_of("dataset_conv_invabs_lam"))
+    assert np.allclose(got, z["dataset_conv_invabs"], rtol=0, atol=1e-8), (got, z["dataset_conv_invabs"])
