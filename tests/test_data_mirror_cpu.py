@@ -10,7 +10,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from helpers import GOLDEN, ROOT
+from helpers import GOLDEN
 
 
 def test_structured_1d_generators_equal_the_reference_bit_for_bit():

@@ -10,7 +10,7 @@ import scipy.sparse as sp
 import torch
 
 import strength_ref as sr
-from oracle import pyamg_restated as pr, reference_path as rp, multilevel as oml
+from oracle import pyamg_restated as pr, multilevel as oml
 
 
 def anisotropic(n, eps):
