@@ -9,8 +9,13 @@ import numpy as np
 import torch
 import torch.nn.functional as nnF
 
-from mlamg import core
+from mlamg import core, MlamgError
 from mlamg import autograd as ag
+
+# The coarse solve is an explicit dense fp64 inverse (k^2 doubles, twice) and the gradient of P^T A P goes through a dense
+# N x k block: fine for the training grids of the reference (N of a few thousand, utils/create_data.py), refused beyond these
+MAX_COARSE = 8192
+MAX_BLOCK_ELEMENTS = 1 << 31
 
 
 def add_lagrange_rowcols(A, device='cpu'):
@@ -46,6 +51,9 @@ def amg_loss(P, A, test_vecs, tot_num_loop=5, no_prerelax=1, no_postrelax=1, dev
     Ad = Ad.with_values(Ad.val.detach())
     Pd = core.DeviceCSR.wrap(P, torch.float32)
     pv = Pd.val                                                       # may carry the autograd link to the caller's P
+    if Pd.shape[1] > MAX_COARSE or Pd.shape[0] * Pd.shape[1] >= MAX_BLOCK_ELEMENTS:
+        raise MlamgError(3, f"amg_loss: {Pd.shape[0]} x {Pd.shape[1]} interpolation is beyond the dense coarse solve of the loss "
+                            f"(coarse size <= {MAX_COARSE}, N * k < 2^31)")
     dev = pv.device
     Pop = ag.SparseOperand(Pd)
     Aop = ag.SparseOperand(Ad)

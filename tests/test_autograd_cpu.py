@@ -229,3 +229,13 @@ def test_descent_on_the_edge_weights_lowers_the_loss(cpu_kernels):
         opt.step()
         hist.append(float(val.detach()))
     assert hist[-1] < 0.8 * hist[0], hist
+
+
+def test_amg_loss_refuses_sizes_beyond_its_dense_coarse_solve(cpu_kernels):
+    import mlamg
+    import ns.model.loss as loss
+    n, k = 20000, loss.MAX_COARSE + 1
+    P = sp.csr_matrix((np.ones(n, dtype=np.float32), (np.arange(n), np.arange(n) % k)), shape=(n, k))
+    A = sp.eye(n, format="csr", dtype=np.float32)
+    with pytest.raises(mlamg.MlamgError):
+        loss.amg_loss(_dev(P, torch.float32), _dev(A, torch.float32), 2)
