@@ -23,6 +23,7 @@ import torch
 import ns.lib.multigrid
 import ns.lib.sparse_tensor
 import ns.model.agg_interp as agg_interp
+from ns.lib.profiler import Profiler
 from mlamg import core
 
 
@@ -65,7 +66,9 @@ def evaluate_dataset(weights, dataset, model=None, alpha=0.3, omega=2. / 3., num
     for i, st in enumerate(states):
         try:
             with torch.no_grad():
-                P_T = model.forward(st.device_A if getattr(model, 'accepts_device_matrix', False) else st.A, alpha)[1]
+                P_T = None
+                with Profiler('model inferencing'):                 # :97 (wall clock, device time and kernel count of the tail)
+                    P_T = model.forward(st.device_A if getattr(model, 'accepts_device_matrix', False) else st.A, alpha)[1]
             P = ns.lib.sparse_tensor.to_scipy(P_T)
         except Exception:                                           # noqa: BLE001  (:99-102: score the grid as 1.0)
             print(f'Could not evaluate grid {i}: {traceback.format_exc()}')

@@ -103,3 +103,27 @@ def test_legacy_permutation_head_is_numpys():
         out = np.empty(k, dtype=np.int32)
         check(lib.mlamg_legacy_permutation_head(seed, n, k, out.ctypes.data_as(ctypes.c_void_p)))
         assert np.array_equal(out, np.random.RandomState(seed).permutation(n)[:k]), (seed, n)
+
+
+def test_profiler_mirror_nests_and_prints_like_the_reference(capsys):
+    """ns/lib/profiler.py:4-52: disabled = silent no-op; enabled = hierarchical print when the root section closes;
+    exceptions inside a section are swallowed, as in the reference (__exit__ returns True)"""
+    from ns.lib.profiler import Profiler
+    with Profiler("off"):
+        pass
+    assert capsys.readouterr().out == ""
+    Profiler.enabled = True
+    try:
+        with Profiler("root"):
+            with Profiler("child a"):
+                pass
+            with Profiler("child b"):
+                with Profiler("grandchild"):
+                    raise ValueError("swallowed")
+        lines = capsys.readouterr().out.splitlines()
+    finally:
+        Profiler.enabled = False
+        Profiler.current = None
+    assert [ln.strip().split("]")[0] + "]" for ln in lines] == ["[root]", "[child a]", "[child b]", "[grandchild]"]
+    assert [len(ln) - len(ln.lstrip()) for ln in lines] == [0, 2, 2, 4]
+    assert all(ln.split("] ")[1].split("s")[0].replace(".", "").isdigit() for ln in lines)
