@@ -181,6 +181,9 @@ int oracle_modified_bf_##SUF(int n, long long nnz, const long long *row,        
         }                                                                                 \
         passes++;                                                                         \
         if (finished) break;                                                              \
+        /* float32 distances relaxed with float64 weights can be rounded UP on the store and */ \
+        /* then "improve" for ever (the reference's loop never ends there): give up loudly   */ \
+        if (passes > 4 * n + 16) return -passes;                                          \
     }                                                                                     \
     return passes;                                                                        \
 }

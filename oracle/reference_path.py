@@ -73,9 +73,12 @@ def modified_bellman_ford(S_coo, centers):
     if suf == "f64":
         w = w.astype(np.float64)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    getattr(pr.lib(), f"oracle_modified_bf_{suf}")(
+    passes = getattr(pr.lib(), f"oracle_modified_bf_{suf}")(
         ctypes.c_int(n), ctypes.c_longlong(len(w)), p(row), p(col), p(w),
         ctypes.c_int(len(centers)), p(centers), p(dist), p(near))
+    if passes < 0:
+        raise RuntimeError("modified_bellman_ford: no fixed point after %d passes (float32 distances with float64 weights can be "
+                           "rounded up on the store and relax for ever; the reference's callers pass float32 weights)" % -passes)
     return dist, near
 
 
