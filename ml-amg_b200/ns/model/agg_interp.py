@@ -18,6 +18,17 @@ import mlamg
 from mlamg import core
 
 
+def topk_vec(x, k):
+    """:14-22  indicator vector of the k largest scores (1.0 at the aggregate centres), on x's device"""
+    if len(x.shape) != 1:
+        x = x.squeeze()
+    assert len(x.shape) == 1
+    top_k = torch.argsort(x, descending=True)[:k]
+    top_k_vec = torch.zeros(x.shape, device=x.device)
+    top_k_vec[top_k] = 1.0
+    return top_k_vec
+
+
 def _pattern(A):
     Ad = core.DeviceCSR.wrap(A)
     return Ad

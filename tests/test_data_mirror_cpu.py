@@ -106,3 +106,10 @@ def test_lagrange_helpers_and_their_reference_shapes():
     assert torch.equal(B, torch.tensor([[2.0, 0.0, 1.0], [-1.0, 3.0, 1.0], [1.0, 1.0, 0.0]]))
     v = loss.add_lagrange_vec(torch.ones(2, 3))
     assert v.shape == (3, 3) and torch.equal(v[-1], torch.zeros(3))
+
+
+def test_topk_vec():
+    import ns.model.agg_interp as ai
+    x = torch.tensor([[0.3], [0.9], [0.1], [0.5]])
+    v = ai.topk_vec(x, 2)
+    assert torch.equal(v, torch.tensor([0.0, 1.0, 0.0, 1.0])) and torch.equal(torch.where(v == 1)[0], torch.tensor([1, 3]))
