@@ -2,7 +2,7 @@
 which aggregation arguments, which start vector, which solver arguments) against the convergence factors the UNMODIFIED
 reference drivers returned (tests/golden/make_golden_eval.py).  The device modules the drivers call are replaced — in this
 test only — by the oracle's statements of the same functions, so what is exercised is the driver logic itself; the device
-modules are held to the same numbers on the GPU (tests/test_zz_gpu_modes.py)."""
+modules are held to the same numbers on the GPU (tests/test_zzz_gpu_modes.py)."""
 import importlib.util
 import os
 
