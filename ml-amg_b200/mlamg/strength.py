@@ -120,17 +120,18 @@ def approximate_spectral_radius(M, tol=0.01, maxiter=15, restart=5, return_trace
         nvecs = ev.shape[0]
         max_index = int(np.abs(ev).argmax())
         error = H[nvecs, nvecs - 1] * evect[-1, max_index]
-        y = evect[:, max_index]
-        if np.iscomplexobj(y) and np.any(y.imag != 0):
-            raise NotImplementedError("complex Ritz vector (non-symmetric operator): not supported on the device path")
-        y = np.real(y)
-        v0 = torch.zeros(n, dtype=dtype, device=dev)
-        for c, v in zip(y, V[:-1]):
-            core.axpby(float(c), v, 1.0, v0)
         rho = float(np.abs(ev[max_index]))
         trace.append((rho, float(np.abs(error))))
         if (np.abs(error) / np.abs(ev[max_index]) < tol) or breakdown_flag:
             break
+        # restart from the Ritz vector of the dominant eigenvalue (pyamg forms it before the test and drops it on exit)
+        y = evect[:, max_index]
+        if np.iscomplexobj(y) and np.any(y.imag != 0):
+            raise NotImplementedError("restart from a complex Ritz vector (non-symmetric operator) is not supported on the device path")
+        y = np.real(y)
+        v0 = torch.zeros(n, dtype=dtype, device=dev)
+        for c, v in zip(y, V[:-1]):
+            core.axpby(float(c), v, 1.0, v0)
     return (rho, trace) if return_trace else rho
 
 
