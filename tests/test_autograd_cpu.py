@@ -145,7 +145,7 @@ def test_amg_loss_value_and_gradient_vs_reference(cpu_kernels, name):
     assert abs(float(val.detach()) - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
     val.backward()
     g = Pd.val.grad.numpy()
-    print(f"{name}: loss rel err {abs(float(val) - float(z['loss'])) / float(z['loss']):.1e}, gradient max err "
+    print(f"{name}: loss rel err {abs(float(val.detach()) - float(z['loss'])) / float(z['loss']):.1e}, gradient max err "
           f"{np.abs(g - z['grad']).max():.2e} (tolerance {grad_tolerance(z):.2e}, |grad|max {np.abs(z['grad']).max():.2e})")
     assert np.abs(g - z["grad"]).max() <= grad_tolerance(z), (np.abs(g - z["grad"]).max(), grad_tolerance(z))
 
