@@ -1,14 +1,15 @@
-"""Mirror of the reference's nested section profiler (/root/reference/ns/lib/profiler.py:4-52; switched on by
-utils/train_dataset.py:52, wraps the model inference at :97) with the device's view added: besides the wall-clock time
-of a section, the time between two CUDA events recorded on the current stream at its entry and exit, and the number
-of libmlamg_b200 kernels launched inside it.  Same usage and output shape:
+"""Section timer with the device's view: the B200 counterpart of the reference's nested wall-clock profiler
+(/root/reference/ns/lib/profiler.py:4-52; switched on by utils/train_dataset.py:52, wraps the model inference at :97).
 
     Profiler.enabled = True
     with Profiler('label'):
-        ...                      # nested `with` blocks print hierarchically when the root section closes
+        ...                      # nested sections are reported as an indented tree when the outermost one closes
 
-As in the reference, `__exit__` returns True: an exception raised inside a section is swallowed (its callers rely on the
-surrounding try / except of the fitness loop, utils/train_dataset.py:95-103).
+Every section reports three things: host wall-clock seconds (what the reference prints), the time between two CUDA
+events recorded on the current stream at its entry and exit (host launch overhead excluded), and how many kernels of
+libmlamg_b200.so were launched inside it.  Output lines keep the reference's shape `[label] 0.01234s`, the device part
+is appended in parentheses.  Like the reference's, a section swallows an exception raised inside it (its callers sit in
+the try / except of the fitness loop, utils/train_dataset.py:95-103), and a disabled profiler is a silent no-op.
 """
 import time
 
@@ -17,54 +18,74 @@ import torch
 import mlamg
 
 
+class _Mark:
+    """host clock, an optional CUDA event on the current stream and the library's launch counter, read together"""
+    __slots__ = ("wall", "event", "launches")
+
+    def __init__(self):
+        self.event = None
+        if torch.cuda.is_available():
+            self.event = torch.cuda.Event(enable_timing=True)
+            self.event.record()
+        self.launches = mlamg.launch_count()
+        self.wall = time.time()
+
+
 class Profiler:
-    enabled = False
-    current = None
+    enabled = False          # class-level switch, as in the reference
+    current = None           # innermost open section
     tab_width = 2
 
     def __init__(self, section_name):
         self.section_name = section_name
         self.children = []
+        self.parent = None
+        self._begin = self._end = None
 
+    # ---- context manager ------------------------------------------------------------------------
     def __enter__(self):
-        if not Profiler.enabled:
-            return
-        self.parent = Profiler.current
-        if self.parent is not None:
-            self.parent.children.append(self)
-        Profiler.current = self
-        self._events = None
-        if torch.cuda.is_available():
-            self._events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self._events[0].record()
-        self._launches = mlamg.launch_count()
-        self.start_time = time.time()
-        return self
+        if Profiler.enabled:
+            self.parent, Profiler.current = Profiler.current, self
+            if self.parent is not None:
+                self.parent.children.append(self)
+            self._begin = _Mark()
+            return self
 
-    def _resolve(self):
-        self.device_time = None
-        if self._events is not None:
-            self.device_time = self._events[0].elapsed_time(self._events[1]) * 1e-3
-        for child in self.children:
-            child._resolve()
-
-    def print_recursive(self, level):
-        dev = '' if self.device_time is None else f' (device {self.device_time:.5f}s, {self.kernel_launches} kernels)'
-        print(((level * Profiler.tab_width) * ' ') + f'[{self.section_name}] {self.running_time:.5f}s' + dev)
-        for child in self.children:
-            child.print_recursive(level + 1)
-
-    def __exit__(self, type, value, tb):
-        if not Profiler.enabled:
-            return True
-        if self._events is not None:
-            self._events[1].record()
-        self.running_time = time.time() - self.start_time
-        self.kernel_launches = mlamg.launch_count() - self._launches
-        if self.parent is None:
-            if self._events is not None:
-                torch.cuda.synchronize()
-            self._resolve()
-            self.print_recursive(0)
-        Profiler.current = self.parent
+    def __exit__(self, exc_type, exc, tb):
+        if Profiler.enabled and self._begin is not None:
+            self._end = _Mark()
+            Profiler.current = self.parent
+            if self.parent is None:
+                if self._end.event is not None:
+                    self._end.event.synchronize()            # the last event of the tree: every other one is complete
+                for depth, node in self._walk(0):
+                    print(' ' * (depth * Profiler.tab_width) + node._line())
         return True
+
+    # ---- results --------------------------------------------------------------------------------
+    @property
+    def running_time(self):
+        return self._end.wall - self._begin.wall
+
+    @property
+    def device_time(self):
+        if self._begin.event is None or self._end.event is None:
+            return None
+        return self._begin.event.elapsed_time(self._end.event) * 1e-3
+
+    @property
+    def kernel_launches(self):
+        return self._end.launches - self._begin.launches
+
+    def _walk(self, depth):
+        yield depth, self
+        for child in self.children:
+            if child._end is not None:
+                yield from child._walk(depth + 1)
+
+    def _line(self):
+        text = f'[{self.section_name}] {self.running_time:.5f}s'
+        dev = self.device_time
+        if dev is not None:
+            text += f' (device {dev:.5f}s, {self.kernel_launches} kernels)'
+        return text
